@@ -1,0 +1,190 @@
+"""The DBS reallocator: re-split a fixed global batch ``B`` across ranks in proportion to
+each rank's measured throughput.
+
+Algorithm (reference ``dbs.py:458-476``): with previous shares ``p_i``
+and pure-compute times ``t_i`` of the last epoch, rank *i* processed ``p_i / t_i`` share per
+second, so its new share is ``r_i = (p_i/t_i) / Σ_j (p_j/t_j)``.  The integer local batches
+are ``round(r_i · B)`` under some rounding rule, and the shares handed to the data
+partitioner / gradient weights are ``b_i / Σ b``.
+
+Rounding rules
+  * ``largest_remainder`` (default): floor, then hand the ``B − Σfloor`` leftover samples to
+    the largest fractional parts.  Σ b_i == B always (fixes SURVEY D5), every rank keeps at
+    least ``min_local`` samples so a slow rank is never absorbing (fixes D7), and batches can be
+    constrained to a multiple of ``quantum`` (CUDA-graph / tile friendly).
+  * ``reference``: the reference's rule — only fractional parts that are both among the
+    ``B − Σfloor`` largest *and* ≥ 0.5 are rounded up (``dbs.py:469-473``), so Σ b_i may be
+    ``B−1`` or ``B−2``.  Kept for bit-parity experiments.
+"""
+from __future__ import annotations
+
+from typing import Sequence, Tuple
+
+import numpy as np
+
+
+def throughput_shares(nodes_time: Sequence[float], partition: Sequence[float]) -> np.ndarray:
+    t = np.maximum(np.asarray(nodes_time, dtype=np.float64), 1e-12)
+    p = np.asarray(partition, dtype=np.float64)
+    rate = p / t
+    s = rate.sum()
+    if not np.isfinite(s) or s <= 0:
+        return np.full(len(p), 1.0 / len(p))
+    return rate / s
+
+
+def _largest_remainder(target: np.ndarray, total: int) -> np.ndarray:
+    """Integers ≥ 0 summing to ``total`` closest (in the Hamilton sense) to ``target``."""
+    fl = np.floor(target + 1e-12).astype(np.int64)
+    left = int(total - fl.sum())
+    if left > 0:
+        frac = target - fl
+        # stable: ties go to the lower rank index so every rank computes the same answer
+        order = np.lexsort((np.arange(len(frac)), -frac))
+        fl[order[:left]] += 1
+    elif left < 0:                      # only reachable through min/quantum clamping
+        frac = target - fl
+        order = np.lexsort((np.arange(len(frac)), frac))
+        k = 0
+        while left < 0:
+            i = order[k % len(order)]
+            if fl[i] > 0:
+                fl[i] -= 1
+                left += 1
+            k += 1
+    return fl
+
+
+def integer_split(shares: Sequence[float], batch_size: int, min_local: int = 1,
+                  quantum: int = 1) -> np.ndarray:
+    """Split ``batch_size`` into per-rank integers ∝ ``shares`` with Σ == batch_size,
+    each ≥ ``min_local`` (when feasible) and a multiple of ``quantum`` (when feasible)."""
+    shares = np.asarray(shares, dtype=np.float64)
+    n = len(shares)
+    shares = shares / shares.sum()
+    q = max(1, int(quantum))
+    if batch_size % q != 0 or batch_size // q < n:
+        q = 1
+    units = batch_size // q
+    min_units = max(0, -(-int(min_local) // q))          # ceil(min_local / q)
+    if min_units * n > units:
+        min_units = units // n
+    # water-filling: pin ranks that fall under the minimum, re-split the rest proportionally
+    fixed = np.zeros(n, dtype=bool)
+    out = np.zeros(n, dtype=np.float64)
+    for _ in range(n + 1):
+        free_units = units - min_units * int(fixed.sum())
+        free_share = shares[~fixed].sum()
+        if free_share <= 0:
+            out[~fixed] = free_units / max(1, int((~fixed).sum()))
+        else:
+            out[~fixed] = shares[~fixed] / free_share * free_units
+        out[fixed] = min_units
+        newly = (~fixed) & (out < min_units - 1e-9)
+        if not newly.any():
+            break
+        fixed |= newly
+    ints = np.empty(n, dtype=np.int64)
+    ints[fixed] = min_units
+    if (~fixed).any():
+        free_total = units - min_units * int(fixed.sum())
+        sub = _largest_remainder(out[~fixed], free_total)
+        # rounding may still push a free rank below the minimum by one unit; repair
+        ints[~fixed] = sub
+        low = (~fixed) & (ints < min_units)
+        while low.any():
+            i = int(np.argmax(low))
+            j = int(np.argmax(np.where(fixed | low, -1, ints)))
+            ints[i] += 1
+            ints[j] -= 1
+            low = (~fixed) & (ints < min_units)
+    return ints * q
+
+
+def reference_split(shares: Sequence[float], batch_size: int) -> np.ndarray:
+    """Bit-compatible with the reference's rounding (``dbs.py:465-473``), including its
+    sample loss and the ``argsort()[-0:]`` quirk (D6)."""
+    shares = np.asarray(shares, dtype=np.float64)
+    norm_batch = shares * batch_size / shares.sum()
+    fl = np.floor(norm_batch)
+    ceil_counter = int(batch_size - int(fl.sum()))
+    frac = norm_batch - fl
+    idx_ceil = frac.argsort()[-ceil_counter:]           # ceil_counter == 0 ⇒ all indices (D6)
+    idx_round = np.argwhere(frac >= 0.5).reshape(-1)
+    idx = np.intersect1d(idx_ceil, idx_round)
+    fl[idx] += 1
+    return fl.astype(np.int64)
+
+
+def get_size(nodes_time: Sequence[float], partition_size: Sequence[float], batch_size: int,
+             rounding: str = "largest_remainder", min_local: int = 1, quantum: int = 1
+             ) -> Tuple[np.ndarray, np.ndarray]:
+    """New ``(fractions, local_batches)`` from last epoch's compute times and shares.
+
+    ``fractions = local_batches / Σ local_batches`` — exactly what the reference returns
+    (``dbs.py:474``) and what feeds the data partitioner and the allreduce weights."""
+    r = throughput_shares(nodes_time, partition_size)
+    if rounding == "reference":
+        ints = reference_split(r, batch_size)
+    else:
+        ints = integer_split(r, batch_size, min_local=min_local, quantum=quantum)
+    tot = ints.sum()
+    frac = ints / tot if tot > 0 else np.full(len(ints), 1.0 / len(ints))
+    return frac, ints
+
+
+class Reallocator:
+    """Stateful wrapper used by the trainer: owns the current split, applies an optional EMA
+    to the time signal, and only moves when DBS is enabled (``-dbs``; static DP otherwise,
+    reference ``dbs.py:379,388``)."""
+
+    def __init__(self, world_size: int, batch_size: int, enabled: bool = True,
+                 rounding: str = "largest_remainder", min_local: int = 1, quantum: int = 1,
+                 ema: float = 0.0):
+        self.world_size = world_size
+        self.batch_size = batch_size
+        self.enabled = enabled
+        self.rounding = rounding
+        self.min_local = min_local
+        self.quantum = quantum
+        self.ema = ema
+        self.nodes_time = np.ones(world_size, dtype=np.float64)          # dbs.py:378
+        self.fractions = np.full(world_size, 1.0 / world_size)           # dbs.py:379
+        self.local_batches = self._initial_split()
+        self.history = []
+
+    def _initial_split(self) -> np.ndarray:
+        if self.rounding == "reference":
+            return np.full(self.world_size, int(self.batch_size * (1.0 / self.world_size)), dtype=np.int64)
+        return integer_split(np.ones(self.world_size), self.batch_size, self.min_local, self.quantum)
+
+    def observe(self, nodes_time: Sequence[float]) -> None:
+        t = np.asarray(nodes_time, dtype=np.float64)
+        if self.ema > 0 and len(self.history) > 0:
+            t = self.ema * self.nodes_time + (1.0 - self.ema) * t
+        self.nodes_time = t
+
+    def step(self) -> Tuple[np.ndarray, np.ndarray]:
+        """Called at the start of every epoch (or every N steps).  Returns the split to use."""
+        if self.enabled:
+            self.fractions, self.local_batches = get_size(
+                self.nodes_time, self.fractions, self.batch_size, self.rounding,
+                self.min_local, self.quantum)
+        self.history.append(self.local_batches.copy())
+        return self.fractions, self.local_batches
+
+    def weights(self, uniform: bool = False) -> np.ndarray:
+        """Gradient-allreduce weights ``w_r = b_r / Σ b`` (reference ``dbs.py:293``), or the
+        ``-de`` ablation ``1/n``."""
+        if uniform:
+            return np.full(self.world_size, 1.0 / self.world_size)
+        return self.fractions / self.fractions.sum()
+
+    def state_dict(self):
+        return {"nodes_time": self.nodes_time.tolist(), "fractions": self.fractions.tolist(),
+                "local_batches": self.local_batches.tolist()}
+
+    def load_state_dict(self, sd):
+        self.nodes_time = np.asarray(sd["nodes_time"], dtype=np.float64)
+        self.fractions = np.asarray(sd["fractions"], dtype=np.float64)
+        self.local_batches = np.asarray(sd["local_batches"], dtype=np.int64)

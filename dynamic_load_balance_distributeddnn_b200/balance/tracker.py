@@ -1,0 +1,73 @@
+"""Per-rank iteration-time tracker.
+
+The reference measures ``compute = epoch wall − Σ time blocked in req.wait()`` with
+``time.time()`` and no device sync (``dbs.py:222-250``, ``:297-299``), which on a GPU
+mis-attributes asynchronous backward time to *sync* (SURVEY D10).  This tracker keeps
+the same two quantities — compute seconds (the DBS feedback signal) and sync/straggler-wait
+seconds — but sources them from the device:
+
+* CUDA: a pair of CUDA events brackets every step's compute region on the compute stream;
+  the straggler wait is measured *inside* the allreduce kernel's entry barrier with
+  ``%globaltimer`` and accumulated in a device counter (``parallel/symm.py``), so no host
+  sync is needed per step; events are resolved lazily at epoch end.
+* CPU/gloo: ``time.perf_counter`` around the compute region and around the collective.
+
+Injected straggle (host sleep or device burner placed between backward and the allreduce,
+exactly where the reference puts ``fault_tolerance_wait``, ``dbs.py:236``) counts as compute.
+"""
+from __future__ import annotations
+
+import time
+from typing import List, Optional
+
+import torch
+
+
+class TimeTracker:
+    def __init__(self, device: torch.device):
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        self.reset()
+
+    def reset(self) -> None:
+        self._compute_s = 0.0
+        self._sync_s = 0.0
+        self._pairs: List = []
+        self._t0: Optional[float] = None
+        self._wall0 = time.perf_counter()
+        self.steps = 0
+
+    # ---- compute region -------------------------------------------------------------
+    def start_compute(self) -> None:
+        if self.cuda:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._e0 = e
+        else:
+            self._t0 = time.perf_counter()
+
+    def stop_compute(self) -> None:
+        if self.cuda:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._pairs.append((self._e0, e))
+        else:
+            self._compute_s += time.perf_counter() - self._t0
+        self.steps += 1
+
+    def add_compute(self, seconds: float) -> None:
+        self._compute_s += seconds
+
+    def add_sync(self, seconds: float) -> None:
+        self._sync_s += seconds
+
+    # ---- epoch summary -------------------------------------------------------------
+    def finish(self):
+        """→ (compute_seconds, sync_seconds, wall_seconds) for the epoch."""
+        if self.cuda:
+            torch.cuda.synchronize(self.device)
+            for a, b in self._pairs:
+                self._compute_s += a.elapsed_time(b) * 1e-3
+            self._pairs.clear()
+        wall = time.perf_counter() - self._wall0
+        return self._compute_s, self._sync_s, wall

@@ -1,0 +1,365 @@
+// GroupNorm (+ReLU, +residual) forward / backward for NHWC activations, bf16 or fp32.
+//
+// Replaces the reference's per-layer ATen native_group_norm + relu (+ add) launches
+// (reference Net/Densenet.py:18-19,31; Net/Resnet.py:50-54).
+//
+// Both directions share one structure:
+//   (1) nc_reduce2 : per-(sample, channel) reduction of two quantities over H*W
+//         fwd: (sum x, sum x^2)          bwd: (sum dz, sum dz*x),  dz = dy * [y > 0]
+//       -> a tiny fp32 table [N][C][2]; group statistics for ANY grouping of channels are sums
+//       of table entries, so DenseNet's growing concat buffer never has to be re-read for stats.
+//   (2) an apply pass with per-(sample, channel) affine coefficients precomputed in shared memory
+//         fwd: y  = act(a[c]*x + b[c] (+ residual))
+//         bwd: dx = k1[c]*dz + k2[c]*x + k3[c]   (optionally accumulated into dx)
+// Rows are pixels (n, h, w); `ld*` are row strides in elements so channel slices of a wider
+// buffer can be read / written in place.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// ---------------------------------------------------------------------------------------------
+// (1) per-(n, c) reduction
+// MODE 0: q0 = x, q1 = x*x                    (inputs: x)
+// MODE 1: q0 = dz, q1 = dz*x, dz = dy*(y>0)   (inputs: x, dy, y)  [relu]
+// MODE 2: q0 = dy, q1 = dy*x                  (inputs: x, dy)     [no relu]
+template <typename T, int V, int MODE>
+__global__ void __launch_bounds__(kThreads)
+nc_reduce2_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy,
+                  const T* __restrict__ y, int64_t ldy, float* __restrict__ table,
+                  int HW, int C, int rows_per_block) {
+  extern __shared__ float smem[];            // [2*C]
+  const int n = blockIdx.y;
+  const int lanes = C / V;                   // channel-vector lanes
+  const int row_lanes = max(1, kThreads / lanes);
+  for (int i = threadIdx.x; i < 2 * C; i += kThreads) smem[i] = 0.f;
+  __syncthreads();
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(HW, r0 + rows_per_block);
+  for (int lane0 = 0; lane0 < lanes; lane0 += kThreads) {      // loop only when C/V > 256
+    const int lane = lane0 + (threadIdx.x % min(lanes, kThreads));
+    const int rl = threadIdx.x / min(lanes, kThreads);
+    if (lane < lanes && rl < row_lanes) {
+      float a0[V], a1[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) { a0[i] = 0.f; a1[i] = 0.f; }
+      const int c = lane * V;
+      for (int r = r0 + rl; r < r1; r += row_lanes) {
+        const int64_t row = (int64_t)n * HW + r;
+        float xv[V];
+        load_vec<T, V>(x + row * ldx + c, xv);
+        if constexpr (MODE == 0) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) { a0[i] += xv[i]; a1[i] += xv[i] * xv[i]; }
+        } else {
+          float gv[V];
+          load_vec<T, V>(dy + row * lddy + c, gv);
+          if constexpr (MODE == 1) {
+            float yv[V];
+            load_vec<T, V>(y + row * ldy + c, yv);
+#pragma unroll
+            for (int i = 0; i < V; ++i) gv[i] = yv[i] > 0.f ? gv[i] : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < V; ++i) { a0[i] += gv[i]; a1[i] += gv[i] * xv[i]; }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        atomicAdd(&smem[2 * (c + i)], a0[i]);
+        atomicAdd(&smem[2 * (c + i) + 1], a1[i]);
+      }
+    }
+  }
+  __syncthreads();
+  float* dst = table + (int64_t)n * C * 2;
+  for (int i = threadIdx.x; i < 2 * C; i += kThreads) atomicAdd(&dst[i], smem[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// group statistics from the table:  mean/rstd [N][G]
+__global__ void gn_finalize_kernel(const float* __restrict__ table, float* __restrict__ mean,
+                                   float* __restrict__ rstd, int N, int C, int G, int HW, float eps) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * G) return;
+  const int n = idx / G, g = idx % G, cpg = C / G;
+  const float* t = table + ((int64_t)n * C + (int64_t)g * cpg) * 2;
+  float s = 0.f, ss = 0.f;
+  for (int i = 0; i < cpg; ++i) { s += t[2 * i]; ss += t[2 * i + 1]; }
+  const float m = 1.f / ((float)cpg * (float)HW);
+  const float mu = s * m;
+  const float var = fmaxf(ss * m - mu * mu, 0.f);
+  mean[idx] = mu;
+  rstd[idx] = rsqrtf(var + eps);
+}
+
+// ---------------------------------------------------------------------------------------------
+// (2a) forward apply: y = act(gamma*(x-mu)*rstd + beta (+ res))
+template <typename T, int V, bool RELU, bool RES>
+__global__ void __launch_bounds__(kThreads)
+gn_fwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ res, int64_t ldr,
+                    T* __restrict__ y, int64_t ldy, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, int HW, int C, int G, int rows_per_block) {
+  extern __shared__ float smem[];            // a[C], b[C]
+  float* sa = smem;
+  float* sb = smem + C;
+  const int n = blockIdx.y, cpg = C / G;
+  for (int c = threadIdx.x; c < C; c += kThreads) {
+    const int g = c / cpg;
+    const float r = rstd[n * G + g], mu = mean[n * G + g];
+    const float a = gamma[c] * r;
+    sa[c] = a;
+    sb[c] = beta[c] - mu * a;
+  }
+  __syncthreads();
+  const int lanes = C / V;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(HW, r0 + rows_per_block);
+  const int64_t total = (int64_t)(r1 - r0) * lanes;
+  for (int64_t i = threadIdx.x; i < total; i += kThreads) {
+    const int r = r0 + (int)(i / lanes);
+    const int c = (int)(i % lanes) * V;
+    const int64_t row = (int64_t)n * HW + r;
+    float xv[V], out[V];
+    load_vec<T, V>(x + row * ldx + c, xv);
+#pragma unroll
+    for (int k = 0; k < V; ++k) out[k] = fmaf(sa[c + k], xv[k], sb[c + k]);
+    if constexpr (RES) {
+      float rv[V];
+      load_vec<T, V>(res + row * ldr + c, rv);
+#pragma unroll
+      for (int k = 0; k < V; ++k) out[k] += rv[k];
+    }
+    if constexpr (RELU) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) out[k] = fmaxf(out[k], 0.f);
+    }
+    store_vec<T, V>(y + row * ldy + c, out);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (2b) backward apply: dx (+)= k1[c]*dz + k2[c]*x + k3[c];  optional dres = dz
+template <typename T, int V, bool RELU, bool RES, bool ACC>
+__global__ void __launch_bounds__(kThreads)
+gn_bwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy,
+                    const T* __restrict__ y, int64_t ldy, T* __restrict__ dx, int64_t lddx,
+                    T* __restrict__ dres, int64_t lddr, const float* __restrict__ gamma,
+                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const float* __restrict__ table, int HW, int C, int G, int rows_per_block) {
+  extern __shared__ float smem[];            // k1[C], k2[C], k3[C], s1[G], s2[G]
+  float* k1 = smem;
+  float* k2 = smem + C;
+  float* k3 = smem + 2 * C;
+  float* s1 = smem + 3 * C;
+  float* s2 = s1 + G;
+  const int n = blockIdx.y, cpg = C / G;
+  const float* t = table + (int64_t)n * C * 2;
+  for (int g = threadIdx.x; g < G; g += kThreads) {
+    const float mu = mean[n * G + g], r = rstd[n * G + g];
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < cpg; ++i) {
+      const int c = g * cpg + i;
+      const float A = t[2 * c], B = t[2 * c + 1];
+      a += gamma[c] * A;
+      b += gamma[c] * r * (B - mu * A);
+    }
+    s1[g] = a;
+    s2[g] = b;
+  }
+  __syncthreads();
+  const float inv_m = 1.f / ((float)cpg * (float)HW);
+  for (int c = threadIdx.x; c < C; c += kThreads) {
+    const int g = c / cpg;
+    const float mu = mean[n * G + g], r = rstd[n * G + g];
+    k1[c] = gamma[c] * r;
+    const float q = r * r * s2[g] * inv_m;
+    k2[c] = -q;
+    k3[c] = -r * s1[g] * inv_m + q * mu;
+  }
+  __syncthreads();
+  const int lanes = C / V;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(HW, r0 + rows_per_block);
+  const int64_t total = (int64_t)(r1 - r0) * lanes;
+  for (int64_t i = threadIdx.x; i < total; i += kThreads) {
+    const int r = r0 + (int)(i / lanes);
+    const int c = (int)(i % lanes) * V;
+    const int64_t row = (int64_t)n * HW + r;
+    float xv[V], gv[V], out[V];
+    load_vec<T, V>(x + row * ldx + c, xv);
+    load_vec<T, V>(dy + row * lddy + c, gv);
+    if constexpr (RELU) {
+      float yv[V];
+      load_vec<T, V>(y + row * ldy + c, yv);
+#pragma unroll
+      for (int k = 0; k < V; ++k) gv[k] = yv[k] > 0.f ? gv[k] : 0.f;
+    }
+    if constexpr (RES) store_vec<T, V>(dres + row * lddr + c, gv);
+#pragma unroll
+    for (int k = 0; k < V; ++k) out[k] = fmaf(k1[c + k], gv[k], fmaf(k2[c + k], xv[k], k3[c + k]));
+    if constexpr (ACC) {
+      float old[V];
+      load_vec<T, V>(dx + row * lddx + c, old);
+#pragma unroll
+      for (int k = 0; k < V; ++k) out[k] += old[k];
+    }
+    store_vec<T, V>(dx + row * lddx + c, out);
+  }
+}
+
+// dgamma[c] = sum_n rstd*(B - mu*A), dbeta[c] = sum_n A
+__global__ void gn_param_grad_kernel(const float* __restrict__ table, const float* __restrict__ mean,
+                                     const float* __restrict__ rstd, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, int N, int C, int G) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int g = c / (C / G);
+  float dg = 0.f, db = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float A = table[((int64_t)n * C + c) * 2], B = table[((int64_t)n * C + c) * 2 + 1];
+    dg += rstd[n * G + g] * (B - mean[n * G + g] * A);
+    db += A;
+  }
+  dgamma[c] = dg;
+  dbeta[c] = db;
+}
+
+inline void grid_for(int N, int HW, int C, int V, dim3& grid, int& rows_per_block) {
+  const int lanes = C / V;
+  const int row_lanes = lanes >= kThreads ? 1 : kThreads / lanes;
+  int chunks = (296 * 2 + N - 1) / N;                     // aim for >= ~4 blocks per SM overall
+  int max_chunks = (HW + row_lanes * 4 - 1) / (row_lanes * 4);
+  if (max_chunks < 1) max_chunks = 1;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  rows_per_block = (HW + chunks - 1) / chunks;
+  chunks = (HW + rows_per_block - 1) / rows_per_block;
+  grid = dim3(chunks, N, 1);
+}
+
+template <typename T, int V>
+int reduce2_launch(int mode, const void* x, int64_t ldx, const void* dy, int64_t lddy, const void* y,
+                   int64_t ldy, float* table, int N, int HW, int C, cudaStream_t st) {
+  dim3 grid; int rpb;
+  grid_for(N, HW, C, V, grid, rpb);
+  const size_t sm = 2 * C * sizeof(float);
+  const T* X = (const T*)x; const T* DY = (const T*)dy; const T* Y = (const T*)y;
+  if (mode == 0) nc_reduce2_kernel<T, V, 0><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, HW, C, rpb);
+  else if (mode == 1) nc_reduce2_kernel<T, V, 1><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, HW, C, rpb);
+  else nc_reduce2_kernel<T, V, 2><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, HW, C, rpb);
+  return dlb_post_launch();
+}
+
+template <typename T, int V>
+int fwd_apply_launch(const void* x, int64_t ldx, const void* res, int64_t ldr, void* y, int64_t ldy,
+                     const float* gamma, const float* beta, const float* mean, const float* rstd,
+                     int N, int HW, int C, int G, int relu, cudaStream_t st) {
+  dim3 grid; int rpb;
+  grid_for(N, HW, C, V, grid, rpb);
+  const size_t sm = 2 * C * sizeof(float);
+  const T* X = (const T*)x; const T* R = (const T*)res; T* Y = (T*)y;
+#define GO(RL, RS) gn_fwd_apply_kernel<T, V, RL, RS><<<grid, kThreads, sm, st>>>(X, ldx, R, ldr, Y, ldy, gamma, beta, mean, rstd, HW, C, G, rpb)
+  if (relu) { if (res) GO(true, true); else GO(true, false); }
+  else { if (res) GO(false, true); else GO(false, false); }
+#undef GO
+  return dlb_post_launch();
+}
+
+template <typename T, int V>
+int bwd_apply_launch(const void* x, int64_t ldx, const void* dy, int64_t lddy, const void* y, int64_t ldy,
+                     void* dx, int64_t lddx, void* dres, int64_t lddr, const float* gamma,
+                     const float* mean, const float* rstd, const float* table, int N, int HW, int C,
+                     int G, int relu, int acc, cudaStream_t st) {
+  dim3 grid; int rpb;
+  grid_for(N, HW, C, V, grid, rpb);
+  const size_t sm = (3 * C + 2 * G) * sizeof(float);
+  const T* X = (const T*)x; const T* DY = (const T*)dy; const T* Y = (const T*)y;
+  T* DX = (T*)dx; T* DR = (T*)dres;
+#define GO(RL, RS, AC) gn_bwd_apply_kernel<T, V, RL, RS, AC><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, DX, lddx, DR, lddr, gamma, mean, rstd, table, HW, C, G, rpb)
+  if (relu) {
+    if (dres) { if (acc) GO(true, true, true); else GO(true, true, false); }
+    else { if (acc) GO(true, false, true); else GO(true, false, false); }
+  } else {
+    if (dres) { if (acc) GO(false, true, true); else GO(false, true, false); }
+    else { if (acc) GO(false, false, true); else GO(false, false, false); }
+  }
+#undef GO
+  return dlb_post_launch();
+}
+
+inline bool vec_ok(int dtype, int C, std::initializer_list<int64_t> lds, std::initializer_list<const void*> ptrs) {
+  const int V = dtype == DLB_BF16 ? 8 : 4;
+  if (C % V) return false;
+  for (int64_t l : lds) if (l % V) return false;
+  for (const void* p : ptrs) if (p && ((uintptr_t)p & 15)) return false;
+  return true;
+}
+
+}  // namespace
+
+#define DISPATCH(dtype, vec, CALL)                                                         \
+  do {                                                                                      \
+    if (dtype == DLB_BF16) { if (vec) { using T = __nv_bfloat16; constexpr int V = 8; CALL; } \
+                             else { using T = __nv_bfloat16; constexpr int V = 1; CALL; } }  \
+    else { if (vec) { using T = float; constexpr int V = 4; CALL; }                          \
+           else { using T = float; constexpr int V = 1; CALL; } }                            \
+  } while (0)
+
+// table must hold N*C*2 floats; it is zeroed here.
+DLB_API int dlb_nc_reduce2(int mode, int dtype, const void* x, int64_t ldx, const void* dy, int64_t lddy,
+                           const void* y, int64_t ldy, float* table, int N, int HW, int C, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C > 6000) return -2;
+  cudaMemsetAsync(table, 0, (size_t)N * C * 2 * sizeof(float), st);
+  const bool vec = vec_ok(dtype, C, {ldx, dy ? lddy : 0, y ? ldy : 0}, {x, dy, y});
+  int rc = 0;
+  DISPATCH(dtype, vec, (rc = reduce2_launch<T, V>(mode, x, ldx, dy, lddy, y, ldy, table, N, HW, C, st)));
+  return rc;
+}
+
+DLB_API int dlb_gn_finalize(const float* table, float* mean, float* rstd, int N, int C, int G, int HW,
+                            float eps, void* stream) {
+  const int total = N * G;
+  gn_finalize_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(table, mean, rstd, N, C, G, HW, eps);
+  return dlb_post_launch();
+}
+
+// Forward: stats (reduce + finalize) + apply. `table` is scratch [N*C*2] fp32.
+DLB_API int dlb_gn_forward(int dtype, const void* x, int64_t ldx, const void* res, int64_t ldr, void* y,
+                           int64_t ldy, const float* gamma, const float* beta, float* mean, float* rstd,
+                           float* table, int N, int HW, int C, int G, float eps, int relu,
+                           int stats_ready, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = 0;
+  if (!stats_ready) {
+    rc = dlb_nc_reduce2(0, dtype, x, ldx, nullptr, 0, nullptr, 0, table, N, HW, C, stream);
+    if (rc) return rc;
+    rc = dlb_gn_finalize(table, mean, rstd, N, C, G, HW, eps, stream);
+    if (rc) return rc;
+  }
+  const bool vec = vec_ok(dtype, C, {ldx, res ? ldr : 0, ldy}, {x, res, y});
+  DISPATCH(dtype, vec, (rc = fwd_apply_launch<T, V>(x, ldx, res, ldr, y, ldy, gamma, beta, mean, rstd, N, HW, C, G, relu, st)));
+  return rc;
+}
+
+// Backward: reduce (dz, dz*x) + apply (+ param grads). dres may be null; acc!=0 accumulates into dx.
+DLB_API int dlb_gn_backward(int dtype, const void* x, int64_t ldx, const void* dy, int64_t lddy,
+                            const void* y, int64_t ldy, void* dx, int64_t lddx, void* dres, int64_t lddr,
+                            const float* gamma, const float* mean, const float* rstd, float* table,
+                            float* dgamma, float* dbeta, int N, int HW, int C, int G, int relu, int acc,
+                            void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = dlb_nc_reduce2(relu ? 1 : 2, dtype, x, ldx, dy, lddy, y, ldy, table, N, HW, C, stream);
+  if (rc) return rc;
+  const bool vec = vec_ok(dtype, C, {ldx, lddy, relu ? ldy : 0, lddx, dres ? lddr : 0}, {x, dy, relu ? y : nullptr, dx, dres});
+  DISPATCH(dtype, vec, (rc = bwd_apply_launch<T, V>(x, ldx, dy, lddy, y, ldy, dx, lddx, dres, lddr, gamma, mean, rstd, table, N, HW, C, G, relu, acc, st)));
+  if (rc) return rc;
+  if (dgamma) {
+    gn_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(table, mean, rstd, dgamma, dbeta, N, C, G);
+    rc = dlb_post_launch();
+  }
+  return rc;
+}

@@ -1,0 +1,47 @@
+"""Whole-step CUDA graph: augment → forward → backward → straggler burner → pack(+w_r,+clip) →
+fused weighted allreduce → SGD, captured once per local batch size and replayed.
+
+DenseNet-121 at CIFAR resolution is ~1500 small kernels per step; launch latency, not FLOPs, bounds
+the eager reference.  Everything a replay needs to vary lives in device memory — the
+learning rate, the DBS weight vector, the augmentation step counter, the burner duration — so the
+graph never has to be re-captured except when the rebalancer changes this rank's batch size
+(SURVEY §7.4 item 4); graphs are cached per size.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+
+
+class GraphedStep:
+    def __init__(self, trainer, xb: torch.Tensor, yb: torch.Tensor):
+        self.t = trainer
+        self.x = torch.empty_like(xb)
+        self.y = torch.empty_like(yb)
+        self.x.copy_(xb)
+        self.y.copy_(yb)
+        self.graph = torch.cuda.CUDAGraph()
+        t = trainer
+        t.model.train()
+        t.flat.zero_grad()
+        torch.cuda.synchronize(t.device)
+        launches0 = ops._native.launch_count()
+        with torch.cuda.graph(self.graph):
+            x = self.x if t.is_lm else t._prepare_images(self.x)
+            loss = t._forward_backward(x, self.y)
+            t.injector.device_delay()
+            t.flat.reduce_and_step(t.rank)
+            t.flat.zero_grad()
+            t.loss_acc += loss.float()
+            t.step_t += 1
+        self.native_launches = ops._native.launch_count() - launches0
+        t.flat._keep = None
+
+    def replay(self, xb: torch.Tensor, yb: torch.Tensor) -> None:
+        self.x.copy_(xb, non_blocking=True)
+        self.y.copy_(yb, non_blocking=True)
+        self.graph.replay()
+        lib = ops._native.get()
+        if lib is not None:
+            lib.dlb_launch_count_add(self.native_launches)

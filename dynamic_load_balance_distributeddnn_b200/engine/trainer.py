@@ -1,0 +1,335 @@
+"""Training engine: the DBS control loop.
+
+Per epoch (capabilities of reference ``dbs.py:313-446``; call stack in SURVEY §3.2-3.4):
+
+    LR policy → reallocator.step() (throughput-proportional re-split of the global batch)
+    → re-partition data so every rank runs the SAME number of steps with ITS local batch
+    → train (fwd, bwd, straggler injection, weighted gradient allreduce, SGD)
+    → validate → exchange per-rank pure-compute time → feed the reallocator → record.
+
+What is different by design:
+  * one flat parameter/gradient store and a fused  pack(+w_r,+clip) → allreduce → SGD  pipeline
+    (``parallel/buckets.py``) instead of one scale + one blocking allreduce per parameter tensor;
+  * on CUDA the whole step (augment → forward → backward → pack → collective → SGD) is captured in a
+    CUDA graph per local batch size and replayed; the graph is re-captured when DBS changes the size;
+  * time accounting is device-side (CUDA events + in-kernel barrier-wait counter), never
+    ``time.time()`` around asynchronous launches;
+  * datasets / corpus are built once, only indices are re-sliced per epoch (D11); the loss is
+    accumulated on the device and read back every ``log_every`` steps instead of two ``.item()``
+    syncs per step (K22).
+"""
+from __future__ import annotations
+
+import math
+import os
+import time
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from .. import ops
+from ..balance import Reallocator, TimeTracker
+from ..config import DBSConfig
+from ..data import (BatchStager, DataPartitioner, batchify, load_corpus, load_image_dataset, split_token_stream)
+from ..fault import StragglerInjector
+from ..models import build_model
+from ..parallel import FlatState, make_comm
+from ..utils import StatsRecorder, load_checkpoint, save_checkpoint
+from .lr_policy import lr_at_epoch
+
+_DT = {"fp32": torch.float32, "bf16": torch.bfloat16}
+
+
+class Trainer:
+    def __init__(self, cfg: DBSConfig, rank: int, world: int, device: str, logger, comm=None):
+        self.cfg, self.rank, self.world, self.logger = cfg, rank, world, logger
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        if self.cuda:
+            torch.cuda.set_device(self.device)
+        self.dtype = _DT[cfg.resolved_dtype(device)]
+        self.comm = comm if comm is not None else make_comm(cfg.resolved_comm(device), self.device)
+        self.is_lm = cfg.is_lm
+        self.log_every = 10
+        self._graphs: Dict[int, "GraphedStep"] = {}
+        self._eager_steps_at: Dict[int, int] = {}
+        self._build()
+
+    # ------------------------------------------------------------------------------------------------
+    def _build(self) -> None:
+        cfg = self.cfg
+        # ---- data (built once) ----
+        if self.is_lm:
+            sizes = None
+            if cfg.train_samples:
+                sizes = {"train": cfg.train_samples, "valid": max(1000, cfg.train_samples // 10),
+                         "test": cfg.test_samples or max(1000, cfg.train_samples // 10)}
+            self.corpus = load_corpus(cfg.corpus_root, cfg.synthetic, sizes, cfg.seed)
+            self.ntokens = self.corpus.ntokens
+            self.train_set = self.test_set = None
+        else:
+            self.train_set = load_image_dataset(cfg.dataset, True, cfg.data_root, cfg.synthetic, cfg.train_samples,
+                                                cfg.seed, pin=self.cuda)
+            self.test_set = load_image_dataset(cfg.dataset, False, cfg.data_root, cfg.synthetic, cfg.test_samples,
+                                               cfg.seed, pin=self.cuda)
+            self.ntokens = 0
+        # ---- model: identical init on every rank, then per-rank dropout streams (fixes D20) ----
+        torch.manual_seed(cfg.seed)
+        self.model = build_model(cfg.model, cfg.num_classes, self.ntokens)
+        self.flat = FlatState(self.model, self.device, self.dtype, self.comm, cfg.learning_rate, cfg.momentum,
+                              0.0, cfg.bucket_mb, _DT[cfg.wire_dtype], cfg.resolved_clip() if cfg.clip_mode == "local" else 0.0)
+        self.flat.sync_initial_params()
+        torch.manual_seed(cfg.seed + 1 + self.rank)
+        if self.cuda:
+            torch.cuda.manual_seed(cfg.seed + 1 + self.rank)
+        # ---- balancer, injector, recorder ----
+        self.realloc = Reallocator(self.world, cfg.batch_size, cfg.dynamic_batch_size, cfg.rounding,
+                                   cfg.min_local_batch, cfg.batch_quantum, cfg.time_ema)
+        self.injector = StragglerInjector(self.rank, cfg.fault_tolerance, cfg.fault_tolerance_chance,
+                                          cfg.throttle_rank, cfg.throttle_ms, cfg.throttle_mode, self.device,
+                                          logger=self.logger)
+        self.recorder = StatsRecorder(cfg, enabled=(self.rank == 0))
+        self.tracker = TimeTracker(self.device)
+        self.stager = None
+        if not self.is_lm:
+            self.stager = BatchStager(self.train_set, cfg.batch_size, self.device)
+        self.start_epoch = 0
+        if cfg.resume and cfg.checkpoint_dir:
+            blob = load_checkpoint(cfg, self.flat, self.realloc)
+            if blob is not None:
+                self.start_epoch = int(blob["epoch"]) + 1
+                self.logger.info(f"Rank {self.rank} resumed from epoch {blob['epoch']}")
+        self.total_train_time = 0.0
+        self.global_step = 0
+        self.step_t = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.loss_acc = torch.zeros(1, dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------------------------------------
+    # one optimisation step, eager flavour (CPU, or CUDA before a graph exists for this batch size)
+    def _forward_backward(self, x, y) -> torch.Tensor:
+        if self.is_lm:
+            loss = self.model.forward_loss(x, y)
+        else:
+            out = self.model(x)
+            loss = ops.cross_entropy(out, y)
+        loss.backward()
+        return loss.detach()
+
+    def _prepare_images(self, imgs_u8: torch.Tensor) -> torch.Tensor:
+        ds = self.train_set
+        return ops.augment(imgs_u8, ds.mean, ds.std, ds.pad, ds.flip, self.cfg.seed + self.rank, self.global_step,
+                           self.dtype, step_tensor=self.step_t if (self.cuda and ops._native.available()) else None)
+
+    def _eager_step(self, xb, yb) -> torch.Tensor:
+        self.model.train()
+        self.tracker.start_compute()
+        x = xb if self.is_lm else self._prepare_images(xb)
+        loss = self._forward_backward(x, yb)
+        slept = self.injector.host_delay()             # between backward and allreduce (reference dbs.py:236)
+        self.injector.device_delay()
+        self.tracker.stop_compute()
+        if slept and self.cuda:
+            self.tracker.add_compute(slept)
+        waited = self.flat.reduce_and_step(self.rank)
+        self.flat.zero_grad()
+        self.tracker.add_sync(waited)
+        self.loss_acc += loss.float()
+        if self.cuda:
+            self.step_t += 1
+        return loss
+
+    def train_step(self, xb, yb) -> None:
+        """Dispatch: CUDA-graph replay when enabled and warmed up for this batch size, else eager."""
+        b = int(yb.shape[0]) if not self.is_lm else int(xb.shape[1])
+        use_graph = self.cuda and self.cfg.cuda_graphs and ops._native.available()
+        if use_graph:
+            g = self._graphs.get(b)
+            if g is None:
+                n = self._eager_steps_at.get(b, 0)
+                if n < 3:                                   # warm-up steps at a new size run eagerly
+                    self._eager_steps_at[b] = n + 1
+                    self._eager_step(xb, yb)
+                    self.global_step += 1
+                    return
+                from .graph_step import GraphedStep
+                g = GraphedStep(self, xb, yb)
+                self._graphs[b] = g
+            slept = self.injector.host_delay()
+            if slept:
+                self.tracker.add_compute(slept)
+            self.tracker.start_compute()
+            g.replay(xb, yb)
+            self.tracker.stop_compute()
+        else:
+            self._eager_step(xb, yb)
+        self.global_step += 1
+
+    # ------------------------------------------------------------------------------------------------
+    def _train_epoch_vision(self, epoch: int, shard, steps: int) -> Tuple[float, float, float]:
+        cfg = self.cfg
+        g = torch.Generator().manual_seed(cfg.seed * 7919 + epoch * 131 + self.rank)
+        order = torch.randperm(len(shard), generator=g).numpy()          # DataLoader(shuffle=True)
+        self.comm.barrier()
+        self.tracker.reset()
+        self.loss_acc.zero_()
+        if self.cuda:
+            self.comm.device_wait_seconds(reset=True) if hasattr(self.comm, "device_wait_seconds") else None
+        running_mark, epoch_loss = 0.0, 0.0
+        for step in range(steps):
+            idx = shard.batch_indices(step, order)
+            xb, yb = self.stager.stage(idx)
+            self.train_step(xb, yb)
+            self.stager.release()
+            if step % self.log_every == 0 and step > 0:
+                acc = float(self.loss_acc.item())
+                self.logger.info(f"Rank {self.rank}, epoch {epoch}: {step}, train_loss {(acc - running_mark) / self.log_every}")
+                running_mark = acc
+        return self._finish_epoch(epoch, steps)
+
+    def _train_epoch_lm(self, epoch: int, tokens: torch.Tensor, local_batch: int, steps: int):
+        cfg = self.cfg
+        data = batchify(tokens, local_batch)                     # [rows, b]
+        if self.cuda:
+            data = data.pin_memory()
+        self.comm.barrier()
+        self.tracker.reset()
+        self.loss_acc.zero_()
+        if self.cuda and hasattr(self.comm, "device_wait_seconds"):
+            self.comm.device_wait_seconds(reset=True)
+        running_mark = 0.0
+        for step in range(steps):
+            i = step * cfg.bptt
+            src = data[i:i + cfg.bptt]
+            tgt = data[i + 1:i + 1 + cfg.bptt].reshape(-1)
+            if self.cuda:
+                src = src.to(self.device, non_blocking=True)
+                tgt = tgt.to(self.device, non_blocking=True)
+            self.train_step(src, tgt)
+            if step % self.log_every == 0 and step > 0:
+                acc = float(self.loss_acc.item())
+                self.logger.info(f"Rank {self.rank}, epoch {epoch}: {step}, train_loss {(acc - running_mark) / self.log_every}")
+                running_mark = acc
+        return self._finish_epoch(epoch, steps)
+
+    def _finish_epoch(self, epoch: int, steps: int):
+        compute_s, sync_s, wall_s = self.tracker.finish()
+        if self.cuda and isinstance(self.comm.device_wait_seconds(), float):
+            pass
+        dev_wait = self.comm.device_wait_seconds() if self.cuda else 0.0
+        if dev_wait > 0:
+            # graph replays time the whole step on the device; the in-kernel entry-barrier wait is the
+            # sync share (same definition as the reference: compute = wall − Σ wait, dbs.py:250)
+            sync_s += dev_wait
+            if self._graphs:
+                compute_s = max(0.0, compute_s - dev_wait)
+        loss = float(self.loss_acc.item()) / max(1, steps)
+        if hasattr(self.comm, "check_errors"):
+            self.comm.check_errors()
+        self.logger.info(f"Rank {self.rank}, epoch {epoch}, train_time {wall_s}, train_loss {loss}")
+        return compute_s, sync_s, loss, wall_s
+
+    # ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def validate(self, epoch: int) -> Tuple[float, float]:
+        """Sharded evaluation (every rank scores 1/world of the test set; the reference scores the whole
+        set on every rank and double-normalises the loss).  Returns (mean loss, accuracy %
+        for vision | perplexity for the LM)."""
+        self.model.eval()
+        stats = torch.zeros(3, dtype=torch.float64, device=self.device)      # loss_sum, correct, count
+        if self.is_lm:
+            data = batchify(self.corpus.test, 10)                             # eval batch 10 (dataloader.py:109)
+            rows = list(range(0, data.size(0) - 1, self.cfg.bptt))
+            for k, i in enumerate(rows):
+                if k % self.world != self.rank:
+                    continue
+                seq = min(self.cfg.bptt, data.size(0) - 1 - i)
+                src = data[i:i + seq].to(self.device)
+                tgt = data[i + 1:i + 1 + seq].reshape(-1).to(self.device)
+                logp = self.model(src).reshape(-1, self.ntokens)
+                stats[0] += F.nll_loss(logp.float(), tgt, reduction="sum").double()
+                stats[2] += tgt.numel()
+        else:
+            ds = self.test_set
+            n = len(ds)
+            bs = 500
+            for k, s in enumerate(range(0, n, bs)):
+                if k % self.world != self.rank:
+                    continue
+                imgs = ds.images[s:s + bs].to(self.device, non_blocking=True)
+                labels = ds.labels[s:s + bs].to(self.device, non_blocking=True)
+                x = ops.augment(imgs, ds.mean, ds.std, 0, False, 0, 0, self.dtype)
+                out = self.model(x).float()
+                stats[0] += F.cross_entropy(out, labels, reduction="sum").double()
+                stats[1] += (out.argmax(1) == labels).sum().double()
+                stats[2] += labels.numel()
+        if self.world > 1 and dist.is_initialized():
+            dist.all_reduce(stats)
+        cnt = max(1.0, float(stats[2].item()))
+        val_loss = float(stats[0].item()) / cnt
+        metric = math.exp(min(val_loss, 50.0)) if self.is_lm else 100.0 * float(stats[1].item()) / cnt
+        name = "perplexity" if self.is_lm else "accuracy"
+        self.logger.info(f"Rank {self.rank}, epoch {epoch}, val_loss {val_loss}, {name} {metric}")
+        self.model.train()
+        return val_loss, metric
+
+    # ------------------------------------------------------------------------------------------------
+    def run(self) -> StatsRecorder:
+        cfg = self.cfg
+        self.logger.info(f"Initiating Rank {self.rank}, World Size {self.world}")
+        self.logger.info(f"Rank {self.rank} start training")
+        for epoch in range(self.start_epoch, cfg.epoch_size):
+            lr = lr_at_epoch(cfg.learning_rate, epoch, cfg.epoch_size, cfg.lr_policy, cfg.one_cycle_policy,
+                             cfg.disable_enhancements)
+            self.flat.set_lr(lr)
+            fractions, local_batches = self.realloc.step()
+            if cfg.dynamic_batch_size:
+                self.logger.info(f"Rank {self.rank}, adjusted partition size to {fractions}")
+            self.flat.set_weights(self.realloc.weights(uniform=cfg.disable_enhancements))
+            b = int(local_batches[self.rank])
+            # ---- re-partition (indices only) ----
+            if self.is_lm:
+                pieces = split_token_stream(self.corpus.train.numel(), local_batches)
+                tokens = self.corpus.train[pieces[self.rank]]
+                rows = tokens.numel() // b
+                steps = (rows - 1) // cfg.bptt
+                if cfg.max_steps_per_epoch:
+                    steps = min(steps, cfg.max_steps_per_epoch)
+                length = rows * b
+            else:
+                part = DataPartitioner(len(self.train_set), local_batches, cfg.seed, True, cfg.max_steps_per_epoch)
+                shard = part.use(self.rank)
+                steps, length = part.steps, len(shard)
+            self.logger.info(f"Rank {self.rank}, number of batches {steps}, batch size {b}, length {length}")
+            self.injector.begin_epoch(epoch, steps)
+            t0 = time.perf_counter()
+            if self.is_lm:
+                compute_s, sync_s, loss, wall_s = self._train_epoch_lm(epoch, tokens, b, steps)
+            else:
+                compute_s, sync_s, loss, wall_s = self._train_epoch_vision(epoch, shard, steps)
+            self.total_train_time += time.perf_counter() - t0
+            val_loss, metric = self.validate(epoch) if cfg.validate else (float("nan"), float("nan"))
+            # ---- DBS feedback: exchange pure compute time (reference dbs.py:423-426) ----
+            nodes_time = self.comm.gather_times(compute_s)
+            if cfg.dynamic_batch_size:
+                self.realloc.observe(nodes_time)
+                self.logger.info(f"Rank {self.rank}, total time {nodes_time}")
+            self.recorder.append(epoch=epoch, train_loss=loss, train_time=compute_s, sync_time=sync_s, val_loss=val_loss,
+                                 accuracy=metric, partition=np.asarray(fractions), node_time=list(nodes_time),
+                                 wallclock_time=self.total_train_time, local_batches=[int(x) for x in local_batches],
+                                 samples_per_sec=(steps * cfg.batch_size / wall_s) if wall_s > 0 else 0.0,
+                                 straggler_wait_ms_per_step=1e3 * sync_s / max(1, steps), steps=steps, lr=lr)
+            if cfg.checkpoint_dir and self.rank == 0:
+                save_checkpoint(cfg, epoch, self.flat, self.realloc)
+        if self.rank == 0:
+            self.recorder.save()
+        self.logger.info(f"Rank {self.rank} Terminated")
+        self.logger.info(f"Rank {self.rank} Total Time:")
+        self.logger.info(self.total_train_time)
+        return self.recorder
+
+    def close(self) -> None:
+        self._graphs.clear()
+        self.comm.close()

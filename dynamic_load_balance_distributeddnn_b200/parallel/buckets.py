@@ -1,0 +1,200 @@
+"""Flat parameter / gradient / momentum storage and the fused optimizer step.
+
+The reference keeps 362 separate parameter tensors (DenseNet-121), scales and all-reduces each one
+separately and lets ``torch.optim.SGD`` loop over them (``dbs.py:291-301,369,238``).  Here:
+
+* all parameters live in ONE fp32 master buffer (+ one bf16 *shadow* buffer when computing in bf16);
+  ``param.data`` of every module parameter is a view into master (fp32-kept params such as norm
+  affines) or shadow (bf16 weights) — the model code is unchanged;
+* after backward the scattered ``.grad`` tensors are packed by a multi-tensor kernel straight into the
+  symmetric allreduce input buffer, applying the rank's DBS weight ``w_r = b_r / B`` and the local
+  gradient-clip coefficient on the way (no separate scale / clip kernels);
+* the buckets are reduced by the comm back-end into the output buffer;
+* one fused kernel applies momentum-SGD to the master buffer and refreshes the bf16 shadow.
+
+A pure-PyTorch implementation of the same steps runs on CPU (gloo debug mode) and is the numerics
+reference for the kernels.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from ..ops import _native as nat
+from .comm import Comm, SymmComm
+
+_ALIGN = 32          # elements; keeps every parameter 64-byte aligned in bf16 and 128-byte in fp32
+
+
+class FlatState:
+    def __init__(self, model: nn.Module, device, compute_dtype: torch.dtype, comm: Comm,
+                 lr: float, momentum: float = 0.9, weight_decay: float = 0.0, bucket_mb: float = 8.0,
+                 wire_dtype: torch.dtype = torch.float32, clip_norm: float = 0.0):
+        self.device = torch.device(device)
+        self.comm = comm
+        self.params: List[nn.Parameter] = [p for p in model.parameters()]
+        self.compute_dtype = compute_dtype
+        self.momentum, self.weight_decay, self.clip_norm = momentum, weight_decay, clip_norm
+        self.native = self.device.type == "cuda" and nat.available()
+        self.offsets: List[int] = []
+        off = 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        world = max(1, comm.world)
+        pad_to = _ALIGN * world
+        self.numel = (off + pad_to - 1) // pad_to * pad_to
+        self.master = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
+        self.shadow = torch.zeros(self.numel, dtype=torch.bfloat16, device=self.device) \
+            if compute_dtype == torch.bfloat16 else None
+        self.mom = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
+        self.wire_dtype = wire_dtype
+        self.grad_in, self.grad_out = comm.alloc_grad_buffers(self.numel, wire_dtype, self.device)
+        self.lr_t = torch.full((1,), float(lr), dtype=torch.float32, device=self.device)
+        self.weights_t = torch.full((world,), 1.0 / world, dtype=torch.float32, device=self.device)
+        self.sumsq_t = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._adopt(model)
+        self.buckets = self._make_buckets(bucket_mb)
+        self._pack_cache = None
+
+    # ---- parameter adoption -----------------------------------------------------------------------
+    def _adopt(self, model: nn.Module) -> None:
+        with torch.no_grad():
+            for p, off in zip(self.params, self.offsets):
+                n = p.numel()
+                self.master[off:off + n].copy_(p.detach().reshape(-1).to(self.device, torch.float32))
+            if self.shadow is not None:
+                self.shadow.copy_(self.master)
+            for p, off in zip(self.params, self.offsets):
+                n = p.numel()
+                keep32 = getattr(p, "_dlb_keep_fp32", False) or self.shadow is None
+                src = self.master if keep32 else self.shadow
+                p.data = src[off:off + n].view(p.shape)
+                p.grad = None
+        # non-parameter state (buffers such as the positional table) just moves to the device
+        for mod in model.modules():
+            for k, b in list(mod._buffers.items()):
+                if b is not None:
+                    mod._buffers[k] = b.to(self.device)
+
+    def _make_buckets(self, bucket_mb: float) -> List[Tuple[int, int]]:
+        """Contiguous (offset, numel) ranges of the flat buffer, ~bucket_mb each, aligned so every
+        rank-chunk is a whole number of 16-byte vectors."""
+        esize = 2 if self.wire_dtype == torch.bfloat16 else 4
+        target = max(1, int(bucket_mb * (1 << 20) / esize))
+        world = max(1, self.comm.world)
+        quantum = _ALIGN * world
+        target = max(quantum, target // quantum * quantum)
+        out, off = [], 0
+        while off < self.numel:
+            n = min(target, self.numel - off)
+            out.append((off, n))
+            off += n
+        return out
+
+    # ---- synchronisation helpers ------------------------------------------------------------------
+    def sync_initial_params(self) -> None:
+        """Average the initial replicas (reference dbs.py:365-367) — a no-op numerically when all
+        ranks share the init seed, but it guarantees bit-identical starting points."""
+        if self.comm.world > 1:
+            self.comm.average_(self.master)
+            self.refresh_shadow()
+
+    def refresh_shadow(self) -> None:
+        if self.shadow is not None:
+            if self.native:
+                nat.check(nat.require().dlb_cast_f32_bf16(self.master.data_ptr(), self.shadow.data_ptr(), self.numel,
+                                                          nat.stream_ptr(self.device)), "cast")
+            else:
+                self.shadow.copy_(self.master)
+
+    def set_lr(self, lr: float) -> None:
+        self.lr_t.fill_(float(lr))
+
+    def set_weights(self, weights: Sequence[float]) -> None:
+        self.weights_t.copy_(torch.as_tensor(list(weights), dtype=torch.float32))
+        self._weights_host = [float(w) for w in weights]
+
+    # ---- the post-backward pipeline ---------------------------------------------------------------
+    def _grad_lists(self):
+        ptrs, offs, numels, dtypes, keep = [], [], [], [], []
+        for p, off in zip(self.params, self.offsets):
+            g = p.grad
+            if g is None:
+                g = torch.zeros_like(p)
+            if not g.is_contiguous():
+                g = g.contiguous()
+            keep.append(g)
+            ptrs.append(g.data_ptr()); offs.append(off); numels.append(g.numel()); dtypes.append(nat.dtype_code(g.dtype))
+        n = len(ptrs)
+        return ((ctypes.c_void_p * n)(*ptrs), (ctypes.c_longlong * n)(*offs), (ctypes.c_int * n)(*numels),
+                (ctypes.c_int * n)(*dtypes), n, keep)
+
+    def reduce_and_step(self, rank: int) -> float:
+        """pack(+weight,+clip) → allreduce buckets → fused SGD.  Returns host-measured wait seconds
+        (non-zero only for host-blocking back-ends)."""
+        if self.native:
+            return self._reduce_and_step_native(rank)
+        return self._reduce_and_step_torch(rank)
+
+    def _reduce_and_step_native(self, rank: int) -> float:
+        lib = nat.require()
+        st = nat.stream_ptr(self.device)
+        ptrs, offs, numels, dtypes, n, keep = self._grad_lists()
+        use_clip = self.clip_norm > 0
+        if use_clip:
+            nat.check(lib.dlb_zero_f32(self.sumsq_t.data_ptr(), 1, st), "zero")
+            nat.check(lib.dlb_mt_sumsq(n, ptrs, numels, dtypes, self.sumsq_t.data_ptr(), st), "mt_sumsq")
+        nat.check(lib.dlb_mt_pack(n, ptrs, offs, numels, dtypes, self.grad_in.data_ptr(), nat.dtype_code(self.wire_dtype),
+                                  self.weights_t.data_ptr(), rank, self.sumsq_t.data_ptr() if use_clip else None,
+                                  float(self.clip_norm), st), "mt_pack")
+        self._keep = keep
+        if self.comm.world > 1:
+            waited = self.comm.allreduce_buckets(self.grad_in, self.grad_out, self.buckets)
+            g = self.grad_out
+        else:                              # single rank: the packed (weighted, clipped) gradient IS the result
+            waited, g = 0.0, self.grad_in
+        if g.dtype != torch.float32:
+            g = g.float()
+        nat.check(lib.dlb_sgd_flat(self.master.data_ptr(), self.mom.data_ptr(), g.data_ptr(),
+                                   nat.ptr(self.shadow), self.numel, self.lr_t.data_ptr(), float(self.momentum),
+                                   float(self.weight_decay), st), "sgd_flat")
+        return waited
+
+    def _reduce_and_step_torch(self, rank: int) -> float:
+        with torch.no_grad():
+            scale = float(self.weights_t[rank].item())
+            if self.clip_norm > 0:
+                ss = sum(float((p.grad.float() ** 2).sum()) for p in self.params if p.grad is not None)
+                scale *= min(1.0, self.clip_norm / (math.sqrt(ss) + 1e-6))
+            self.grad_in.zero_()
+            for p, off in zip(self.params, self.offsets):
+                if p.grad is not None:
+                    self.grad_in[off:off + p.numel()].copy_(p.grad.reshape(-1).to(self.grad_in.dtype) * scale)
+            waited = self.comm.allreduce_buckets(self.grad_in, self.grad_out, self.buckets)
+            g = self.grad_out.float()
+            if self.weight_decay:
+                g = g + self.weight_decay * self.master
+            self.mom.mul_(self.momentum).add_(g)
+            self.master.add_(self.mom * (-self.lr_t))
+            if self.shadow is not None:
+                self.shadow.copy_(self.master)
+        return waited
+
+    def zero_grad(self) -> None:
+        for p in self.params:
+            p.grad = None
+
+    # ---- checkpointing ------------------------------------------------------------------------------
+    def state_dict(self):
+        return {"master": self.master.detach().cpu(), "momentum": self.mom.detach().cpu(), "lr": float(self.lr_t.item())}
+
+    def load_state_dict(self, sd) -> None:
+        self.master.copy_(sd["master"].to(self.device))
+        self.mom.copy_(sd["momentum"].to(self.device))
+        self.set_lr(sd["lr"])
+        self.refresh_shadow()

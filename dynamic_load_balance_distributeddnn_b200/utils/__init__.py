@@ -1,0 +1,7 @@
+from .checkpoint import load_checkpoint, save_checkpoint
+from .clocks import ClockSampler
+from .logging import done_marker, init_logger, log_path
+from .stats import StatsRecorder, load_stats
+
+__all__ = ["load_checkpoint", "save_checkpoint", "ClockSampler", "done_marker", "init_logger", "log_path",
+           "StatsRecorder", "load_stats"]

@@ -1,0 +1,96 @@
+"""Reallocator property tests (SURVEY §4 'Unit (CPU)': Σ=B exactly, min-bs clamp, fixed point,
+proportionality, permutation equivariance, agreement with the reference rule where it sums to B)."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from dynamic_load_balance_distributeddnn_b200.balance import (Reallocator, get_size, integer_split, reference_split,
+                                                                throughput_shares)
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.integers(2, 16).flatmap(lambda n: st.tuples(
+    st.lists(st.floats(0.01, 100.0), min_size=n, max_size=n),
+    st.integers(n, 4096))))
+def test_sum_exact_and_min(arg):
+    times, B = arg
+    n = len(times)
+    frac, ints = get_size(times, np.full(n, 1.0 / n), B)
+    assert ints.sum() == B
+    assert (ints >= 1).all()
+    assert abs(frac.sum() - 1.0) < 1e-9
+
+
+def test_golden_examples_from_survey():
+    # SURVEY Appendix A.1 worked examples
+    f, b = get_size([1, 1, 1, 1], [.25] * 4, 512)
+    assert list(b) == [128] * 4
+    f, b = get_size([10, 10, 10, 20], [.25] * 4, 512)
+    assert b.sum() == 512 and sorted(b)[0] == 73 and sorted(b)[-1] in (146, 147)
+    f, b = get_size([1.0, 1.3, 2.1], [1 / 3] * 3, 100)
+    assert list(b) == [45, 34, 21]
+    f, b = get_size([.4269, .4319, .4320], [1 / 3] * 3, 64)
+    assert list(b) == [22, 21, 21]
+    # reference rule reproduces the reference's sample loss (D5) and the dead rank (D7)
+    assert reference_split(throughput_shares([10, 10, 10, 20], [.25] * 4), 512).sum() == 511
+    assert reference_split(throughput_shares([1, 1, 1, 100], [.25] * 4), 64)[3] == 0
+    # ours keeps the slow rank alive
+    f, b = get_size([1, 1, 1, 100], [.25] * 4, 64)
+    assert b[3] >= 1 and b.sum() == 64
+
+
+def test_fixed_point_when_times_equalise():
+    f, b = get_size([10, 10, 10, 20], [.25] * 4, 512)
+    f2, b2 = get_size([8.75] * 4, f, 512)
+    assert list(b2) == list(b)
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.lists(st.floats(0.1, 10.0), min_size=3, max_size=8), st.integers(64, 2048))
+def test_permutation_equivariance_and_monotonicity(times, B):
+    n = len(times)
+    p = np.full(n, 1.0 / n)
+    _, b = get_size(times, p, B)
+    perm = np.random.RandomState(0).permutation(n)
+    _, bp = get_size(np.asarray(times)[perm], p, B)
+    # multiset of batches is permutation invariant (ties may swap ±1 between equal ranks)
+    assert sorted(b) == sorted(bp)
+    order = np.argsort(times)
+    assert b[order[0]] >= b[order[-1]]              # the fastest rank never gets less than the slowest
+
+
+def test_agrees_with_reference_when_reference_is_exact():
+    rng = np.random.RandomState(1)
+    agree = 0
+    for _ in range(200):
+        n = rng.randint(2, 9)
+        t = rng.uniform(0.5, 2.0, n)
+        B = int(rng.choice([64, 128, 512, 1000]))
+        shares = throughput_shares(t, np.full(n, 1.0 / n))
+        ref = reference_split(shares, B)
+        if ref.sum() == B:
+            agree += int((integer_split(shares, B) == ref).all())
+            assert (integer_split(shares, B) == ref).all()
+    assert agree > 50
+
+
+def test_quantum_and_regrowth():
+    b = integer_split([0.5, 0.3, 0.2], 512, min_local=8, quantum=8)
+    assert b.sum() == 512 and (b % 8 == 0).all()
+    r = Reallocator(4, 64, enabled=True)
+    r.step()
+    r.observe([1, 1, 1, 100])
+    _, b1 = r.step()
+    assert b1[3] >= 1
+    r.observe([1, 1, 1, 1.0 * b1[3] / b1[0]])       # the slow rank recovered: same per-sample speed as the others
+    _, b2 = r.step()
+    assert b2[3] > b1[3]                             # it re-grows (the reference's share-0 state is absorbing, D7)
+
+
+def test_static_when_disabled():
+    r = Reallocator(4, 512, enabled=False)
+    r.observe([1, 2, 3, 4])
+    f, b = r.step()
+    assert list(b) == [128] * 4
+    assert np.allclose(r.weights(), 0.25)
+    assert np.allclose(r.weights(uniform=True), 0.25)

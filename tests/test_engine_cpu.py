@@ -1,0 +1,127 @@
+"""Integration on CPU/gloo (BASELINE config #1: MnistNet ws=2 DBS on) + weighted-allreduce invariance."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run_cli(tmp_path, extra, timeout=420):
+    cmd = [sys.executable, os.path.join(ROOT, "dbs.py")] + extra + ["--log_dir", str(tmp_path / "logs"),
+                                                                      "--stats_dir", str(tmp_path / "statis")]
+    env = dict(os.environ, PYTHONPATH=ROOT, OMP_NUM_THREADS="2")
+    return subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=timeout)
+
+
+def test_mnistnet_ws2_gloo_dbs(tmp_path):
+    from dynamic_load_balance_distributeddnn_b200.utils import load_stats
+    args = "-d true -ws 2 -b 64 -m mnistnet -ds mnist -e 3 --synthetic true --train_samples 1536 --test_samples 256 " \
+           "--throttle_rank 1 --throttle_ms 60 --master_port 29611".split()
+    r = _run_cli(tmp_path, args)
+    assert r.returncode == 0, r.stderr[-3000:]
+    stem = "mnistnet-mnist-debug1-n2-bs64-lr0.0100-ep3-dbs1-ft0-ftc0.100000-node%d-ocp0"
+    for rank in (0, 1):
+        assert (tmp_path / "logs" / (stem % rank + ".log")).is_file()
+    stats = load_stats(str(tmp_path / "statis" / (stem % 0 + ".npy")))
+    for k in ("epoch", "train_loss", "train_time", "sync_time", "val_loss", "accuracy", "partition", "node_time", "wallclock_time"):
+        assert len(stats[k]) == 3, k
+    assert stats["train_loss"][-1] < stats["train_loss"][0]
+    lb = stats["local_batches"]
+    assert all(sum(x) == 64 for x in lb)
+    assert lb[0] == [32, 32] and lb[-1][1] < 32 < lb[-1][0]          # the throttled rank lost batch share
+    # second invocation is skipped through the completion marker
+    r2 = _run_cli(tmp_path, args)
+    assert r2.returncode == 0 and "skipping" in r2.stdout
+
+
+def test_failure_propagates_exit_code(tmp_path):
+    r = _run_cli(tmp_path, "-d true -ws 2 -b 64 -m mnistnet -ds cifar10 -e 1 --synthetic true --train_samples 256 "
+                           "--test_samples 64 --master_port 29612".split(), timeout=300)
+    assert r.returncode != 0                                          # incompatible model/dataset must not exit 0
+
+
+def _invariance_worker(rank, world, port, split, outdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dynamic_load_balance_distributeddnn_b200.models import build_model
+    from dynamic_load_balance_distributeddnn_b200.parallel import FlatState, make_comm
+    torch.manual_seed(0)
+    model = build_model("resnet18", 10)
+    comm = make_comm("gloo", "cpu")
+    flat = FlatState(model, "cpu", torch.float32, comm, lr=0.1, momentum=0.9)
+    flat.set_weights([s / sum(split) for s in split])
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(sum(split), 3, 32, 32, generator=g)
+    y = torch.randint(0, 10, (sum(split),), generator=g)
+    lo = sum(split[:rank])
+    xs, ys = x[lo:lo + split[rank]], y[lo:lo + split[rank]]
+    model.train()
+    loss = torch.nn.functional.cross_entropy(model(xs), ys)
+    loss.backward()
+    flat.reduce_and_step(rank)
+    torch.save((rank, flat.grad_out.clone(), flat.master.clone()), os.path.join(outdir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("split", [[4, 4], [6, 2], [3, 4, 1]])
+def test_weighted_allreduce_equals_full_batch_gradient(split, tmp_path):
+    """Σ_r (b_r/B)·g_r == gradient of the mean loss over the global batch, for any split —
+    exact for GroupNorm models up to fp association — and replicas stay bit-identical."""
+    from dynamic_load_balance_distributeddnn_b200.models import build_model
+    from dynamic_load_balance_distributeddnn_b200.parallel import FlatState, SingleComm
+    world = len(split)
+    ctx = mp.get_context("spawn")
+    port = 29620 + world * 3 + split[0]
+    procs = [ctx.Process(target=_invariance_worker, args=(r, world, port, split, str(tmp_path))) for r in range(world)]
+    [p.start() for p in procs]
+    [p.join(240) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    res = [torch.load(str(tmp_path / f"r{r}.pt")) for r in range(world)]
+    for r in range(1, world):
+        assert torch.equal(res[0][1], res[r][1]) and torch.equal(res[0][2], res[r][2])     # bit-identical replicas
+    torch.manual_seed(0)
+    model = build_model("resnet18", 10)
+    flat = FlatState(model, "cpu", torch.float32, SingleComm(), lr=0.1, momentum=0.9)
+    flat.set_weights([1.0])
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(sum(split), 3, 32, 32, generator=g)
+    y = torch.randint(0, 10, (sum(split),), generator=g)
+    torch.nn.functional.cross_entropy(model(x), y).backward()
+    flat.reduce_and_step(0)
+    n = min(flat.numel, res[0][1].numel())                    # padding depends on the world size
+    assert torch.allclose(flat.grad_out[:n], res[0][1][:n], atol=2e-5, rtol=1e-4)
+    assert torch.allclose(flat.master[:n], res[0][2][:n], atol=2e-6, rtol=1e-5)
+
+
+def test_lr_policies():
+    from dynamic_load_balance_distributeddnn_b200.engine import lr_at_epoch
+    assert lr_at_epoch(0.1, 5, 10, enabled=False) == 0.1
+    assert lr_at_epoch(0.1, 5, 10, disabled_enhancements=True) == 0.1
+    assert abs(lr_at_epoch(0.1, 0, 10) - 0.001) < 1e-12 and lr_at_epoch(0.1, 5, 10) == 0.1
+    assert abs(lr_at_epoch(0.1, 10, 10) - 0.001) < 1e-9
+    # legacy = the reference's live curve: discontinuous drop at 0.7E (dbs.py:210)
+    assert lr_at_epoch(0.1, 6, 10, "legacy") == 0.1
+    assert abs(lr_at_epoch(0.1, 7, 10, "legacy") - 0.1 * (1 - 0.99 * 7 / 10)) < 1e-12
+
+
+def test_fault_injector_reference_semantics():
+    from dynamic_load_balance_distributeddnn_b200.fault import StragglerInjector
+    inj = StragglerInjector(0, enabled=True, chance=1.0, seed=3)
+    d = inj.begin_epoch(0, 100)
+    assert inj.waiting and 5 <= inj.wait_seconds <= 10 and 4 <= inj.until_epoch <= 20
+    assert abs(d - inj.wait_seconds / 100) < 1e-12
+    until = inj.until_epoch
+    assert inj.begin_epoch(until, 50) == inj.wait_seconds / 50        # still waiting at fault_round
+    inj.chance = 0.0
+    assert inj.begin_epoch(until + 1, 50) == 0.0 and not inj.waiting  # phase over, luck says no
+    fixed = StragglerInjector(2, throttle_rank=2, throttle_ms=5.0)
+    assert fixed.begin_epoch(0, 10) == 0.005 and StragglerInjector(1, throttle_rank=2, throttle_ms=5.0).begin_epoch(0, 10) == 0.0
