@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""Headline benchmark (BASELINE.json): DenseNet-121, CIFAR-10-shape synthetic data, GLOBAL batch 512,
+images/s for the whole job, device-timed, max over ranks, at N GPUs of one node, with one rank throttled
+when N > 1 so the DBS rebalancer has something to do.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus 8 --steps 20 --warmup 5
+    python bench.py --impl reference ...      # the UNMODIFIED reference from baseline/_ref, same metric
+
+Own arm, per rank:  W warm-up steps at the uniform split (eager warm-up + CUDA-graph capture) → exchange
+measured compute times with the P2P-store all-gather kernel → DBS reallocation → warm-up at the new local
+batch (re-capture) → timed region.  Two timed regions of exactly K steps each, both bracketed by
+barrier + cuda synchronize and timed with CUDA events, max over ranks:
+  * ``e2e``   — the public API path a user runs: every step gathers its batch into pinned host memory, copies
+                it host→device, runs the step (augment → fwd → bwd → pack(+w_r) → fused allreduce → SGD) and
+                copies the running loss device→host.
+  * ``value`` — the same K steps with the batch already resident on the device (kernel-only number).
+Scaling is STRONG: the global batch stays 512 as N grows (that is what `-b` means in the reference).
+"""
+from __future__ import annotations
+
+import argparse
+import datetime
+import itertools
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "densenet121_cifar10_images_per_sec"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", choices=("ours", "reference"), default="ours")
+    p.add_argument("--model", default="densenet")
+    p.add_argument("--dataset", default="cifar10")
+    p.add_argument("--batch", type=int, default=512, help="GLOBAL batch")
+    p.add_argument("--throttle-ms", type=float, default=3.0, help="extra ms/step on the last rank when N>1")
+    p.add_argument("--no-dbs", action="store_true")
+    p.add_argument("--no-graphs", action="store_true")
+    p.add_argument("--comm", default="auto")
+    p.add_argument("--algo", default="auto")
+    p.add_argument("--dtype", default="bf16")
+    return p.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    return rank, world, local
+
+
+def max_over_ranks(value: float, device, world: int) -> float:
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, device, world: int) -> float:
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+# =====================================================================================================
+def run_ours(a) -> dict:
+    import torch
+    import torch.distributed as dist
+    from dynamic_load_balance_distributeddnn_b200.config import DBSConfig
+    from dynamic_load_balance_distributeddnn_b200.data import DataPartitioner
+    from dynamic_load_balance_distributeddnn_b200.engine import Trainer
+    from dynamic_load_balance_distributeddnn_b200.ops import _native
+    from dynamic_load_balance_distributeddnn_b200.utils import ClockSampler, init_logger
+
+    rank, world, local = dist_env()
+    assert world == a.gpus or world == 1, f"WORLD_SIZE {world} != --gpus {a.gpus}"
+    device = f"cuda:{local}"
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(device), timeout=datetime.timedelta(seconds=300))
+    W, K = max(3, a.warmup), a.steps
+    total_steps = 2 * (W + 8) + 2 * K + 8
+    throttle = a.throttle_ms if world > 1 else 0.0
+    cfg = DBSConfig(debug=False, world_size=world, batch_size=a.batch, model=a.model, dataset=a.dataset, synthetic=True,
+                    train_samples=a.batch * total_steps, test_samples=256, epoch_size=1, validate=False,
+                    dynamic_batch_size=not a.no_dbs, cuda_graphs=not a.no_graphs, comm=a.comm, allreduce_algo=a.algo,
+                    dtype=a.dtype, throttle_rank=world - 1 if throttle > 0 else -1, throttle_ms=throttle,
+                    throttle_mode="sleep", log_dir="/tmp/dlb_bench/logs", stats_dir="/tmp/dlb_bench/statis")
+    logger = init_logger(cfg, rank, stream=False)
+    tr = Trainer(cfg, rank, world, device, logger)
+    is_lm = tr.is_lm
+
+    def make_shard(local_batches, n_steps, seed):
+        part = DataPartitioner(len(tr.train_set), local_batches, seed, True, n_steps)
+        return part.use(rank)
+
+    def run_steps(shard, n, e2e=True, sink=None):
+        import numpy as np
+        order = np.arange(len(shard))
+        for s in range(n):
+            if e2e or s == 0:
+                xb, yb = tr.stager.stage(shard.batch_indices(s, order))
+            tr.train_step(xb, yb)
+            if e2e:
+                tr.stager.release()
+                if sink is not None:
+                    sink[s % sink.shape[0]].copy_(tr.loss_acc, non_blocking=True)      # D2H of the step's result
+        if not e2e:
+            tr.stager.release()
+
+    # ---- phase 1: uniform split, warm-up + measure compute time --------------------------------------
+    fractions, lb = tr.realloc.step()
+    tr.flat.set_weights(tr.realloc.weights())
+    tr.injector.begin_epoch(0, W + 8)
+    tr.comm.barrier()
+    tr.tracker.reset()
+    if hasattr(tr.comm, "device_wait_seconds"):
+        tr.comm.device_wait_seconds()
+    run_steps(make_shard(lb, W + 8, 1), W + 8)
+    compute_s, sync_s, _ = tr.tracker.finish()
+    dev_wait = tr.comm.device_wait_seconds() if hasattr(tr.comm, "device_wait_seconds") else 0.0
+    compute_s = max(1e-6, compute_s - dev_wait) if tr._graphs else compute_s
+    times = tr.comm.gather_times(compute_s)
+    lb0 = [int(x) for x in lb]
+    if world > 1 and not a.no_dbs:
+        tr.realloc.observe(times)
+        fractions, lb = tr.realloc.step()
+        tr.flat.set_weights(tr.realloc.weights())
+    # ---- phase 2: warm-up at the rebalanced local batch (graph re-capture) ------------------------------
+    run_steps(make_shard(lb, W + 8, 2), W + 8)
+    torch.cuda.synchronize()
+
+    sink = torch.zeros(8, 1, dtype=torch.float32).pin_memory()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+
+    def timed(e2e: bool, seed: int):
+        shard = make_shard(lb, K, seed)
+        if world > 1:
+            dist.barrier()
+        tr.comm.barrier()
+        torch.cuda.synchronize()
+        if hasattr(tr.comm, "device_wait_seconds"):
+            tr.comm.device_wait_seconds()
+        n0 = _native.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_steps(shard, K, e2e=e2e, sink=sink if e2e else None)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        wait = tr.comm.device_wait_seconds() if hasattr(tr.comm, "device_wait_seconds") else 0.0
+        return max_over_ranks(ms, device, world), _native.launch_count() - n0, max_over_ranks(wait, device, world)
+
+    ms_e2e, _, wait_e2e = timed(True, 3)
+    ms_dev, launches, wait_dev = timed(False, 4)
+    clk = clocks.stop() if rank == 0 else {}
+    if hasattr(tr.comm, "check_errors"):
+        tr.comm.check_errors()
+    h2d = tr.stager.bytes_per_step
+    loss = float(tr.loss_acc.item())
+    value = a.batch * K / (ms_dev * 1e-3)
+    e2e_value = a.batch * K / (ms_e2e * 1e-3)
+    out = {
+        "metric": METRIC if a.model == "densenet" else f"{a.model}_{a.dataset}_images_per_sec",
+        "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": K, "warmup": 2 * (W + 8),
+        "ms_per_step": round(ms_dev / K, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": a.dtype, "data": "synthetic (CIFAR-10-shape uint8 images, random-init weights)", "impl": "ours",
+        "config": {"model": "DenseNet-121 (GroupNorm)" if a.model == "densenet" else a.model, "global_batch": a.batch,
+                   "image": "3x32x32", "parallelism": f"dp{world}", "dbs": not a.no_dbs,
+                   "local_batches_before": lb0, "local_batches": [int(x) for x in lb],
+                   "throttle": {"rank": world - 1, "ms_per_step": throttle} if throttle > 0 else None,
+                   "comm": tr.comm.name, "cuda_graphs": bool(tr._graphs), "optimizer": "SGD momentum 0.9 (in timed region)",
+                   "l2": "per-step working set (activations+grads, >1 GB) exceeds the 126 MB L2; no explicit flush"},
+        "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "ms_per_step": round(ms_e2e / K, 4),
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "straggler_wait_ms_per_step": round(1e3 * wait_dev / K, 4),
+        "clocks": {"sm_mhz": clk.get("sm_mhz"), "sm_max_mhz": clk.get("sm_max_mhz"), "reasons": clk.get("reasons", [])},
+        "final_loss_acc": loss,
+    }
+    tr.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return out if rank == 0 else {}
+
+
+# =====================================================================================================
+def run_reference(a) -> dict:
+    """The unmodified reference (baseline/_ref): its own models, DataLoader, per-parameter SSGD allreduce,
+    torch.optim.SGD, get_size and time_allreduce, called in the order its run() calls them.  Shims live
+    OUTSIDE its source: synthetic torchvision datasets (no network), pre-created log dirs, a deterministic
+    straggler in place of the broken -ft injector, CUDA-event timing, and islice() so every rank runs
+    exactly K steps (the reference can dead-lock on unequal step counts)."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    rank, world, local = dist_env()
+    if not os.path.isfile(os.path.join(ref_dir, "dbs.py")):
+        return {"impl": "reference", "unavailable": "baseline/_ref not installed (run tools/install_reference.sh)"}
+    try:
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+        import torchvision
+        from PIL import Image
+    except Exception as e:           # noqa: BLE001
+        return {"impl": "reference", "unavailable": f"import failed: {e!r}"}
+
+    W, K = max(3, a.warmup), a.steps
+    work = f"/tmp/dlb_ref_run_{os.getpid()}"
+    os.makedirs(os.path.join(work, "logs"), exist_ok=True)
+    os.makedirs(os.path.join(work, "statis"), exist_ok=True)
+    os.chdir(work)
+    sys.path.insert(0, ref_dir)
+    argv = ["dbs.py", "-d", "false", "-ws", str(world), "-b", str(a.batch), "-m", a.model, "-ds", a.dataset, "-e", "2",
+            "-dbs", "false" if a.no_dbs else "true"]
+    if world > 1:
+        argv += ["-gpu", ",".join(str(i) for i in range(world))]
+    sys.argv = argv
+
+    n_holder = {"n": a.batch * (W + 2)}
+
+    class _Synth(torch.utils.data.Dataset):
+        """torchvision.datasets.CIFAR10-shaped stand-in: uint8 HWC arrays → PIL → the reference's transforms."""
+        def __init__(self, root, train=True, download=False, transform=None, **kw):
+            self.transform = transform
+            g = np.random.RandomState(1234 if train else 4321)
+            self.n_full = 50000 if train else 512
+            self.data = g.randint(0, 256, size=(4096, 32, 32, 3), dtype=np.uint8)
+            self.targets = g.randint(0, 10, size=(4096,)).tolist()
+            self.train = train
+
+        def __len__(self):
+            return n_holder["n"] if self.train else self.n_full
+
+        def __getitem__(self, i):
+            img = Image.fromarray(self.data[i % 4096])
+            if self.transform is not None:
+                img = self.transform(img)
+            return img, self.targets[i % 4096]
+
+    torchvision.datasets.CIFAR10 = _Synth
+    torchvision.datasets.CIFAR100 = _Synth
+    import dbs                      # parses sys.argv at import (reference dbs.py:22)
+    import dataloader
+    import dbs_logging
+
+    device = f"cuda:{local}"
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world,
+                                timeout=datetime.timedelta(seconds=300))
+    else:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("cpu:gloo,cuda:nccl", rank=0, world_size=1)
+    dbs.DEVICE = device
+    dbs.logger = dbs_logging.init_logger(dbs.args, rank, dbs.base_filename)
+    import logging
+    for h in dbs.logger.logger.handlers:
+        if isinstance(h, logging.StreamHandler) and not isinstance(h, logging.FileHandler):
+            h.setLevel(logging.ERROR)
+    throttle = a.throttle_ms if world > 1 else 0.0
+    if throttle > 0:
+        def _wait(epoch, batch_num, r):        # deterministic stand-in for the broken -ft injector
+            if r == world - 1:
+                time.sleep(throttle * 1e-3)
+        dbs.fault_tolerance_wait = _wait
+
+    # ---- what reference run() does (dbs.py:313-379), with its own classes/functions -----------------
+    torch.manual_seed(1234)
+    if a.model == "densenet":
+        import Net.Densenet
+        model = Net.Densenet.DenseNet121(10)
+    elif a.model == "resnet50":
+        import Net.Resnet
+        model = Net.Resnet.ResNet50(10)
+    else:
+        import Net.Resnet
+        model = Net.Resnet.ResNet101(10)
+    model = model.to(device)
+    for _, p in model.named_parameters():
+        dist.all_reduce(p.data, op=dist.ReduceOp.SUM)
+        p.data /= float(world)
+    optimizer = torch.optim.SGD(model.parameters(), lr=dbs.lr, momentum=0.9)
+    criterion = torch.nn.functional.cross_entropy
+    nodes_time = np.array([1.0 for _ in range(world)])
+    partition = np.array([1.0 / world for _ in range(world)])
+
+    def epoch(e, n_steps, timed):
+        nonlocal partition, nodes_time
+        if dbs.dbs_enabled:
+            partition = dbs.get_size(nodes_time, partition)
+        n_holder["n"] = a.batch * (n_steps + 2)
+        train_set, _, bsz = dataloader.partition_dataset(a.dataset, partition, rank, a.batch, 1234)
+        loader = itertools.islice(iter(train_set), n_steps)
+        if timed:
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        t_train, t_sync, loss = dbs.train(loader, model, optimizer, criterion, e, n_steps, partition)
+        ms = 0.0
+        if timed:
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+        if dbs.dbs_enabled:
+            nodes_time = np.array(dbs.time_allreduce(torch.tensor([t_train], dtype=torch.float32).cpu(), rank, world))
+        return ms, int(bsz), t_sync, loss
+
+    from dynamic_load_balance_distributeddnn_b200.utils import ClockSampler
+    epoch(0, W, False)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms, bsz, t_sync, loss = epoch(1, K, True)
+    clk = clocks.stop() if rank == 0 else {}
+    ms = max_over_ranks(ms, device, world)
+    global_bs = int(sum_over_ranks(float(bsz), device, world))
+    value = global_bs * K / (ms * 1e-3)
+    out = {
+        "metric": METRIC if a.model == "densenet" else f"{a.model}_{a.dataset}_images_per_sec",
+        "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "fp32", "data": "synthetic (CIFAR-10-shape, random-init weights)", "impl": "reference",
+        "config": {"model": a.model, "global_batch": a.batch, "effective_global_batch": global_bs, "parallelism": f"dp{world}",
+                   "backend": "cpu:gloo,cuda:nccl", "partition": [float(x) for x in partition],
+                   "throttle": {"rank": world - 1, "ms_per_step": throttle} if throttle > 0 else None,
+                   "l2": "per-step working set exceeds L2"},
+        "e2e": {"value": round(value, 2), "unit": "images/s", "h2d_bytes_per_step": int(bsz) * 3 * 32 * 32 * 4 + int(bsz) * 8,
+                "d2h_bytes_per_step": 8, "note": "the reference has no device-only path: its step always includes its DataLoader"},
+        "gpu_launches": 0,
+        "straggler_wait_ms_per_step": round(1e3 * t_sync / K, 4),
+        "clocks": {"sm_mhz": clk.get("sm_mhz"), "sm_max_mhz": clk.get("sm_max_mhz"), "reasons": clk.get("reasons", [])},
+    }
+    dist.destroy_process_group()
+    return out if rank == 0 else {}
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        try:
+            out = run_reference(a)
+        except Exception as e:          # noqa: BLE001
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            out = {"impl": "reference", "unavailable": f"reference run failed: {e!r}"[:300]}
+            if int(os.environ.get("RANK", "0")) != 0:
+                out = {}
+    else:
+        out = run_ours(a)
+    if out:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,176 @@
+"""Numerics of the hand-written sm_100a kernels against plain PyTorch fp32 references (run on the B200
+box: ``gpurun -- python -m pytest tests -m gpu``)."""
+import ctypes
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nat():
+    from dynamic_load_balance_distributeddnn_b200.ops import _native
+    assert _native.available(), "native library must be built and loadable on the GPU box"
+    return _native
+
+
+def _cl(x):
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape,groups", [((4, 64, 32, 32), 32), ((3, 128, 16, 16), 32), ((5, 96, 8, 8), 8),
+                                          ((2, 1024, 4, 4), 32), ((2, 20, 7, 5), 4), ((2, 32, 9, 9), 32)])
+@pytest.mark.parametrize("relu,res", [(True, False), (False, False), (True, True)])
+def test_group_norm_act_fwd_bwd(nat, dtype, shape, groups, relu, res):
+    from dynamic_load_balance_distributeddnn_b200 import ops
+    torch.manual_seed(0)
+    dev = "cuda"
+    x = _cl(torch.randn(shape, device=dev) * 2 + 0.5).to(dtype).requires_grad_(True)
+    w = (torch.rand(shape[1], device=dev) + 0.5).requires_grad_(True)
+    b = (torch.randn(shape[1], device=dev) * 0.1).requires_grad_(True)
+    r = _cl(torch.randn(shape, device=dev)).to(dtype).requires_grad_(True) if res else None
+    y = ops.group_norm_act(x, groups, w, b, 1e-5, relu, r)
+    gy = _cl(torch.randn(shape, device=dev)).to(dtype)
+    y.backward(gy)
+    xr = x.detach().float().requires_grad_(True)
+    wr, br = w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    rr = r.detach().float().requires_grad_(True) if res else None
+    yr = ops.group_norm_act_reference(xr, groups, wr, br, 1e-5, relu, rr)
+    yr.backward(gy.float())
+    tol = 2e-4 if dtype == torch.float32 else 3e-2
+    assert torch.allclose(y.float(), yr, atol=tol, rtol=tol), (y.float() - yr).abs().max()
+    gtol = 1e-3 if dtype == torch.float32 else 6e-2
+    assert torch.allclose(x.grad.float(), xr.grad, atol=gtol, rtol=gtol), (x.grad.float() - xr.grad).abs().max()
+    scale = max(1.0, float(wr.grad.abs().max()))
+    assert float((w.grad - wr.grad).abs().max()) < (2e-3 if dtype == torch.float32 else 5e-2) * scale
+    assert float((b.grad - br.grad).abs().max()) < (2e-3 if dtype == torch.float32 else 5e-2) * max(1.0, float(br.grad.abs().max()))
+    if res:
+        assert torch.allclose(r.grad.float(), rr.grad, atol=gtol, rtol=gtol)
+
+
+def test_group_norm_on_channel_slice(nat):
+    """Channel slices of a wider NHWC buffer (DenseNet concat buffer) are read in place."""
+    from dynamic_load_balance_distributeddnn_b200 import ops
+    torch.manual_seed(1)
+    buf = _cl(torch.randn(3, 256, 8, 8, device="cuda")).bfloat16()
+    x = buf[:, 64:192]
+    w = torch.rand(128, device="cuda") + 0.5
+    b = torch.randn(128, device="cuda")
+    y = ops.group_norm_act(x, 32, w, b)
+    yr = ops.group_norm_act_reference(x.float(), 32, w, b)
+    assert torch.allclose(y.float(), yr, atol=3e-2, rtol=3e-2)
+
+
+def test_pack_sumsq_sgd(nat):
+    from dynamic_load_balance_distributeddnn_b200.models import build_model
+    from dynamic_load_balance_distributeddnn_b200.parallel import FlatState, SingleComm
+    torch.manual_seed(0)
+    m_ref = build_model("resnet18", 10).cuda()
+    m = build_model("resnet18", 10)
+    m.load_state_dict(m_ref.state_dict())
+    flat = FlatState(m, "cuda", torch.float32, SingleComm(), lr=0.1, momentum=0.9, clip_norm=0.5)
+    flat.set_weights([1.0])
+    opt = torch.optim.SGD(m_ref.parameters(), lr=0.1, momentum=0.9)
+    for it in range(3):
+        x = torch.randn(4, 3, 32, 32, device="cuda")
+        y = torch.randint(0, 10, (4,), device="cuda")
+        for mod in (m, m_ref):
+            mod.train()
+        F.cross_entropy(m(x), y).backward()
+        F.cross_entropy(m_ref(x), y).backward()
+        torch.nn.utils.clip_grad_norm_(m_ref.parameters(), 0.5)
+        opt.step(); opt.zero_grad()
+        flat.reduce_and_step(0); flat.zero_grad()
+    for p, q in zip(m.parameters(), m_ref.parameters()):
+        assert torch.allclose(p, q, atol=3e-4, rtol=1e-3), (p - q).abs().max()
+
+
+def test_bf16_shadow_tracks_master(nat):
+    from dynamic_load_balance_distributeddnn_b200.models import build_model
+    from dynamic_load_balance_distributeddnn_b200.parallel import FlatState, SingleComm
+    m = build_model("densenet", 10)
+    flat = FlatState(m, "cuda", torch.bfloat16, SingleComm(), lr=0.05)
+    flat.set_weights([1.0])
+    assert m.conv1.weight.dtype == torch.bfloat16 and m.dense1[0].gn1.weight.dtype == torch.float32
+    x = torch.randn(4, 3, 32, 32, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+    F.cross_entropy(m(x).float(), torch.randint(0, 10, (4,), device="cuda")).backward()
+    flat.reduce_and_step(0)
+    torch.cuda.synchronize()
+    assert torch.equal(flat.shadow, flat.master.bfloat16())
+    assert flat.mom.abs().sum() > 0
+
+
+def test_augment_matches_reference_semantics(nat):
+    from dynamic_load_balance_distributeddnn_b200 import ops
+    u8 = torch.randint(0, 256, (16, 32, 32, 3), dtype=torch.uint8, device="cuda")
+    mean, std = (0.4914, 0.4822, 0.4465), (0.2023, 0.1994, 0.2010)
+    x = ops.augment(u8, mean, std, 0, False, dtype=torch.float32)
+    ref = (u8.float() / 255 - torch.tensor(mean, device="cuda")) / torch.tensor(std, device="cuda")
+    assert torch.allclose(x.permute(0, 2, 3, 1), ref, atol=1e-5)
+    xa = ops.augment(u8, mean, std, 4, True, seed=1, step=2, dtype=torch.bfloat16)
+    assert xa.shape == (16, 3, 32, 32) and xa.dtype == torch.bfloat16 and torch.isfinite(xa.float()).all()
+    # every output row is either padding (normalised zero) or a (possibly flipped/shifted) copy of the source
+    z = ((0 - torch.tensor(mean)) / torch.tensor(std)).bfloat16().float()
+    vals = xa.float().permute(0, 2, 3, 1)[0, 0, 0].cpu()
+    src = ((u8[0].float() / 255).cpu() - torch.tensor(mean)) / torch.tensor(std)
+    assert torch.allclose(vals, z, atol=2e-2) or ((src.bfloat16().float() - vals).abs().sum(-1) < 5e-2).any()
+
+
+def test_single_rank_collectives(nat):
+    from dynamic_load_balance_distributeddnn_b200.parallel import SymmComm
+    c = SymmComm("cuda")
+    gin, gout = c.alloc_grad_buffers(1 << 16, torch.float32, "cuda")
+    gin.copy_(torch.randn(1 << 16, device="cuda"))
+    w = torch.tensor([0.5], device="cuda")
+    for algo in ("oneshot", "twoshot"):
+        c.algo = algo
+        gout.zero_()
+        c.allreduce_buckets(gin, gout, [(0, 1 << 15), (1 << 15, 1 << 15)], w)
+        torch.cuda.synchronize()
+        assert torch.allclose(gout, 0.5 * gin)
+    c.barrier()
+    assert c.gather_times(1.25) == [1.25]
+    c.check_errors()
+    c.close()
+
+
+def test_whole_step_cuda_graph_matches_eager(nat, tmp_path):
+    """Graph replay and eager execution of the same steps give the same parameters."""
+    from dynamic_load_balance_distributeddnn_b200.config import DBSConfig
+    from dynamic_load_balance_distributeddnn_b200.engine import Trainer
+    from dynamic_load_balance_distributeddnn_b200.utils import init_logger
+    res = []
+    for graphs in (False, True):
+        cfg = DBSConfig(debug=False, world_size=1, batch_size=32, model="resnet18", dataset="cifar10", synthetic=True,
+                        train_samples=32 * 8, test_samples=64, epoch_size=1, validate=False, cuda_graphs=graphs,
+                        dtype="fp32", log_dir=str(tmp_path / f"l{int(graphs)}"), stats_dir=str(tmp_path / "s"))
+        t = Trainer(cfg, 0, 1, "cuda:0", init_logger(cfg, 0, stream=False))
+        t.train_set.pad, t.train_set.flip = 0, False          # deterministic inputs
+        for s in range(6):
+            xb, yb = t.stager.stage(list(range(s * 32, s * 32 + 32)))
+            t.train_step(xb, yb)
+            t.stager.release()
+        torch.cuda.synchronize()
+        assert graphs == bool(t._graphs)
+        res.append((t.flat.master.clone(), float(t.loss_acc.item())))
+        t.close()
+    assert abs(res[0][1] - res[1][1]) < 2e-2 * abs(res[0][1])
+    assert float((res[0][0] - res[1][0]).abs().max()) < 5e-3
+
+
+def test_densenet_trains_bf16(nat, tmp_path):
+    from dynamic_load_balance_distributeddnn_b200.config import DBSConfig
+    from dynamic_load_balance_distributeddnn_b200.engine import Trainer
+    from dynamic_load_balance_distributeddnn_b200.utils import init_logger
+    cfg = DBSConfig(debug=False, world_size=1, batch_size=64, model="densenet", dataset="cifar10", synthetic=True,
+                    train_samples=64 * 12, test_samples=128, epoch_size=2, validate=True, learning_rate=0.05,
+                    log_dir=str(tmp_path / "l"), stats_dir=str(tmp_path / "s"))
+    t = Trainer(cfg, 0, 1, "cuda:0", init_logger(cfg, 0, stream=False))
+    rec = t.run()
+    assert rec.data["train_loss"][-1] < rec.data["train_loss"][0]
+    assert math.isfinite(rec.data["val_loss"][-1])
+    t.close()
