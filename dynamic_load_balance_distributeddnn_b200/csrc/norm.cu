@@ -27,7 +27,7 @@ constexpr int kThreads = 256;
 template <typename T, int V, int MODE>
 __global__ void __launch_bounds__(kThreads)
 nc_reduce2_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy,
-                  const T* __restrict__ y, int64_t ldy, float* __restrict__ table,
+                  const T* __restrict__ y, int64_t ldy, float* __restrict__ table, int64_t table_ns,
                   int HW, int C, int rows_per_block) {
   extern __shared__ float smem[];            // [2*C]
   const int n = blockIdx.y;
@@ -65,26 +65,40 @@ nc_reduce2_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy
           for (int i = 0; i < V; ++i) { a0[i] += gv[i]; a1[i] += gv[i] * xv[i]; }
         }
       }
+      // lanes of a warp that own the same channels sit `lanes` apart: fold them first
+      bool owner = true;
+      if (lanes < 32 && (lanes & (lanes - 1)) == 0) {
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        atomicAdd(&smem[2 * (c + i)], a0[i]);
-        atomicAdd(&smem[2 * (c + i) + 1], a1[i]);
+        for (int i = 0; i < V; ++i) {
+          for (int o = lanes; o < 32; o <<= 1) {
+            a0[i] += __shfl_xor_sync(0xffffffffu, a0[i], o);
+            a1[i] += __shfl_xor_sync(0xffffffffu, a1[i], o);
+          }
+        }
+        owner = (threadIdx.x & 31) < lanes;
+      }
+      if (owner) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          atomicAdd(&smem[2 * (c + i)], a0[i]);
+          atomicAdd(&smem[2 * (c + i) + 1], a1[i]);
+        }
       }
     }
   }
   __syncthreads();
-  float* dst = table + (int64_t)n * C * 2;
+  float* dst = table + (int64_t)n * table_ns;
   for (int i = threadIdx.x; i < 2 * C; i += kThreads) atomicAdd(&dst[i], smem[i]);
 }
 
 // ---------------------------------------------------------------------------------------------
 // group statistics from the table:  mean/rstd [N][G]
-__global__ void gn_finalize_kernel(const float* __restrict__ table, float* __restrict__ mean,
+__global__ void gn_finalize_kernel(const float* __restrict__ table, int64_t table_ns, float* __restrict__ mean,
                                    float* __restrict__ rstd, int N, int C, int G, int HW, float eps) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * G) return;
   const int n = idx / G, g = idx % G, cpg = C / G;
-  const float* t = table + ((int64_t)n * C + (int64_t)g * cpg) * 2;
+  const float* t = table + (int64_t)n * table_ns + (int64_t)g * cpg * 2;
   float s = 0.f, ss = 0.f;
   for (int i = 0; i < cpg; ++i) { s += t[2 * i]; ss += t[2 * i + 1]; }
   const float m = 1.f / ((float)cpg * (float)HW);
@@ -148,7 +162,7 @@ gn_bwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
                     const T* __restrict__ y, int64_t ldy, T* __restrict__ dx, int64_t lddx,
                     T* __restrict__ dres, int64_t lddr, const float* __restrict__ gamma,
                     const float* __restrict__ mean, const float* __restrict__ rstd,
-                    const float* __restrict__ table, int HW, int C, int G, int rows_per_block) {
+                    const float* __restrict__ table, int64_t table_ns, int HW, int C, int G, int rows_per_block) {
   extern __shared__ float smem[];            // k1[C], k2[C], k3[C], s1[G], s2[G]
   float* k1 = smem;
   float* k2 = smem + C;
@@ -156,7 +170,7 @@ gn_bwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
   float* s1 = smem + 3 * C;
   float* s2 = s1 + G;
   const int n = blockIdx.y, cpg = C / G;
-  const float* t = table + (int64_t)n * C * 2;
+  const float* t = table + (int64_t)n * table_ns;
   for (int g = threadIdx.x; g < G; g += kThreads) {
     const float mu = mean[n * G + g], r = rstd[n * G + g];
     float a = 0.f, b = 0.f;
@@ -210,21 +224,30 @@ gn_bwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
   }
 }
 
-// dgamma[c] = sum_n rstd*(B - mu*A), dbeta[c] = sum_n A
-__global__ void gn_param_grad_kernel(const float* __restrict__ table, const float* __restrict__ mean,
+// dgamma[c] = sum_n rstd*(B - mu*A), dbeta[c] = sum_n A.   Block = 32 channels x 8 sample-lanes.
+__global__ void __launch_bounds__(256) gn_param_grad_kernel(const float* __restrict__ table, int64_t table_ns, const float* __restrict__ mean,
                                      const float* __restrict__ rstd, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta, int N, int C, int G) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const int g = c / (C / G);
+  __shared__ float sg[8][33], sb[8][33];
+  const int cx = threadIdx.x & 31, ny = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   float dg = 0.f, db = 0.f;
-  for (int n = 0; n < N; ++n) {
-    const float A = table[((int64_t)n * C + c) * 2], B = table[((int64_t)n * C + c) * 2 + 1];
-    dg += rstd[n * G + g] * (B - mean[n * G + g] * A);
-    db += A;
+  if (c < C) {
+    const int g = c / (C / G);
+    for (int n = ny; n < N; n += 8) {
+      const float2 t = *reinterpret_cast<const float2*>(table + (int64_t)n * table_ns + 2 * c);
+      dg += rstd[n * G + g] * (t.y - mean[n * G + g] * t.x);
+      db += t.x;
+    }
   }
-  dgamma[c] = dg;
-  dbeta[c] = db;
+  sg[ny][cx] = dg; sb[ny][cx] = db;
+  __syncthreads();
+  if (ny == 0 && c < C) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { dg += sg[k][cx]; db += sb[k][cx]; }
+    dgamma[c] = dg;
+    dbeta[c] = db;
+  }
 }
 
 inline void grid_for(int N, int HW, int C, int V, dim3& grid, int& rows_per_block) {
@@ -242,14 +265,14 @@ inline void grid_for(int N, int HW, int C, int V, dim3& grid, int& rows_per_bloc
 
 template <typename T, int V>
 int reduce2_launch(int mode, const void* x, int64_t ldx, const void* dy, int64_t lddy, const void* y,
-                   int64_t ldy, float* table, int N, int HW, int C, cudaStream_t st) {
+                   int64_t ldy, float* table, int64_t table_ns, int N, int HW, int C, cudaStream_t st) {
   dim3 grid; int rpb;
   grid_for(N, HW, C, V, grid, rpb);
   const size_t sm = 2 * C * sizeof(float);
   const T* X = (const T*)x; const T* DY = (const T*)dy; const T* Y = (const T*)y;
-  if (mode == 0) nc_reduce2_kernel<T, V, 0><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, HW, C, rpb);
-  else if (mode == 1) nc_reduce2_kernel<T, V, 1><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, HW, C, rpb);
-  else nc_reduce2_kernel<T, V, 2><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, HW, C, rpb);
+  if (mode == 0) nc_reduce2_kernel<T, V, 0><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb);
+  else if (mode == 1) nc_reduce2_kernel<T, V, 1><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb);
+  else nc_reduce2_kernel<T, V, 2><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb);
   return dlb_post_launch();
 }
 
@@ -271,14 +294,14 @@ int fwd_apply_launch(const void* x, int64_t ldx, const void* res, int64_t ldr, v
 template <typename T, int V>
 int bwd_apply_launch(const void* x, int64_t ldx, const void* dy, int64_t lddy, const void* y, int64_t ldy,
                      void* dx, int64_t lddx, void* dres, int64_t lddr, const float* gamma,
-                     const float* mean, const float* rstd, const float* table, int N, int HW, int C,
+                     const float* mean, const float* rstd, const float* table, int64_t table_ns, int N, int HW, int C,
                      int G, int relu, int acc, cudaStream_t st) {
   dim3 grid; int rpb;
   grid_for(N, HW, C, V, grid, rpb);
   const size_t sm = (3 * C + 2 * G) * sizeof(float);
   const T* X = (const T*)x; const T* DY = (const T*)dy; const T* Y = (const T*)y;
   T* DX = (T*)dx; T* DR = (T*)dres;
-#define GO(RL, RS, AC) gn_bwd_apply_kernel<T, V, RL, RS, AC><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, DX, lddx, DR, lddr, gamma, mean, rstd, table, HW, C, G, rpb)
+#define GO(RL, RS, AC) gn_bwd_apply_kernel<T, V, RL, RS, AC><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, DX, lddx, DR, lddr, gamma, mean, rstd, table, table_ns, HW, C, G, rpb)
   if (relu) {
     if (dres) { if (acc) GO(true, true, true); else GO(true, true, false); }
     else { if (acc) GO(true, false, true); else GO(true, false, false); }
@@ -308,22 +331,51 @@ inline bool vec_ok(int dtype, int C, std::initializer_list<int64_t> lds, std::in
            else { using T = float; constexpr int V = 1; CALL; } }                            \
   } while (0)
 
-// table must hold N*C*2 floats; it is zeroed here.
+// table: fp32 [N][table_ns] with (q0,q1) pairs for C channels starting at `table`; zeroed here.
 DLB_API int dlb_nc_reduce2(int mode, int dtype, const void* x, int64_t ldx, const void* dy, int64_t lddy,
-                           const void* y, int64_t ldy, float* table, int N, int HW, int C, void* stream) {
+                           const void* y, int64_t ldy, float* table, int64_t table_ns, int N, int HW, int C, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (C > 6000) return -2;
-  cudaMemsetAsync(table, 0, (size_t)N * C * 2 * sizeof(float), st);
+  if (table_ns <= 0) table_ns = 2 * (int64_t)C;
+  cudaMemset2DAsync(table, (size_t)table_ns * sizeof(float), 0, (size_t)C * 2 * sizeof(float), (size_t)N, st);
   const bool vec = vec_ok(dtype, C, {ldx, dy ? lddy : 0, y ? ldy : 0}, {x, dy, y});
   int rc = 0;
-  DISPATCH(dtype, vec, (rc = reduce2_launch<T, V>(mode, x, ldx, dy, lddy, y, ldy, table, N, HW, C, st)));
+  DISPATCH(dtype, vec, (rc = reduce2_launch<T, V>(mode, x, ldx, dy, lddy, y, ldy, table, table_ns, N, HW, C, st)));
   return rc;
 }
 
-DLB_API int dlb_gn_finalize(const float* table, float* mean, float* rstd, int N, int C, int G, int HW,
+DLB_API int dlb_gn_finalize(const float* table, int64_t table_ns, float* mean, float* rstd, int N, int C, int G, int HW,
                             float eps, void* stream) {
   const int total = N * G;
-  gn_finalize_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(table, mean, rstd, N, C, G, HW, eps);
+  if (table_ns <= 0) table_ns = 2 * (int64_t)C;
+  gn_finalize_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(table, table_ns, mean, rstd, N, C, G, HW, eps);
+  return dlb_post_launch();
+}
+
+DLB_API int dlb_gn_fwd_apply(int dtype, const void* x, int64_t ldx, const void* res, int64_t ldr, void* y, int64_t ldy,
+                             const float* gamma, const float* beta, const float* mean, const float* rstd,
+                             int N, int HW, int C, int G, int relu, void* stream) {
+  int rc = 0;
+  const bool vec = vec_ok(dtype, C, {ldx, res ? ldr : 0, ldy}, {x, res, y});
+  DISPATCH(dtype, vec, (rc = fwd_apply_launch<T, V>(x, ldx, res, ldr, y, ldy, gamma, beta, mean, rstd, N, HW, C, G, relu, (cudaStream_t)stream)));
+  return rc;
+}
+
+DLB_API int dlb_gn_bwd_apply(int dtype, const void* x, int64_t ldx, const void* dy, int64_t lddy, const void* y, int64_t ldy,
+                             void* dx, int64_t lddx, void* dres, int64_t lddr, const float* gamma, const float* mean,
+                             const float* rstd, const float* table, int64_t table_ns, int N, int HW, int C, int G,
+                             int relu, int acc, void* stream) {
+  int rc = 0;
+  if (table_ns <= 0) table_ns = 2 * (int64_t)C;
+  const bool vec = vec_ok(dtype, C, {ldx, lddy, relu ? ldy : 0, lddx, dres ? lddr : 0}, {x, dy, relu ? y : nullptr, dx, dres});
+  DISPATCH(dtype, vec, (rc = bwd_apply_launch<T, V>(x, ldx, dy, lddy, y, ldy, dx, lddx, dres, lddr, gamma, mean, rstd, table, table_ns, N, HW, C, G, relu, acc, (cudaStream_t)stream)));
+  return rc;
+}
+
+DLB_API int dlb_gn_param_grad(const float* table, int64_t table_ns, const float* mean, const float* rstd, float* dgamma,
+                              float* dbeta, int N, int C, int G, void* stream) {
+  if (table_ns <= 0) table_ns = 2 * (int64_t)C;
+  gn_param_grad_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(table, table_ns, mean, rstd, dgamma, dbeta, N, C, G);
   return dlb_post_launch();
 }
 
@@ -332,17 +384,14 @@ DLB_API int dlb_gn_forward(int dtype, const void* x, int64_t ldx, const void* re
                            int64_t ldy, const float* gamma, const float* beta, float* mean, float* rstd,
                            float* table, int N, int HW, int C, int G, float eps, int relu,
                            int stats_ready, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
   int rc = 0;
   if (!stats_ready) {
-    rc = dlb_nc_reduce2(0, dtype, x, ldx, nullptr, 0, nullptr, 0, table, N, HW, C, stream);
+    rc = dlb_nc_reduce2(0, dtype, x, ldx, nullptr, 0, nullptr, 0, table, 0, N, HW, C, stream);
     if (rc) return rc;
-    rc = dlb_gn_finalize(table, mean, rstd, N, C, G, HW, eps, stream);
+    rc = dlb_gn_finalize(table, 0, mean, rstd, N, C, G, HW, eps, stream);
     if (rc) return rc;
   }
-  const bool vec = vec_ok(dtype, C, {ldx, res ? ldr : 0, ldy}, {x, res, y});
-  DISPATCH(dtype, vec, (rc = fwd_apply_launch<T, V>(x, ldx, res, ldr, y, ldy, gamma, beta, mean, rstd, N, HW, C, G, relu, st)));
-  return rc;
+  return dlb_gn_fwd_apply(dtype, x, ldx, res, ldr, y, ldy, gamma, beta, mean, rstd, N, HW, C, G, relu, stream);
 }
 
 // Backward: reduce (dz, dz*x) + apply (+ param grads). dres may be null; acc!=0 accumulates into dx.
@@ -351,15 +400,10 @@ DLB_API int dlb_gn_backward(int dtype, const void* x, int64_t ldx, const void* d
                             const float* gamma, const float* mean, const float* rstd, float* table,
                             float* dgamma, float* dbeta, int N, int HW, int C, int G, int relu, int acc,
                             void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  int rc = dlb_nc_reduce2(relu ? 1 : 2, dtype, x, ldx, dy, lddy, y, ldy, table, N, HW, C, stream);
+  int rc = dlb_nc_reduce2(relu ? 1 : 2, dtype, x, ldx, dy, lddy, y, ldy, table, 0, N, HW, C, stream);
   if (rc) return rc;
-  const bool vec = vec_ok(dtype, C, {ldx, lddy, relu ? ldy : 0, lddx, dres ? lddr : 0}, {x, dy, relu ? y : nullptr, dx, dres});
-  DISPATCH(dtype, vec, (rc = bwd_apply_launch<T, V>(x, ldx, dy, lddy, y, ldy, dx, lddx, dres, lddr, gamma, mean, rstd, table, N, HW, C, G, relu, acc, st)));
+  rc = dlb_gn_bwd_apply(dtype, x, ldx, dy, lddy, y, ldy, dx, lddx, dres, lddr, gamma, mean, rstd, table, 0, N, HW, C, G, relu, acc, stream);
   if (rc) return rc;
-  if (dgamma) {
-    gn_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(table, mean, rstd, dgamma, dbeta, N, C, G);
-    rc = dlb_post_launch();
-  }
+  if (dgamma) rc = dlb_gn_param_grad(table, 0, mean, rstd, dgamma, dbeta, N, C, G, stream);
   return rc;
 }

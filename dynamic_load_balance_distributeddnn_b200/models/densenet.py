@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import ops
 from .layers import Conv2d, GroupNormAct, Linear
 
 _GROUPS = 32
@@ -47,8 +48,11 @@ class DenseStage(nn.Sequential):
 
     def forward(self, x):
         if self.fused and x.is_cuda:
-            from ..ops import dense_block
-            if dense_block.supported(self, x):
+            try:
+                from ..ops import dense_block
+            except ImportError:
+                dense_block = None
+            if dense_block is not None and dense_block.supported(self, x):
                 return dense_block.run(self, x)
         return super().forward(x)
 
@@ -60,7 +64,9 @@ class Transition(nn.Module):
         self.conv = Conv2d(in_planes, out_planes, kernel_size=1, bias=False)
 
     def forward(self, x):
-        return F.avg_pool2d(self.conv(self.gn(x)), 2)
+        # avg-pool and a 1x1 convolution are both linear and commute: pooling FIRST is the same function
+        # with 4x fewer conv FLOPs / bytes (reference order: conv then pool, Net/Densenet.py:31-32)
+        return self.conv(ops.avg_pool2d(self.gn(x), 2))
 
 
 class DenseNet(nn.Module):
@@ -94,7 +100,7 @@ class DenseNet(nn.Module):
         out = self.trans2(self.dense2(out))
         out = self.trans3(self.dense3(out))
         out = self.dense4(out)
-        out = F.avg_pool2d(self.gn(out), 4).flatten(1)
+        out = ops.avg_pool2d(self.gn(out), 4).flatten(1)
         return self.linear(out)
 
 

@@ -1,0 +1,156 @@
+"""Concat-free execution of a DenseNet dense block (forward + hand-written backward).
+
+The reference grows its feature map with ``torch.cat([out, x], 1)`` in every bottleneck
+(``Net/Densenet.py:20``): 58 full-tensor copies per forward in DenseNet-121 plus, in backward, a strided
+slice + add per layer.  Here a whole stage runs on ONE preallocated NHWC buffer:
+
+* layer *l* reads the channel slice ``[off_l, C_total)`` in place and writes its ``g`` new channels just in
+  front of it (same channel order as the reference's prepending, so weights interchange);
+* per-(sample, channel) sums ``(Σx, Σx²)`` are computed ONCE when a channel is produced and kept in a
+  table; every later GroupNorm over a growing channel set derives its group statistics from the table
+  (``dlb_gn_finalize``) instead of re-reading the buffer — and the transition / classifier GN that follows
+  the block re-uses the same table;
+* the backward walks the layers in reverse, accumulating ``dX`` into one gradient buffer in place
+  (``gn_bwd_apply`` with ``acc=1`` on the slice), so no gradient ``cat``/``narrow``/``add`` kernels run.
+
+Convolutions go through ``ops.conv`` (tcgen05 implicit GEMM when supported, vendor library otherwise).
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+
+from . import _native as nat
+from .norm import _nhwc_view
+
+_CONV_BWD = torch.ops.aten.convolution_backward
+
+
+def supported(stage, x: torch.Tensor) -> bool:
+    if not (x.is_cuda and nat.available() and x.dim() == 4 and x.dtype in (torch.bfloat16, torch.float32)):
+        return False
+    if len(stage) == 0:
+        return False
+    c0 = x.shape[1]
+    g = stage[0].conv2.out_channels
+    return c0 % 8 == 0 and g % 8 == 0 and stage[0].gn1.weight.dtype == torch.float32
+
+
+def _conv_fwd(x, w, pad):
+    return torch.nn.functional.conv2d(x, w if w.dtype == x.dtype else w.to(x.dtype), None, 1, pad)
+
+
+class _DenseBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eps, groups, *params):
+        lib = nat.require()
+        st = nat.stream_ptr(x.device)
+        n_layers = len(params) // 6
+        n, c0, h, w = x.shape
+        hw = h * w
+        g = params[5].shape[0]
+        ct = c0 + n_layers * g
+        dt = nat.dtype_code(x.dtype)
+        buf = torch.empty((n, ct, h, w), dtype=x.dtype, device=x.device).contiguous(memory_format=torch.channels_last)
+        table = torch.empty((n, ct, 2), dtype=torch.float32, device=x.device)
+        tns = 2 * ct
+        buf[:, ct - c0:].copy_(x)
+        esz = buf.element_size()
+
+        def slice_ptr(c_off):
+            return buf.data_ptr() + c_off * esz
+
+        def stats(c_off, c):
+            nat.check(lib.dlb_nc_reduce2(0, dt, slice_ptr(c_off), ct, 0, 0, 0, 0, table.data_ptr() + c_off * 8, tns,
+                                         n, hw, c, st), "dense.stats")
+        stats(ct - c0, c0)
+        saved = []
+        for l in range(n_layers):
+            g1w, g1b, w1, g2w, g2b, w2 = params[6 * l:6 * l + 6]
+            cl = c0 + l * g
+            off = ct - cl
+            mean1 = torch.empty(n * groups, dtype=torch.float32, device=x.device)
+            rstd1 = torch.empty_like(mean1)
+            nat.check(lib.dlb_gn_finalize(table.data_ptr() + off * 8, tns, mean1.data_ptr(), rstd1.data_ptr(), n, cl, groups,
+                                          hw, eps, st), "dense.fin1")
+            xhat = torch.empty((n, cl, h, w), dtype=x.dtype, device=x.device).contiguous(memory_format=torch.channels_last)
+            nat.check(lib.dlb_gn_fwd_apply(dt, slice_ptr(off), ct, 0, 0, xhat.data_ptr(), cl, g1w.data_ptr(), g1b.data_ptr(),
+                                           mean1.data_ptr(), rstd1.data_ptr(), n, hw, cl, groups, 1, st), "dense.apply1")
+            y = _conv_fwd(xhat, w1, 0)
+            cm = y.shape[1]
+            mean2 = torch.empty(n * groups, dtype=torch.float32, device=x.device)
+            rstd2 = torch.empty_like(mean2)
+            t2 = torch.empty(n * cm * 2, dtype=torch.float32, device=x.device)
+            yv, _, _, _, ldy = _nhwc_view(y)
+            yhat = torch.empty_like(yv, memory_format=torch.channels_last)
+            nat.check(lib.dlb_gn_forward(dt, yv.data_ptr(), ldy, 0, 0, yhat.data_ptr(), cm, g2w.data_ptr(), g2b.data_ptr(),
+                                         mean2.data_ptr(), rstd2.data_ptr(), t2.data_ptr(), n, hw, cm, groups, eps, 1, 0, st),
+                      "dense.gn2")
+            new = _conv_fwd(yhat, w2, 1)
+            buf[:, off - g:off].copy_(new)
+            stats(off - g, g)
+            saved += [xhat, yv, yhat, mean1, rstd1, mean2, rstd2]
+        ctx.save_for_backward(buf, *params, *saved)
+        ctx.cfg = (n_layers, n, c0, h, w, g, ct, groups, eps)
+        ctx.mark_non_differentiable(table)
+        return buf, table
+
+    @staticmethod
+    def backward(ctx, dout, _dtable):
+        lib = nat.require()
+        n_layers, n, c0, h, w, g, ct, groups, eps = ctx.cfg
+        tensors = ctx.saved_tensors
+        buf = tensors[0]
+        params = tensors[1:1 + 6 * n_layers]
+        saved = tensors[1 + 6 * n_layers:]
+        st = nat.stream_ptr(buf.device)
+        dt = nat.dtype_code(buf.dtype)
+        hw = h * w
+        esz = buf.element_size()
+        dbuf = dout.contiguous(memory_format=torch.channels_last).clone()
+        grads: List = [None] * (6 * n_layers)
+        for l in reversed(range(n_layers)):
+            g1w, g1b, w1, g2w, g2b, w2 = params[6 * l:6 * l + 6]
+            xhat, y, yhat, mean1, rstd1, mean2, rstd2 = saved[7 * l:7 * l + 7]
+            cl = c0 + l * g
+            off = ct - cl
+            cm = y.shape[1]
+            dnew = dbuf[:, off - g:off].contiguous(memory_format=torch.channels_last)
+            w2c = w2 if w2.dtype == yhat.dtype else w2.to(yhat.dtype)
+            dyhat, dw2, _ = _CONV_BWD(dnew, yhat, w2c, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [True, True, False])
+            dyhat = dyhat.contiguous(memory_format=torch.channels_last)
+            # GN2 + ReLU backward
+            dy = torch.empty_like(y, memory_format=torch.channels_last)
+            t2 = torch.empty(n * cm * 2, dtype=torch.float32, device=buf.device)
+            dg2 = torch.empty(cm, dtype=torch.float32, device=buf.device)
+            db2 = torch.empty(cm, dtype=torch.float32, device=buf.device)
+            nat.check(lib.dlb_gn_backward(dt, y.data_ptr(), cm, dyhat.data_ptr(), cm, yhat.data_ptr(), cm, dy.data_ptr(), cm,
+                                          0, 0, g2w.data_ptr(), mean2.data_ptr(), rstd2.data_ptr(), t2.data_ptr(),
+                                          dg2.data_ptr(), db2.data_ptr(), n, hw, cm, groups, 1, 0, st), "dense.gn2_bwd")
+            w1c = w1 if w1.dtype == xhat.dtype else w1.to(xhat.dtype)
+            dxhat, dw1, _ = _CONV_BWD(dy, xhat, w1c, None, [1, 1], [0, 0], [1, 1], False, [0, 0], 1, [True, True, False])
+            dxhat = dxhat.contiguous(memory_format=torch.channels_last)
+            # GN1 + ReLU backward, accumulated in place into the gradient buffer slice
+            t1 = torch.empty(n * cl * 2, dtype=torch.float32, device=buf.device)
+            dg1 = torch.empty(cl, dtype=torch.float32, device=buf.device)
+            db1 = torch.empty(cl, dtype=torch.float32, device=buf.device)
+            xs = buf.data_ptr() + off * esz
+            dxs = dbuf.data_ptr() + off * esz
+            nat.check(lib.dlb_gn_backward(dt, xs, ct, dxhat.data_ptr(), cl, xhat.data_ptr(), cl, dxs, ct, 0, 0,
+                                          g1w.data_ptr(), mean1.data_ptr(), rstd1.data_ptr(), t1.data_ptr(),
+                                          dg1.data_ptr(), db1.data_ptr(), n, hw, cl, groups, 1, 1, st), "dense.gn1_bwd")
+            grads[6 * l:6 * l + 6] = [dg1.to(g1w.dtype), db1.to(g1b.dtype), dw1.to(w1.dtype), dg2.to(g2w.dtype),
+                                      db2.to(g2b.dtype), dw2.to(w2.dtype)]
+        dx = dbuf[:, ct - c0:]
+        return (dx, None, None, *grads)
+
+
+def run(stage, x: torch.Tensor) -> torch.Tensor:
+    params = []
+    for blk in stage:
+        params += [blk.gn1.weight, blk.gn1.bias, blk.conv1.weight, blk.gn2.weight, blk.gn2.bias, blk.conv2.weight]
+    first = stage[0]
+    out, table = _DenseBlockFn.apply(x, float(first.gn1.eps), int(first.gn1.num_groups), *params)
+    out._dlb_nc_table = table           # (Σx, Σx²) per (sample, channel): lets the next GroupNorm skip its stats pass
+    return out

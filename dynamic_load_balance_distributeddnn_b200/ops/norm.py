@@ -56,7 +56,7 @@ def _nhwc_view(x: torch.Tensor):
 
 class _GNActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, num_groups, eps, relu):
+    def forward(ctx, x, weight, bias, residual, num_groups, eps, relu, nc_table=None):
         lib = nat.require()
         x, n, hw, c, ldx = _nhwc_view(x)
         y = torch.empty_like(x, memory_format=torch.channels_last)
@@ -68,13 +68,20 @@ class _GNActFn(torch.autograd.Function):
         g = num_groups
         mean = torch.empty(n * g, dtype=torch.float32, device=x.device)
         rstd = torch.empty(n * g, dtype=torch.float32, device=x.device)
-        table = torch.empty(n * c * 2, dtype=torch.float32, device=x.device)
         w32 = weight if weight.dtype == torch.float32 else weight.float()
         b32 = bias if bias.dtype == torch.float32 else bias.float()
+        st = nat.stream_ptr(x.device)
+        if nc_table is not None and nc_table.shape[0] == n and nc_table.shape[1] == c:
+            # per-(sample, channel) sums were produced upstream (dense block): no stats pass over x
+            nat.check(lib.dlb_gn_finalize(nc_table.data_ptr(), 2 * c, mean.data_ptr(), rstd.data_ptr(), n, c, g, hw,
+                                          float(eps), st), "gn_finalize")
+            table_ptr, ready = 0, 1
+        else:
+            table = torch.empty(n * c * 2, dtype=torch.float32, device=x.device)
+            table_ptr, ready = table.data_ptr(), 0
         nat.check(lib.dlb_gn_forward(nat.dtype_code(x.dtype), x.data_ptr(), ldx, res_p, ldr, y.data_ptr(), ldy,
                                      w32.data_ptr(), b32.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                     table.data_ptr(), n, hw, c, g, float(eps), int(relu), 0,
-                                     nat.stream_ptr(x.device)), "gn_forward")
+                                     table_ptr, n, hw, c, g, float(eps), int(relu), ready, st), "gn_forward")
         ctx.save_for_backward(x, y if relu else None, w32, mean, rstd)
         ctx.cfg = (n, hw, c, g, ldx, ldy, bool(relu), residual is not None, weight.dtype, bias.dtype)
         return y
@@ -97,11 +104,11 @@ class _GNActFn(torch.autograd.Function):
                                       w32.data_ptr(), mean.data_ptr(), rstd.data_ptr(), table.data_ptr(),
                                       dgamma.data_ptr(), dbeta.data_ptr(), n, hw, c, g, int(relu), 0,
                                       nat.stream_ptr(x.device)), "gn_backward")
-        return dx, dgamma.to(wdt), dbeta.to(bdt), dres, None, None, None
+        return dx, dgamma.to(wdt), dbeta.to(bdt), dres, None, None, None, None
 
 
 def group_norm_act(x: torch.Tensor, num_groups: int, weight: torch.Tensor, bias: torch.Tensor,
                    eps: float = 1e-5, relu: bool = True, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     if x.is_cuda and nat.available() and x.dtype in (torch.float32, torch.bfloat16) and x.dim() == 4:
-        return _GNActFn.apply(x, weight, bias, residual, num_groups, eps, relu)
+        return _GNActFn.apply(x, weight, bias, residual, num_groups, eps, relu, getattr(x, "_dlb_nc_table", None))
     return group_norm_act_reference(x, num_groups, weight, bias, eps, relu, residual)

@@ -119,7 +119,7 @@ class SymmComm(Comm):
         self._ctx = None
         self._time_ctx = None
         self._counters = torch.zeros(4, dtype=torch.int64, device=self.device)   # [0]=wait_ns, [1]=err flag (int32 view)
-        self._err_view = self._counters[1:2].view(torch.int32)
+        self._err_view = self._counters[1:2].view(torch.int32)[:1]
         flag_bytes = int(self.lib.dlb_comm_flag_words()) * 4
         self._flags = self.alloc.alloc("flags", flag_bytes)
         self._times = self.alloc.alloc("times", 256)

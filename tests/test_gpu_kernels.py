@@ -174,3 +174,49 @@ def test_densenet_trains_bf16(nat, tmp_path):
     assert rec.data["train_loss"][-1] < rec.data["train_loss"][0]
     assert math.isfinite(rec.data["val_loss"][-1])
     t.close()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_avg_pool_matches_torch(nat, dtype):
+    from dynamic_load_balance_distributeddnn_b200 import ops
+    for shape, k in (((3, 64, 8, 8), 2), ((2, 128, 4, 4), 4), ((2, 24, 8, 8), 8), ((2, 20, 6, 6), 2)):
+        x = _cl(torch.randn(shape, device="cuda")).to(dtype).requires_grad_(True)
+        y = ops.avg_pool2d(x, k)
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        xr = x.detach().float().requires_grad_(True)
+        yr = F.avg_pool2d(xr, k)
+        yr.backward(gy.float())
+        tol = 1e-5 if dtype == torch.float32 else 2e-2
+        assert torch.allclose(y.float(), yr, atol=tol, rtol=tol)
+        assert torch.allclose(x.grad.float(), xr.grad, atol=tol, rtol=tol)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-3), (torch.bfloat16, 8e-2)])
+def test_dense_block_fused_matches_unfused(nat, dtype, tol):
+    """Concat-free dense stage (in-place buffer, stats table, hand-written backward) == cat-based autograd."""
+    from dynamic_load_balance_distributeddnn_b200.models import densenet
+    torch.manual_seed(0)
+    stage = densenet.DenseNet([3], growth_rate=32, num_classes=10).dense1.cuda()
+    trans_gn = densenet.GroupNormAct(32, 64 + 3 * 32).cuda()
+    for m in stage.modules():
+        if isinstance(m, torch.nn.Conv2d):
+            m.weight.data = m.weight.data.to(dtype)
+    x0 = _cl(torch.randn(4, 64, 16, 16, device="cuda")).to(dtype)
+    outs = []
+    for fused in (False, True):
+        densenet.DenseStage.fused = fused
+        for p in list(stage.parameters()) + list(trans_gn.parameters()):
+            p.grad = None
+        x = x0.clone().requires_grad_(True)
+        y = trans_gn(stage(x))                     # the following GN consumes the stats table in the fused path
+        gy = torch.randn(y.shape, device="cuda", generator=torch.Generator("cuda").manual_seed(5)).to(dtype)
+        y.backward(gy)
+        outs.append((y.detach().float(), x.grad.float(), [p.grad.float().clone() for p in stage.parameters()],
+                     [p.grad.float().clone() for p in trans_gn.parameters()]))
+    densenet.DenseStage.fused = True
+    (y0, dx0, g0, t0), (y1, dx1, g1, t1) = outs
+    assert torch.allclose(y0, y1, atol=tol, rtol=tol), (y0 - y1).abs().max()
+    assert float((dx0 - dx1).abs().max()) < tol * max(1.0, float(dx0.abs().max()))
+    for a, b in zip(g0 + t0, g1 + t1):
+        assert float((a - b).abs().max()) < tol * max(1.0, float(a.abs().max())), (a - b).abs().max()
