@@ -28,7 +28,8 @@ template <typename T, int V, int MODE>
 __global__ void __launch_bounds__(kThreads)
 nc_reduce2_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy,
                   const T* __restrict__ y, int64_t ldy, float* __restrict__ table, int64_t table_ns,
-                  int HW, int C, int rows_per_block) {
+                  int HW, int C, int rows_per_block, const float* __restrict__ mean,
+                  const float* __restrict__ rstd, int G, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   extern __shared__ float smem[];            // [2*C]
   const int n = blockIdx.y;
   const int lanes = C / V;                   // channel-vector lanes
@@ -45,24 +46,35 @@ nc_reduce2_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy
 #pragma unroll
       for (int i = 0; i < V; ++i) { a0[i] = 0.f; a1[i] = 0.f; }
       const int c = lane * V;
-      for (int r = r0 + rl; r < r1; r += row_lanes) {
-        const int64_t row = (int64_t)n * HW + r;
-        float xv[V];
-        load_vec<T, V>(x + row * ldx + c, xv);
-        if constexpr (MODE == 0) {
+      constexpr int UNR = (MODE == 0) ? 2 : 1;
+      for (int rb = r0 + rl; rb < r1; rb += row_lanes * UNR) {
+        float xv[UNR][V], gv[UNR][V], yv[UNR][V];
 #pragma unroll
-          for (int i = 0; i < V; ++i) { a0[i] += xv[i]; a1[i] += xv[i] * xv[i]; }
-        } else {
-          float gv[V];
-          load_vec<T, V>(dy + row * lddy + c, gv);
-          if constexpr (MODE == 1) {
-            float yv[V];
-            load_vec<T, V>(y + row * ldy + c, yv);
-#pragma unroll
-            for (int i = 0; i < V; ++i) gv[i] = yv[i] > 0.f ? gv[i] : 0.f;
+        for (int u = 0; u < UNR; ++u) {
+          const int r = rb + u * row_lanes;
+          if (r < r1) {
+            const int64_t row = (int64_t)n * HW + r;
+            load_vec<T, V>(x + row * ldx + c, xv[u]);
+            if constexpr (MODE != 0) load_vec<T, V>(dy + row * lddy + c, gv[u]);
+            if constexpr (MODE == 1) load_vec<T, V>(y + row * ldy + c, yv[u]);
           }
+        }
 #pragma unroll
-          for (int i = 0; i < V; ++i) { a0[i] += gv[i]; a1[i] += gv[i] * xv[i]; }
+        for (int u = 0; u < UNR; ++u) {
+          const int r = rb + u * row_lanes;
+          if (r < r1) {
+            if constexpr (MODE == 0) {
+#pragma unroll
+              for (int i = 0; i < V; ++i) { a0[i] += xv[u][i]; a1[i] += xv[u][i] * xv[u][i]; }
+            } else {
+#pragma unroll
+              for (int i = 0; i < V; ++i) {
+                float gz = gv[u][i];
+                if constexpr (MODE == 1) gz = yv[u][i] > 0.f ? gz : 0.f;
+                a0[i] += gz; a1[i] += gz * xv[u][i];
+              }
+            }
+          }
         }
       }
       // lanes of a warp that own the same channels sit `lanes` apart: fold them first
@@ -89,6 +101,19 @@ nc_reduce2_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy
   __syncthreads();
   float* dst = table + (int64_t)n * table_ns;
   for (int i = threadIdx.x; i < 2 * C; i += kThreads) atomicAdd(&dst[i], smem[i]);
+  if constexpr (MODE != 0) {
+    // affine-parameter gradients are linear in the per-(n,c) sums: fold them in here instead of a
+    // separate pass over the table (dbeta = sum A, dgamma = sum rstd*(B - mu*A))
+    if (dgamma != nullptr) {
+      const int cpg = C / G;
+      for (int c = threadIdx.x; c < C; c += kThreads) {
+        const float A = smem[2 * c], B = smem[2 * c + 1];
+        const int g = c / cpg;
+        atomicAdd(&dbeta[c], A);
+        atomicAdd(&dgamma[c], rstd[n * G + g] * (B - mean[n * G + g] * A));
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -131,6 +156,45 @@ gn_fwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
   const int lanes = C / V;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(HW, r0 + rows_per_block);
+  if (lanes <= kThreads) {
+    // one channel-vector per thread for the whole block: coefficients live in registers, rows are
+    // streamed UNR at a time so several 16-byte loads are in flight per thread
+    const int lane = threadIdx.x % lanes, rl = threadIdx.x / lanes, row_lanes = kThreads / lanes;
+    if (rl < row_lanes) {
+      const int c = lane * V;
+      float a[V], b[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) { a[k] = sa[c + k]; b[k] = sb[c + k]; }
+      constexpr int UNR = 2;
+      for (int rb = r0 + rl; rb < r1; rb += row_lanes * UNR) {
+        float xv[UNR][V], rv[UNR][V];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int r = rb + u * row_lanes;
+          if (r < r1) {
+            const int64_t row = (int64_t)n * HW + r;
+            load_vec<T, V>(x + row * ldx + c, xv[u]);
+            if constexpr (RES) load_vec<T, V>(res + row * ldr + c, rv[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int r = rb + u * row_lanes;
+          if (r < r1) {
+            float out[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+              out[k] = fmaf(a[k], xv[u][k], b[k]);
+              if constexpr (RES) out[k] += rv[u][k];
+              if constexpr (RELU) out[k] = fmaxf(out[k], 0.f);
+            }
+            store_vec<T, V>(y + ((int64_t)n * HW + r) * ldy + c, out);
+          }
+        }
+      }
+    }
+    return;
+  }
   const int64_t total = (int64_t)(r1 - r0) * lanes;
   for (int64_t i = threadIdx.x; i < total; i += kThreads) {
     const int r = r0 + (int)(i / lanes);
@@ -197,6 +261,49 @@ gn_bwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
   const int lanes = C / V;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(HW, r0 + rows_per_block);
+  if (lanes <= kThreads) {
+    const int lane = threadIdx.x % lanes, rl = threadIdx.x / lanes, row_lanes = kThreads / lanes;
+    if (rl < row_lanes) {
+      const int c = lane * V;
+      float q1[V], q2[V], q3[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) { q1[k] = k1[c + k]; q2[k] = k2[c + k]; q3[k] = k3[c + k]; }
+      constexpr int UNR = 1;
+      for (int rb = r0 + rl; rb < r1; rb += row_lanes * UNR) {
+        float xv[UNR][V], gv[UNR][V], yv[UNR][V], old[UNR][V];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int r = rb + u * row_lanes;
+          if (r < r1) {
+            const int64_t row = (int64_t)n * HW + r;
+            load_vec<T, V>(x + row * ldx + c, xv[u]);
+            load_vec<T, V>(dy + row * lddy + c, gv[u]);
+            if constexpr (RELU) load_vec<T, V>(y + row * ldy + c, yv[u]);
+            if constexpr (ACC) load_vec<T, V>(dx + row * lddx + c, old[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int r = rb + u * row_lanes;
+          if (r < r1) {
+            const int64_t row = (int64_t)n * HW + r;
+            float out[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+              float gz = gv[u][k];
+              if constexpr (RELU) gz = yv[u][k] > 0.f ? gz : 0.f;
+              gv[u][k] = gz;
+              out[k] = fmaf(q1[k], gz, fmaf(q2[k], xv[u][k], q3[k]));
+              if constexpr (ACC) out[k] += old[u][k];
+            }
+            if constexpr (RES) store_vec<T, V>(dres + row * lddr + c, gv[u]);
+            store_vec<T, V>(dx + row * lddx + c, out);
+          }
+        }
+      }
+    }
+    return;
+  }
   const int64_t total = (int64_t)(r1 - r0) * lanes;
   for (int64_t i = threadIdx.x; i < total; i += kThreads) {
     const int r = r0 + (int)(i / lanes);
@@ -253,8 +360,8 @@ __global__ void __launch_bounds__(256) gn_param_grad_kernel(const float* __restr
 inline void grid_for(int N, int HW, int C, int V, dim3& grid, int& rows_per_block) {
   const int lanes = C / V;
   const int row_lanes = lanes >= kThreads ? 1 : kThreads / lanes;
-  int chunks = (296 * 2 + N - 1) / N;                     // aim for >= ~4 blocks per SM overall
-  int max_chunks = (HW + row_lanes * 4 - 1) / (row_lanes * 4);
+  int chunks = (148 * 8 + N - 1) / N;                     // about one full wave of resident blocks
+  int max_chunks = HW / (row_lanes * 4);                  // keep >= 4 rows per row-lane per block
   if (max_chunks < 1) max_chunks = 1;
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
@@ -265,14 +372,16 @@ inline void grid_for(int N, int HW, int C, int V, dim3& grid, int& rows_per_bloc
 
 template <typename T, int V>
 int reduce2_launch(int mode, const void* x, int64_t ldx, const void* dy, int64_t lddy, const void* y,
-                   int64_t ldy, float* table, int64_t table_ns, int N, int HW, int C, cudaStream_t st) {
+                   int64_t ldy, float* table, int64_t table_ns, int N, int HW, int C, cudaStream_t st,
+                   const float* mean = nullptr, const float* rstd = nullptr, int G = 1, float* dgamma = nullptr,
+                   float* dbeta = nullptr) {
   dim3 grid; int rpb;
   grid_for(N, HW, C, V, grid, rpb);
   const size_t sm = 2 * C * sizeof(float);
   const T* X = (const T*)x; const T* DY = (const T*)dy; const T* Y = (const T*)y;
-  if (mode == 0) nc_reduce2_kernel<T, V, 0><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb);
-  else if (mode == 1) nc_reduce2_kernel<T, V, 1><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb);
-  else nc_reduce2_kernel<T, V, 2><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb);
+  if (mode == 0) nc_reduce2_kernel<T, V, 0><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta);
+  else if (mode == 1) nc_reduce2_kernel<T, V, 1><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta);
+  else nc_reduce2_kernel<T, V, 2><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta);
   return dlb_post_launch();
 }
 
@@ -344,6 +453,21 @@ DLB_API int dlb_nc_reduce2(int mode, int dtype, const void* x, int64_t ldx, cons
   return rc;
 }
 
+// Backward reduction with the affine-parameter gradients folded in (dgamma/dbeta are zeroed here).
+DLB_API int dlb_nc_reduce2_bwd(int relu, int dtype, const void* x, int64_t ldx, const void* dy, int64_t lddy,
+                               const void* y, int64_t ldy, float* table, int64_t table_ns, const float* mean,
+                               const float* rstd, float* dgamma, float* dbeta, int N, int HW, int C, int G, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C > 6000) return -2;
+  if (table_ns <= 0) table_ns = 2 * (int64_t)C;
+  cudaMemset2DAsync(table, (size_t)table_ns * sizeof(float), 0, (size_t)C * 2 * sizeof(float), (size_t)N, st);
+  if (dgamma) { cudaMemsetAsync(dgamma, 0, C * sizeof(float), st); cudaMemsetAsync(dbeta, 0, C * sizeof(float), st); }
+  const bool vec = vec_ok(dtype, C, {ldx, lddy, relu ? ldy : 0}, {x, dy, relu ? y : nullptr});
+  int rc = 0;
+  DISPATCH(dtype, vec, (rc = reduce2_launch<T, V>(relu ? 1 : 2, x, ldx, dy, lddy, y, ldy, table, table_ns, N, HW, C, st, mean, rstd, G, dgamma, dbeta)));
+  return rc;
+}
+
 DLB_API int dlb_gn_finalize(const float* table, int64_t table_ns, float* mean, float* rstd, int N, int C, int G, int HW,
                             float eps, void* stream) {
   const int total = N * G;
@@ -400,10 +524,7 @@ DLB_API int dlb_gn_backward(int dtype, const void* x, int64_t ldx, const void* d
                             const float* gamma, const float* mean, const float* rstd, float* table,
                             float* dgamma, float* dbeta, int N, int HW, int C, int G, int relu, int acc,
                             void* stream) {
-  int rc = dlb_nc_reduce2(relu ? 1 : 2, dtype, x, ldx, dy, lddy, y, ldy, table, 0, N, HW, C, stream);
+  int rc = dlb_nc_reduce2_bwd(relu, dtype, x, ldx, dy, lddy, y, ldy, table, 0, mean, rstd, dgamma, dbeta, N, HW, C, G, stream);
   if (rc) return rc;
-  rc = dlb_gn_bwd_apply(dtype, x, ldx, dy, lddy, y, ldy, dx, lddx, dres, lddr, gamma, mean, rstd, table, 0, N, HW, C, G, relu, acc, stream);
-  if (rc) return rc;
-  if (dgamma) rc = dlb_gn_param_grad(table, 0, mean, rstd, dgamma, dbeta, N, C, G, stream);
-  return rc;
+  return dlb_gn_bwd_apply(dtype, x, ldx, dy, lddy, y, ldy, dx, lddx, dres, lddr, gamma, mean, rstd, table, 0, N, HW, C, G, relu, acc, stream);
 }

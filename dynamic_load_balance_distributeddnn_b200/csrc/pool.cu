@@ -85,3 +85,34 @@ DLB_API int dlb_avgpool_nhwc(int direction, int dtype, const void* in, void* out
   if (C % 4 == 0 && aligned) return launch<float, 4>(fwd, in, out, N, H, W, C, k, st);
   return launch<float, 1>(fwd, in, out, N, H, W, C, k, st);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Strided 2-D copy: `rows` rows of `C` contiguous elements, source/destination row strides in elements.
+// Moves channel slices in and out of the dense-block buffers (ATen's generic strided copy kernel ran at
+// ~1 TB/s on these; profiles/r1_03).
+namespace {
+template <int VB>
+__global__ void __launch_bounds__(256) copy2d_kernel(const unsigned char* __restrict__ src, int64_t lds_b,
+                                                     unsigned char* __restrict__ dst, int64_t ldd_b, int64_t rows, int row_bytes) {
+  const int lanes = row_bytes / VB;
+  const int64_t total = rows * lanes;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / lanes;
+    const int c = (int)(i % lanes) * VB;
+    if constexpr (VB == 16) *reinterpret_cast<uint4*>(dst + r * ldd_b + c) = *reinterpret_cast<const uint4*>(src + r * lds_b + c);
+    else dst[r * ldd_b + c] = src[r * lds_b + c];
+  }
+}
+}  // namespace
+
+DLB_API int dlb_copy2d(const void* src, int64_t lds_bytes, void* dst, int64_t ldd_bytes, int64_t rows, int row_bytes, void* stream) {
+  if (rows <= 0 || row_bytes <= 0) return 0;
+  const bool v16 = (row_bytes % 16 == 0) && (lds_bytes % 16 == 0) && (ldd_bytes % 16 == 0) &&
+                   ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0);
+  const int64_t total = rows * (v16 ? row_bytes / 16 : row_bytes);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (v16) copy2d_kernel<16><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)src, lds_bytes, (unsigned char*)dst, ldd_bytes, rows, row_bytes);
+  else copy2d_kernel<1><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)src, lds_bytes, (unsigned char*)dst, ldd_bytes, rows, row_bytes);
+  return dlb_post_launch();
+}

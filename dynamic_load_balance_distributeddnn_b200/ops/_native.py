@@ -52,10 +52,12 @@ def _declare(lib: ctypes.CDLL) -> None:
         "dlb_launch_count_add": (None, [c_ulonglong]),
         "dlb_nc_reduce2": (i32, [i32, i32, vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, vp]),
         "dlb_gn_finalize": (i32, [vp, i64, vp, vp, i32, i32, i32, i32, c_float, vp]),
+        "dlb_nc_reduce2_bwd": (i32, [i32, i32, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
         "dlb_gn_fwd_apply": (i32, [i32, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
         "dlb_gn_bwd_apply": (i32, [i32, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, i64,
                                    i32, i32, i32, i32, i32, i32, vp]),
         "dlb_gn_param_grad": (i32, [vp, i64, vp, vp, vp, vp, i32, i32, i32, vp]),
+        "dlb_copy2d": (i32, [vp, i64, vp, i64, i64, i32, vp]),
         "dlb_avgpool_nhwc": (i32, [i32, i32, vp, vp, i32, i32, i32, i32, i32, vp]),
         "dlb_gn_forward": (i32, [i32, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, i32, i32, i32, i32,
                                  c_float, i32, i32, vp]),

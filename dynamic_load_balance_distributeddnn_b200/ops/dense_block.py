@@ -37,6 +37,15 @@ def supported(stage, x: torch.Tensor) -> bool:
     return c0 % 8 == 0 and g % 8 == 0 and stage[0].gn1.weight.dtype == torch.float32
 
 
+def _copy_slice(lib, src, dst, st):
+    """dst[...] = src[...] for two NHWC views of identical logical shape (either may be a channel slice)."""
+    s, n, hw, c, lds = _nhwc_view(src)
+    d, _, _, _, ldd = _nhwc_view(dst)
+    assert d.data_ptr() == dst.data_ptr(), "destination must be an NHWC view"
+    esz = src.element_size()
+    nat.check(lib.dlb_copy2d(s.data_ptr(), lds * esz, dst.data_ptr(), ldd * esz, n * hw, c * esz, st), "copy2d")
+
+
 def _conv_fwd(x, w, pad):
     return torch.nn.functional.conv2d(x, w if w.dtype == x.dtype else w.to(x.dtype), None, 1, pad)
 
@@ -55,7 +64,7 @@ class _DenseBlockFn(torch.autograd.Function):
         buf = torch.empty((n, ct, h, w), dtype=x.dtype, device=x.device).contiguous(memory_format=torch.channels_last)
         table = torch.empty((n, ct, 2), dtype=torch.float32, device=x.device)
         tns = 2 * ct
-        buf[:, ct - c0:].copy_(x)
+        _copy_slice(lib, x, buf[:, ct - c0:], st)
         esz = buf.element_size()
 
         def slice_ptr(c_off):
@@ -88,7 +97,7 @@ class _DenseBlockFn(torch.autograd.Function):
                                          mean2.data_ptr(), rstd2.data_ptr(), t2.data_ptr(), n, hw, cm, groups, eps, 1, 0, st),
                       "dense.gn2")
             new = _conv_fwd(yhat, w2, 1)
-            buf[:, off - g:off].copy_(new)
+            _copy_slice(lib, new, buf[:, off - g:off], st)
             stats(off - g, g)
             saved += [xhat, yv, yhat, mean1, rstd1, mean2, rstd2]
         ctx.save_for_backward(buf, *params, *saved)
@@ -108,7 +117,7 @@ class _DenseBlockFn(torch.autograd.Function):
         dt = nat.dtype_code(buf.dtype)
         hw = h * w
         esz = buf.element_size()
-        dbuf = dout.contiguous(memory_format=torch.channels_last).clone()
+        dbuf = dout.clone(memory_format=torch.channels_last)            # one copy: we accumulate into it in place
         grads: List = [None] * (6 * n_layers)
         for l in reversed(range(n_layers)):
             g1w, g1b, w1, g2w, g2b, w2 = params[6 * l:6 * l + 6]
@@ -116,7 +125,8 @@ class _DenseBlockFn(torch.autograd.Function):
             cl = c0 + l * g
             off = ct - cl
             cm = y.shape[1]
-            dnew = dbuf[:, off - g:off].contiguous(memory_format=torch.channels_last)
+            dnew = torch.empty((n, g, h, w), dtype=buf.dtype, device=buf.device).contiguous(memory_format=torch.channels_last)
+            _copy_slice(lib, dbuf[:, off - g:off], dnew, st)
             w2c = w2 if w2.dtype == yhat.dtype else w2.to(yhat.dtype)
             dyhat, dw2, _ = _CONV_BWD(dnew, yhat, w2c, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [True, True, False])
             dyhat = dyhat.contiguous(memory_format=torch.channels_last)
@@ -142,7 +152,8 @@ class _DenseBlockFn(torch.autograd.Function):
                                           dg1.data_ptr(), db1.data_ptr(), n, hw, cl, groups, 1, 1, st), "dense.gn1_bwd")
             grads[6 * l:6 * l + 6] = [dg1.to(g1w.dtype), db1.to(g1b.dtype), dw1.to(w1.dtype), dg2.to(g2w.dtype),
                                       db2.to(g2b.dtype), dw2.to(w2.dtype)]
-        dx = dbuf[:, ct - c0:]
+        dx = torch.empty((n, c0, h, w), dtype=buf.dtype, device=buf.device).contiguous(memory_format=torch.channels_last)
+        _copy_slice(lib, dbuf[:, ct - c0:], dx, st)
         return (dx, None, None, *grads)
 
 

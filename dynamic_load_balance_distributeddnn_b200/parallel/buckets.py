@@ -30,6 +30,19 @@ from .comm import Comm, SymmComm
 _ALIGN = 32          # elements; keeps every parameter 64-byte aligned in bf16 and 128-byte in fp32
 
 
+def _is_conv_weight(p: torch.Tensor) -> bool:
+    return p.dim() == 4
+
+
+def _flat_order(t: torch.Tensor) -> torch.Tensor:
+    """1-D view/copy of ``t`` in the order it is stored in the flat buffers: conv weights are kept
+    O-H-W-I (channels-last), i.e. exactly the K-major [Cout][kh][kw][Cin] operand layout the implicit-GEMM
+    kernels (ours and the vendor's) consume, so no per-call weight re-layout kernel ever runs."""
+    if _is_conv_weight(t):
+        return t.permute(0, 2, 3, 1).reshape(-1)
+    return t.reshape(-1)
+
+
 class FlatState:
     def __init__(self, model: nn.Module, device, compute_dtype: torch.dtype, comm: Comm,
                  lr: float, momentum: float = 0.9, weight_decay: float = 0.0, bucket_mb: float = 8.0,
@@ -66,14 +79,18 @@ class FlatState:
         with torch.no_grad():
             for p, off in zip(self.params, self.offsets):
                 n = p.numel()
-                self.master[off:off + n].copy_(p.detach().reshape(-1).to(self.device, torch.float32))
+                self.master[off:off + n].copy_(_flat_order(p.detach()).to(self.device, torch.float32))
             if self.shadow is not None:
                 self.shadow.copy_(self.master)
             for p, off in zip(self.params, self.offsets):
                 n = p.numel()
                 keep32 = getattr(p, "_dlb_keep_fp32", False) or self.shadow is None
                 src = self.master if keep32 else self.shadow
-                p.data = src[off:off + n].view(p.shape)
+                if _is_conv_weight(p):
+                    o, i, kh, kw = p.shape
+                    p.data = src[off:off + n].view(o, kh, kw, i).permute(0, 3, 1, 2)      # logical OIHW, NHWC memory
+                else:
+                    p.data = src[off:off + n].view(p.shape)
                 p.grad = None
         # non-parameter state (buffers such as the positional table) just moves to the device
         for mod in model.modules():
@@ -126,7 +143,10 @@ class FlatState:
             g = p.grad
             if g is None:
                 g = torch.zeros_like(p)
-            if not g.is_contiguous():
+            if _is_conv_weight(p):
+                if not g.is_contiguous(memory_format=torch.channels_last):
+                    g = g.contiguous(memory_format=torch.channels_last)
+            elif not g.is_contiguous():
                 g = g.contiguous()
             keep.append(g)
             ptrs.append(g.data_ptr()); offs.append(off); numels.append(g.numel()); dtypes.append(nat.dtype_code(g.dtype))
@@ -174,7 +194,7 @@ class FlatState:
             self.grad_in.zero_()
             for p, off in zip(self.params, self.offsets):
                 if p.grad is not None:
-                    self.grad_in[off:off + p.numel()].copy_(p.grad.reshape(-1).to(self.grad_in.dtype) * scale)
+                    self.grad_in[off:off + p.numel()].copy_(_flat_order(p.grad).to(self.grad_in.dtype) * scale)
             waited = self.comm.allreduce_buckets(self.grad_in, self.grad_out, self.buckets)
             g = self.grad_out.float()
             if self.weight_decay:
