@@ -1,0 +1,446 @@
+// Persistent warp-specialised bf16 GEMM on the 5th-gen tensor cores (sm_100a):
+//
+//     D[M, N] (+)= epilogue( prologue(A)[M, K] * B[N, K]^T )          fp32 accumulation in TMEM
+//
+//   * operands staged by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) into a multi-stage shared-memory ring,
+//   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x BN x 16) from shared-memory
+//     matrix descriptors, completion tracked with tcgen05.commit -> mbarrier,
+//   * accumulators live in TMEM, double buffered (2 x BN columns) so the epilogue of tile i overlaps the
+//     main loop of tile i+1; epilogue warps read them back with tcgen05.ld (32x32b.x32),
+//   * persistent grid: one CTA per SM walks the tile list.
+//
+// This is the convolution engine of the CNN zoo for 1x1 convolutions (pure GEMMs in NHWC: A = activations
+// [pixels, Cin] with an arbitrary row stride so channel slices of the DenseNet concat buffer are read in
+// place; B = weights [Cout][Cin], exactly how the flat parameter store keeps them) and for nn.Linear
+// (reference Net/Densenet.py:13,29; Net/Resnet.py:35,39,45; Net/Transformer.py linear layers).
+//
+// Fused variants (template flags):
+//   PRO_GN  : A-operand prologue  a[n,k]*x + b[n,k] -> ReLU  (GroupNorm-apply + ReLU of the *input*, i.e. the
+//             DenseNet pre-activation order GN->ReLU->conv) performed in shared memory between the TMA
+//             arrival and the MMA issue, so the normalised activation never exists in HBM.
+//   EPI_STATS: epilogue additionally accumulates per-(sample, out-channel) sum and sum-of-squares of the
+//             bf16-rounded output into the GroupNorm statistics table (feeds the NEXT GroupNorm for free).
+#include "common.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace {
+
+constexpr int BM = 128;            // UMMA_M (cta_group::1)
+constexpr int BK = 64;             // 64 bf16 = 128 bytes = one SWIZZLE_128B atom row
+constexpr int UMMA_K = 16;
+constexpr int kNumEpiWarps = 4;
+constexpr int kProWarps = 4;       // prologue-transform warps (PRO_GN only)
+constexpr uint32_t kSpinLimit = 1u << 20;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > kSpinLimit) __trap();      // watchdog: never hang the GPU on a protocol bug
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  // K-major, SWIZZLE_128B canonical layout: 8-row groups 1024 B apart (SBO), rows 128 B apart inside a group.
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                 // leading byte offset (ignored for swizzled K-major), canonical 1
+  d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset
+  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct GemmParams {
+  int M, N, K;
+  void* d;            // output, bf16, row-major with row stride ldd (elements)
+  long long ldd;
+  int accumulate_out; // (reserved)
+  // PRO_GN: per-(sample, k) affine coefficients a,b fp32 [num_samples][K] (row n = pixel_row / rows_per_sample)
+  const float* pro_a;
+  const float* pro_b;
+  long long pro_ld;   // row stride (floats) of pro_a / pro_b, a multiple of 64, zero padded
+  int rows_per_sample;
+  // EPI_STATS: table fp32 [num_samples][table_ns] holding (sum, sumsq) pairs per output channel
+  float* stats;
+  long long stats_ns;
+};
+
+template <int BN> struct Cfg {
+  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 5 : 6);
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator (+ idle), 3 = idle (keeps epilogue warps at
+// warp ids 4..7 so that (warp_id % 4) selects their TMEM lane quadrant), 4..7 = epilogue, 8..11 = prologue transform.
+template <int BN, bool PRO_GN, bool EPI_STATS>
+__global__ void __launch_bounds__(PRO_GN ? 384 : 256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* bar_base = smem + C::kStages * C::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);              // TMA bytes landed
+  uint64_t* empty_bar = full_bar + C::kStages;                             // MMA done reading the stage
+  uint64_t* ready_bar = empty_bar + C::kStages;                            // PRO_GN: transform done
+  uint64_t* tmem_full = ready_bar + C::kStages;                            // [2] accumulator complete
+  uint64_t* tmem_empty = tmem_full + 2;                                    // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&ready_bar[s]), kProWarps * 32);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tmem_full[a]), 1);
+      mbar_init(smem_u32(&tmem_empty[a]), kNumEpiWarps);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t / num_n) * BM, n0 = (t % num_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t sb = sa + C::kABytes;
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, C::kStageBytes);
+          tma_load_2d(sa, &tmap_a, fb, kb * BK, m0);
+          tma_load_2d(sb, &tmap_b, fb, kb * BK, n0);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(PRO_GN ? &ready_bar[stage] : &full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t sb = sa + C::kABytes;
+          const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sb);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 32 bytes (16 bf16) along K inside the 128-byte swizzle atom: +2 in 16-byte units
+            umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[stage]));            // frees the smem stage when these MMAs retire
+          if (kb == num_kb - 1) umma_commit(smem_u32(&tmem_full[acc]));
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================================== epilogue =========================================
+    const int q = warp & 3;                                     // TMEM lane quadrant owned by this warp
+    int acc = 0; uint32_t acc_phase = 0;
+    __nv_bfloat16* dptr = reinterpret_cast<__nv_bfloat16*>(p.d);
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m0 = (t / num_n) * BM, n0 = (t % num_n) * BN;
+      mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          packed[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        const int col = n0 + c0;
+        if (row_ok) {
+          __nv_bfloat16* dst = dptr + (long long)row * p.ldd + col;
+          if (col + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              reinterpret_cast<uint4*>(dst)[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col + j < p.N) dst[j] = reinterpret_cast<__nv_bfloat16*>(packed)[j];
+          }
+        }
+        if constexpr (EPI_STATS) {
+          // per-(sample, channel) sum / sumsq of the bf16-rounded outputs; rows of one warp belong to one sample
+          // (host guarantees rows_per_sample % 32 == 0).  Transpose-reduce: after 5 exchange steps lane j
+          // holds the total of column c0 + j over the warp's 32 rows.
+          float s[32], ss[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&packed[j]));
+            if (!row_ok) { f.x = 0.f; f.y = 0.f; }
+            s[2 * j] = f.x; s[2 * j + 1] = f.y;
+            ss[2 * j] = f.x * f.x; ss[2 * j + 1] = f.y * f.y;
+          }
+#pragma unroll
+          for (int step = 0; step < 5; ++step) {
+            const int half = 16 >> step;                       // registers kept per lane after this step
+            const bool upper = (lane >> (4 - step)) & 1;
+#pragma unroll
+            for (int j = 0; j < half; ++j) {
+              const float send_s = upper ? s[j] : s[j + half];
+              const float send_q = upper ? ss[j] : ss[j + half];
+              const float keep_s = upper ? s[j + half] : s[j];
+              const float keep_q = upper ? ss[j + half] : ss[j];
+              s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, 16 >> step);
+              ss[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, 16 >> step);
+            }
+          }
+          // lane -> column mapping produced by the exchange pattern above
+          int cidx = 0;
+#pragma unroll
+          for (int step = 0; step < 5; ++step) cidx |= ((lane >> (4 - step)) & 1) << (4 - step);
+          const int sample = (m0 + q * 32) / p.rows_per_sample;
+          if (m0 + q * 32 < p.M && col + cidx < p.N) {
+            float* tb = p.stats + (long long)sample * p.stats_ns + 2 * (col + cidx);
+            atomicAdd(tb, s[0]);
+            atomicAdd(tb + 1, ss[0]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (PRO_GN && warp >= 8) {
+    // ============================ A-operand prologue: GN-apply + ReLU ========================
+    // The TMA wrote a 128-row x 64-col bf16 tile with the 128B swizzle: 16-byte chunk j of row r lives at
+    // r*128 + ((j ^ (r & 7)) << 4).  Thread (pw, lane) transforms rows pw*32+lane ... in place.
+    const int pw = warp - 8;
+    int stage = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m0 = (t / num_n) * BM;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        uint8_t* sa = smem + stage * C::kStageBytes;
+        const int r = pw * 32 + lane;
+        const int grow = m0 + r;
+        const int sample = min(grow, p.M - 1) / p.rows_per_sample;
+        // coefficient rows are padded to a multiple of BK and zero-filled by the host (a = b = 0 beyond K)
+        const float4* ca = reinterpret_cast<const float4*>(p.pro_a + (long long)sample * p.pro_ld + kb * BK);
+        const float4* cb = reinterpret_cast<const float4*>(p.pro_b + (long long)sample * p.pro_ld + kb * BK);
+        const bool live = grow < p.M;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4* chunk = reinterpret_cast<uint4*>(sa + r * 128 + ((j ^ (r & 7)) << 4));
+          uint4 raw = *chunk;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+          const float4 a0 = __ldg(ca + 2 * j), a1 = __ldg(ca + 2 * j + 1);
+          const float4 b0 = __ldg(cb + 2 * j), b1 = __ldg(cb + 2 * j + 1);
+          float2 f;
+          f = __bfloat1622float2(h[0]);
+          h[0] = __floats2bfloat162_rn(fmaxf(fmaf(a0.x, f.x, b0.x), 0.f), fmaxf(fmaf(a0.y, f.y, b0.y), 0.f));
+          f = __bfloat1622float2(h[1]);
+          h[1] = __floats2bfloat162_rn(fmaxf(fmaf(a0.z, f.x, b0.z), 0.f), fmaxf(fmaf(a0.w, f.y, b0.w), 0.f));
+          f = __bfloat1622float2(h[2]);
+          h[2] = __floats2bfloat162_rn(fmaxf(fmaf(a1.x, f.x, b1.x), 0.f), fmaxf(fmaf(a1.y, f.y, b1.y), 0.f));
+          f = __bfloat1622float2(h[3]);
+          h[3] = __floats2bfloat162_rn(fmaxf(fmaf(a1.z, f.x, b1.z), 0.f), fmaxf(fmaf(a1.w, f.y, b1.w), 0.f));
+          if (!live) raw = make_uint4(0u, 0u, 0u, 0u);
+          *chunk = raw;
+        }
+        fence_proxy_async();                                     // generic-proxy writes -> visible to the MMA (async proxy)
+        mbar_arrive(smem_u32(&ready_bar[stage]));
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult qres;
+    void* ptr = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: inner dim `cols` (contiguous), outer dim `rows` with row stride `ld` elements.
+int make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  auto enc = get_encode();
+  if (!enc) return -10;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -11;
+}
+
+template <int BN, bool PRO, bool STATS>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int sms, cudaStream_t st) {
+  using C = Cfg<BN>;
+  auto kern = gemm_tc_kernel<BN, PRO, STATS>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int num_tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  const int grid = num_tiles < sms ? num_tiles : sms;
+  kern<<<grid, PRO ? 384 : 256, C::kSmemBytes, st>>>(ta, tb, p);
+  return dlb_post_launch();
+}
+
+template <int BN>
+int dispatch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, bool pro, bool stats, int sms, cudaStream_t st) {
+  if (pro && stats) return launch<BN, true, true>(ta, tb, p, sms, st);
+  if (pro) return launch<BN, true, false>(ta, tb, p, sms, st);
+  if (stats) return launch<BN, false, true>(ta, tb, p, sms, st);
+  return launch<BN, false, false>(ta, tb, p, sms, st);
+}
+
+}  // namespace
+
+// D[M,N] (bf16, row stride ldd) = pro(A[M,K] (bf16, row stride lda)) * B[N,K]^T (bf16, row stride ldb).
+//   pro_a/pro_b (optional): fp32 [M / rows_per_sample][K] affine coefficients -> A' = relu(a*A + b)
+//   stats (optional): fp32 table [M / rows_per_sample][stats_ns] accumulating (sum, sumsq) per output column;
+//                     must be zeroed by the caller.
+// Requirements: K % 8 == 0, lda % 8 == 0, ldb % 8 == 0, 16-byte aligned base pointers; with stats or prologue
+// rows_per_sample % 32 == 0 (stats) / any (prologue).
+DLB_API int dlb_gemm_tc(const void* a, long long lda, const void* b, long long ldb, void* d, long long ldd, int M, int N, int K,
+                        const float* pro_a, const float* pro_b, long long pro_ld, int rows_per_sample, float* stats, long long stats_ns,
+                        int sm_limit, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((K % 8) || (lda % 8) || (ldb % 8) || ((uintptr_t)a & 15) || ((uintptr_t)b & 15)) return -3;
+  if (stats && (rows_per_sample % 32)) return -4;
+  if (pro_a && ((pro_ld % BK) || pro_ld < K || ((uintptr_t)pro_a & 15) || ((uintptr_t)pro_b & 15))) return -5;
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int sms = sm_count;
+  if (sm_limit > 0 && sm_limit < sms) sms = sm_limit;
+  const int bn = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+  CUtensorMap ta, tb;
+  int rc = make_map(&ta, a, M, K, lda, BM);
+  if (rc) return rc;
+  rc = make_map(&tb, b, N, K, ldb, bn);
+  if (rc) return rc;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.d = d; p.ldd = ldd; p.accumulate_out = 0;
+  p.pro_a = pro_a; p.pro_b = pro_b; p.pro_ld = pro_ld; p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : M;
+  p.stats = stats; p.stats_ns = stats_ns;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool pro = pro_a != nullptr, sts = stats != nullptr;
+  switch (bn) {
+    case 32: return dispatch<32>(ta, tb, p, pro, sts, sms, st);
+    case 64: return dispatch<64>(ta, tb, p, pro, sts, sms, st);
+    case 128: return dispatch<128>(ta, tb, p, pro, sts, sms, st);
+    default: return dispatch<256>(ta, tb, p, pro, sts, sms, st);
+  }
+}

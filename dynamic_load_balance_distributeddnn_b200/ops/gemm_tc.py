@@ -1,0 +1,106 @@
+"""Python face of the tcgen05/TMA GEMM (``csrc/gemm_tc.cu``): plain GEMM, 1x1 convolution autograd op,
+and the fused GroupNorm-prologue / statistics-epilogue variants used by the dense block."""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+from . import _native as nat
+from .norm import _nhwc_view
+
+_DECLARED = False
+ENABLED = os.environ.get("DLB_TC_GEMM", "1") == "1"
+
+
+def _lib():
+    global _DECLARED
+    lib = nat.require()
+    if not _DECLARED:
+        vp, i64, i32 = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
+        nat.declare("dlb_gemm_tc", i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, i32, vp, i64, i32, vp])
+        _DECLARED = True
+    return lib
+
+
+def available() -> bool:
+    return ENABLED and nat.available() and hasattr(nat.get(), "dlb_gemm_tc")
+
+
+def gemm_raw(a_ptr: int, lda: int, b_ptr: int, ldb: int, d_ptr: int, ldd: int, m: int, n: int, k: int, device,
+             pro_a: Optional[torch.Tensor] = None, pro_b: Optional[torch.Tensor] = None, rows_per_sample: int = 0,
+             stats: Optional[torch.Tensor] = None, stats_ptr: int = 0, stats_ns: int = 0, sm_limit: int = 0) -> None:
+    pro_ld = pro_a.shape[1] if pro_a is not None else 0
+    sp = stats_ptr if stats_ptr else nat.ptr(stats)
+    rc = _lib().dlb_gemm_tc(a_ptr, lda, b_ptr, ldb, d_ptr, ldd, m, n, k, nat.ptr(pro_a), nat.ptr(pro_b), pro_ld,
+                            rows_per_sample, sp, stats_ns, sm_limit, nat.stream_ptr(device))
+    nat.check(rc, "gemm_tc")
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, pro_a=None, pro_b=None,
+         rows_per_sample: int = 0, stats=None, stats_ns: int = 0) -> torch.Tensor:
+    """out[M,N] = pro(a[M,K]) @ b[N,K]^T.  a, b, out: bf16 2-D with unit inner stride (row strides free)."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1
+    m, k = a.shape
+    n = b.shape[0]
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.bfloat16, device=a.device)
+    assert out.stride(1) == 1
+    gemm_raw(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), out.stride(0), m, n, k, a.device,
+             pro_a, pro_b, rows_per_sample, stats, 0, stats_ns)
+    return out
+
+
+def _w2d(weight: torch.Tensor) -> torch.Tensor:
+    """[O, I, 1, 1] (any layout) -> contiguous-row [O, I] view."""
+    o, i = weight.shape[0], weight.shape[1]
+    w = weight.reshape(o, i)
+    return w if w.stride(1) == 1 else w.contiguous()
+
+
+class _Conv1x1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight):
+        xv, n, hw, c, ld = _nhwc_view(x)
+        o = weight.shape[0]
+        h, w = x.shape[2], x.shape[3]
+        y = torch.empty((n, o, h, w), dtype=x.dtype, device=x.device).contiguous(memory_format=torch.channels_last)
+        w2 = _w2d(weight)
+        gemm_raw(xv.data_ptr(), ld, w2.data_ptr(), w2.stride(0), y.data_ptr(), o, n * hw, o, c, x.device)
+        ctx.save_for_backward(xv, weight)
+        ctx.cfg = (n, hw, c, ld, o, h, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xv, weight = ctx.saved_tensors
+        n, hw, c, ld, o, h, w = ctx.cfg
+        dyv, _, _, _, lddy = _nhwc_view(dy)
+        dx = dw = None
+        w2 = _w2d(weight)
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device).contiguous(memory_format=torch.channels_last)
+            wt = w2.t().contiguous()                                   # [Cin, Cout]: B operand of dX = dY * W
+            gemm_raw(dyv.data_ptr(), lddy, wt.data_ptr(), wt.stride(0), dx.data_ptr(), c, n * hw, c, o, dy.device)
+        if ctx.needs_input_grad[1]:
+            x2 = torch.as_strided(xv, (n * hw, c), (ld, 1))
+            dy2 = torch.as_strided(dyv, (n * hw, o), (lddy, 1))
+            dw = (dy2.t() @ x2).reshape(weight.shape[0], weight.shape[1], 1, 1).to(weight.dtype)
+        return dx, dw
+
+
+def conv_supported(x, weight, stride, padding, groups) -> bool:
+    if not available():
+        return False
+    return (x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and x.dim() == 4 and groups == 1
+            and stride == 1 and padding == 0 and weight.shape[2] == 1 and weight.shape[3] == 1
+            and x.shape[1] % 8 == 0 and x.shape[0] * x.shape[2] * x.shape[3] >= 128)
+
+
+def conv2d(x, weight, bias, stride, padding):
+    y = _Conv1x1Fn.apply(x, weight)
+    if bias is not None:
+        y = y + bias.to(y.dtype).view(1, -1, 1, 1)
+    return y

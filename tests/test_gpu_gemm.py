@@ -1,0 +1,94 @@
+"""tcgen05/TMA GEMM numerics vs fp32 PyTorch (own file: a protocol bug traps the context, so the driver script
+runs this module in its own process under `timeout`)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def g():
+    from dynamic_load_balance_distributeddnn_b200.ops import gemm_tc
+    assert gemm_tc.available()
+    return gemm_tc
+
+
+def _ref(a, b):
+    return a.float() @ b.float().t()
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (256, 128, 128), (4096, 128, 256), (1000, 40, 72), (65536, 128, 64),
+                                   (8192, 256, 1024), (300, 32, 1152), (5000, 200, 200), (128 * 148 * 2 + 77, 128, 192)])
+def test_plain_gemm(g, m, n, k):
+    torch.manual_seed(m + n + k)
+    a = torch.randn(m, k, device="cuda").bfloat16()
+    b = (torch.randn(n, k, device="cuda") / k ** 0.5).bfloat16()
+    d = g.gemm(a, b)
+    torch.cuda.synchronize()
+    r = _ref(a, b)
+    err = (d.float() - r).abs().max().item()
+    assert err < 2e-2 * max(1.0, r.abs().max().item()), err
+
+
+def test_strided_operands_and_output(g):
+    """A is a channel slice of a wider NHWC buffer; D is written into a channel slice of another buffer."""
+    torch.manual_seed(0)
+    big = torch.randn(4096, 320, device="cuda").bfloat16()
+    a = big[:, 64:64 + 192]
+    b = (torch.randn(128, 192, device="cuda") / 14).bfloat16()
+    out_big = torch.zeros(4096, 256, device="cuda", dtype=torch.bfloat16)
+    g.gemm(a, b, out=out_big[:, 32:160])
+    torch.cuda.synchronize()
+    r = _ref(a, b)
+    assert (out_big[:, 32:160].float() - r).abs().max().item() < 2e-2 * r.abs().max().item()
+    assert out_big[:, :32].abs().sum().item() == 0 and out_big[:, 160:].abs().sum().item() == 0
+
+
+@pytest.mark.parametrize("hw,k,n", [(1024, 64, 128), (256, 200, 128), (64, 512, 128), (16, 1024, 128)])
+def test_gn_relu_prologue(g, hw, k, n):
+    torch.manual_seed(1)
+    ns = 8
+    m = ns * hw
+    x = torch.randn(m, k, device="cuda").bfloat16()
+    kp = (k + 63) // 64 * 64
+    pa = torch.zeros(ns, kp, device="cuda"); pb = torch.zeros(ns, kp, device="cuda")
+    pa[:, :k] = torch.rand(ns, k, device="cuda") + 0.5
+    pb[:, :k] = torch.randn(ns, k, device="cuda") * 0.3
+    b = (torch.randn(n, k, device="cuda") / k ** 0.5).bfloat16()
+    d = g.gemm(x, b, pro_a=pa, pro_b=pb, rows_per_sample=hw)
+    torch.cuda.synchronize()
+    xa = torch.relu(x.float().view(ns, hw, k) * pa[:, None, :k] + pb[:, None, :k]).bfloat16().view(m, k)
+    r = _ref(xa, b)
+    err = (d.float() - r).abs().max().item()
+    assert err < 2e-2 * max(1.0, r.abs().max().item()), err
+
+
+@pytest.mark.parametrize("hw,k,n", [(1024, 64, 128), (256, 128, 128), (64, 256, 128), (32, 64, 32)])
+def test_stats_epilogue(g, hw, k, n):
+    torch.manual_seed(2)
+    ns = 6
+    m = ns * hw
+    a = torch.randn(m, k, device="cuda").bfloat16()
+    b = (torch.randn(n, k, device="cuda") / k ** 0.5).bfloat16()
+    table = torch.zeros(ns, n, 2, device="cuda")
+    d = g.gemm(a, b, rows_per_sample=hw, stats=table, stats_ns=2 * n)
+    torch.cuda.synchronize()
+    df = d.float().view(ns, hw, n)
+    assert torch.allclose(table[..., 0], df.sum(1), atol=2e-2, rtol=2e-3), (table[..., 0] - df.sum(1)).abs().max()
+    assert torch.allclose(table[..., 1], (df * df).sum(1), atol=2e-2, rtol=2e-3)
+
+
+def test_conv1x1_autograd(g):
+    from dynamic_load_balance_distributeddnn_b200.ops import gemm_tc
+    torch.manual_seed(3)
+    x = torch.randn(8, 96, 16, 16, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    w = (torch.randn(128, 96, 1, 1, device="cuda") / 10).bfloat16().requires_grad_(True)
+    y = gemm_tc.conv2d(x, w, None, 1, 0)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xr = x.detach().float().requires_grad_(True); wr = w.detach().float().requires_grad_(True)
+    yr = torch.nn.functional.conv2d(xr, wr)
+    yr.backward(gy.float())
+    assert (y.float() - yr).abs().max().item() < 3e-2 * yr.abs().max().item()
+    assert (x.grad.float() - xr.grad).abs().max().item() < 3e-2 * xr.grad.abs().max().item()
+    assert (w.grad.float() - wr.grad).abs().max().item() < 3e-2 * wr.grad.abs().max().item()

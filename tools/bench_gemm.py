@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""tcgen05 GEMM micro-benchmark on the DenseNet 1x1-conv shapes vs cuBLAS (torch.matmul), CUDA-event timed,
+L2 flushed; reports achieved DRAM bandwidth against the measured copy peak (these GEMMs are memory-bound)."""
+import json, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from dynamic_load_balance_distributeddnn_b200.ops import gemm_tc  # noqa: E402
+PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6462.4
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+
+def timeit(fn, iters=5):
+    fn(); torch.cuda.synchronize(); ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    return min(ts)
+
+
+quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
+shapes = [(524288, 128, 64), (524288, 128, 256), (131072, 128, 512), (32768, 128, 1024), (8192, 128, 1024), (524288, 256, 128)]
+if quick:
+    shapes = [(524288, 128, 256)]
+for (m, n, k) in shapes:
+    a = torch.randn(m, k, device="cuda").bfloat16(); b = torch.randn(n, k, device="cuda").bfloat16()
+    d = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+    t1 = timeit(lambda: gemm_tc.gemm(a, b, out=d))
+    t2 = timeit(lambda: torch.matmul(a, b.t(), out=d))
+    byts = (m * k + n * k + m * n) * 2
+    print(f"M={m} N={n} K={k}: tcgen05 {t1*1e3:8.1f} us ({byts/t1/1e6:6.0f} GB/s, {100*byts/t1/1e6/PEAK:5.1f}% of measured copy peak, "
+          f"{2*m*n*k/t1/1e9:7.1f} TFLOP/s)   cuBLAS {t2*1e3:8.1f} us ({byts/t2/1e6:6.0f} GB/s)", flush=True)
