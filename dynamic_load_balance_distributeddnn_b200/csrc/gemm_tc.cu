@@ -351,6 +351,249 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 }
 
+// =========================================================================================================
+// Weight-gradient GEMM:  dW[Co, Ci] += sum_m dY[m, co] * pro(X)[m, ci]        (reduction over pixels m)
+//
+// Both operands are read straight from their NHWC activations, i.e. they are "MN-major" for the tensor core
+// (the reduction index m is the slow dimension): TMA boxes of 64 channels x 64 pixel-rows land in shared
+// memory as 128-byte rows with the 128B swizzle, which is exactly the canonical MN-major SWIZZLE_128B UMMA
+// layout (8-row K groups 1024 B apart = SBO, 64-channel MN groups one box = 8192 B apart = LBO).
+// The X operand can get the same GroupNorm-apply + ReLU prologue as the forward GEMM, so relu(GN(x)) is
+// never materialised for the backward pass either.  The pixel range is split across CTAs (split-K); partial
+// results are combined with vector fp32 reductions (red.global.add.v4.f32) into a zero-initialised dW.
+struct WgradParams {
+  int M, Co, Ci;
+  float* dw;            // fp32 [Co][ldw]
+  long long ldw;
+  int rows_per_split;   // multiple of 64
+  int num_splits;
+  const float* pro_a;
+  const float* pro_b;
+  long long pro_ld;
+  int rows_per_sample;
+};
+
+template <int BN> struct WCfg {
+  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 5 : 6);
+  static constexpr int kBoxBytes = 64 * 64 * 2;                  // 64 channels x 64 pixel rows
+  static constexpr int kABytes = 2 * kBoxBytes;                  // 128 output channels
+  static constexpr int kBBytes = (BN / 64) * kBoxBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;       // LBO: next 64-wide MN group (one TMA box further)
+  d |= (uint64_t)(1024 >> 4) << 32;       // SBO: next 8-row K group
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BN, bool PRO_GN>
+__global__ void __launch_bounds__(PRO_GN ? 384 : 256, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x, const WgradParams p) {
+  using C = WCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* bar_base = smem + C::kStages * C::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* ready_bar = empty_bar + C::kStages;
+  uint64_t* tmem_full = ready_bar + C::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co_tiles = (p.Co + 127) / 128, ci_tiles = (p.Ci + BN - 1) / BN;
+  const int num_units = co_tiles * ci_tiles * p.num_splits;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_dy) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&ready_bar[s]), kProWarps * 32);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tmem_full[a]), 1);
+      mbar_init(smem_u32(&tmem_empty[a]), kNumEpiWarps);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // unit u -> (split, co tile, ci tile); splits vary fastest so neighbouring CTAs stream disjoint pixel ranges
+  auto decode = [&](int u, int& sp, int& co0, int& ci0) {
+    sp = u % p.num_splits;
+    const int t = u / p.num_splits;
+    ci0 = (t % ci_tiles) * BN;
+    co0 = (t / ci_tiles) * 128;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        int sp, co0, ci0; decode(u, sp, co0, ci0);
+        const int r0 = sp * p.rows_per_split, r1 = min(p.M, r0 + p.rows_per_split);
+        for (int r = r0; r < r1; r += 64) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t sb = sa + C::kABytes;
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, C::kStageBytes);
+          tma_load_2d(sa, &tmap_dy, fb, co0, r);
+          tma_load_2d(sa + C::kBoxBytes, &tmap_dy, fb, co0 + 64, r);
+#pragma unroll
+          for (int gi = 0; gi < BN / 64; ++gi) tma_load_2d(sb + gi * C::kBoxBytes, &tmap_x, fb, ci0 + gi * 64, r);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D=f32, A=B=bf16, BOTH MN-major (bits 15, 16), N=BN, M=128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        int sp, co0, ci0; decode(u, sp, co0, ci0);
+        const int r0 = sp * p.rows_per_split, r1 = min(p.M, r0 + p.rows_per_split);
+        mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        bool first = true;
+        for (int r = r0; r < r1; r += 64) {
+          mbar_wait(smem_u32(PRO_GN ? &ready_bar[stage] : &full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t sb = sa + C::kABytes;
+          const uint64_t adesc = make_smem_desc_mn(sa), bdesc = make_smem_desc_mn(sb);
+#pragma unroll
+          for (int k = 0; k < 64 / UMMA_K; ++k) {
+            // advance 16 pixel rows = 2048 bytes along K: +128 in 16-byte units
+            umma_f16(tmem_d, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (first && k == 0) ? 0u : 1u);
+          }
+          first = false;
+          umma_commit(smem_u32(&empty_bar[stage]));
+          if (r + 64 >= r1) umma_commit(smem_u32(&tmem_full[acc]));
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      int sp, co0, ci0; decode(u, sp, co0, ci0);
+      mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
+      tc_fence_after();
+      const int co = co0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+        if (co < p.Co) {
+          float* dst = p.dw + (long long)co * p.ldw + ci0 + c0;
+          if (ci0 + c0 + 32 <= p.Ci && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              red_add_v4(dst + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (ci0 + c0 + j < p.Ci) atomicAdd(dst + j, __uint_as_float(v[j]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (PRO_GN && warp >= 8) {
+    // X tile: (BN/64) boxes of [64 pixel rows][64 channels]; thread -> one pixel row, half of the boxes
+    const int t = threadIdx.x - 256;           // 0..127
+    const int r = t & 63, half = t >> 6;
+    constexpr int kBoxes = BN / 64;
+    constexpr int kBoxesPerThread = (kBoxes + 1) / 2;
+    int stage = 0; uint32_t phase = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      int sp, co0, ci0; decode(u, sp, co0, ci0);
+      const int r0 = sp * p.rows_per_split, r1 = min(p.M, r0 + p.rows_per_split);
+      for (int rr = r0; rr < r1; rr += 64) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        uint8_t* sb = smem + stage * C::kStageBytes + C::kABytes;
+        const int grow = rr + r;
+        const bool live = grow < p.M;
+        const int sample = min(grow, p.M - 1) / p.rows_per_sample;
+#pragma unroll
+        for (int bi = 0; bi < kBoxesPerThread; ++bi) {
+          const int box = half * kBoxesPerThread + bi;
+          if (box < kBoxes) {
+            const int cbase = ci0 + box * 64;
+            const float4* ca = reinterpret_cast<const float4*>(p.pro_a + (long long)sample * p.pro_ld + cbase);
+            const float4* cb = reinterpret_cast<const float4*>(p.pro_b + (long long)sample * p.pro_ld + cbase);
+            const bool in_range = cbase < p.pro_ld;      // coefficient rows are padded to a multiple of 64
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint4* chunk = reinterpret_cast<uint4*>(sb + box * C::kBoxBytes + r * 128 + ((j ^ (r & 7)) << 4));
+              uint4 raw = *chunk;
+              if (live && in_range) {
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+                const float4 a0 = __ldg(ca + 2 * j), a1 = __ldg(ca + 2 * j + 1);
+                const float4 b0 = __ldg(cb + 2 * j), b1 = __ldg(cb + 2 * j + 1);
+                float2 f;
+                f = __bfloat1622float2(h[0]);
+                h[0] = __floats2bfloat162_rn(fmaxf(fmaf(a0.x, f.x, b0.x), 0.f), fmaxf(fmaf(a0.y, f.y, b0.y), 0.f));
+                f = __bfloat1622float2(h[1]);
+                h[1] = __floats2bfloat162_rn(fmaxf(fmaf(a0.z, f.x, b0.z), 0.f), fmaxf(fmaf(a0.w, f.y, b0.w), 0.f));
+                f = __bfloat1622float2(h[2]);
+                h[2] = __floats2bfloat162_rn(fmaxf(fmaf(a1.x, f.x, b1.x), 0.f), fmaxf(fmaf(a1.y, f.y, b1.y), 0.f));
+                f = __bfloat1622float2(h[3]);
+                h[3] = __floats2bfloat162_rn(fmaxf(fmaf(a1.z, f.x, b1.z), 0.f), fmaxf(fmaf(a1.w, f.y, b1.w), 0.f));
+              } else {
+                raw = make_uint4(0u, 0u, 0u, 0u);
+              }
+              *chunk = raw;
+            }
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(smem_u32(&ready_bar[stage]));
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::kTmemCols) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -366,6 +609,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 // 2-D bf16 tensor map: inner dim `cols` (contiguous), outer dim `rows` with row stride `ld` elements.
 int make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  // inner box is always 64 elements = 128 bytes = the swizzle span
   auto enc = get_encode();
   if (!enc) return -10;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -443,4 +687,61 @@ DLB_API int dlb_gemm_tc(const void* a, long long lda, const void* b, long long l
     case 128: return dispatch<128>(ta, tb, p, pro, sts, sms, st);
     default: return dispatch<256>(ta, tb, p, pro, sts, sms, st);
   }
+}
+
+namespace {
+template <int BN, bool PRO>
+int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const WgradParams& p, int grid, cudaStream_t st) {
+  using C = WCfg<BN>;
+  auto kern = wgrad_tc_kernel<BN, PRO>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  kern<<<grid, PRO ? 384 : 256, C::kSmemBytes, st>>>(tdy, tx, p);
+  return dlb_post_launch();
+}
+}  // namespace
+
+// dW[Co][ldw] (fp32, zero-initialised by the caller or accumulated into) += dY[M,Co]^T * pro(X[M,Ci]).
+// dY / X: bf16 row-major with row strides lddy / ldx (elements, multiples of 8).
+DLB_API int dlb_wgrad_tc(const void* dy, long long lddy, const void* x, long long ldx, float* dw, long long ldw, int M, int Co, int Ci,
+                         const float* pro_a, const float* pro_b, long long pro_ld, int rows_per_sample, int sm_limit, void* stream) {
+  if (M <= 0 || Co <= 0 || Ci <= 0) return 0;
+  if ((lddy % 8) || (ldx % 8) || ((uintptr_t)dy & 15) || ((uintptr_t)x & 15) || (Co % 8) || (Ci % 8)) return -3;
+  if (pro_a && ((pro_ld % 64) || pro_ld < Ci || ((uintptr_t)pro_a & 15) || ((uintptr_t)pro_b & 15))) return -5;
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int sms = sm_count;
+  if (sm_limit > 0 && sm_limit < sms) sms = sm_limit;
+  const int bn = Ci <= 64 ? 64 : (Ci <= 128 ? 128 : 256);
+  const int co_tiles = (Co + 127) / 128, ci_tiles = (Ci + bn - 1) / bn;
+  int splits = (2 * sms + co_tiles * ci_tiles - 1) / (co_tiles * ci_tiles);
+  int max_splits = (M + 255) / 256;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int rows = (M + splits - 1) / splits;
+  rows = (rows + 63) / 64 * 64;
+  splits = (M + rows - 1) / rows;
+  CUtensorMap tdy, tx;
+  int rc = make_map(&tdy, dy, M, Co, lddy, 64);
+  if (rc) return rc;
+  rc = make_map(&tx, x, M, Ci, ldx, 64);
+  if (rc) return rc;
+  WgradParams p;
+  p.M = M; p.Co = Co; p.Ci = Ci; p.dw = dw; p.ldw = ldw; p.rows_per_split = rows; p.num_splits = splits;
+  p.pro_a = pro_a; p.pro_b = pro_b; p.pro_ld = pro_ld; p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : M;
+  const int units = co_tiles * ci_tiles * splits;
+  const int grid = units < sms ? units : sms;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool pro = pro_a != nullptr;
+  if (bn == 64) return pro ? launch_wgrad<64, true>(tdy, tx, p, grid, st) : launch_wgrad<64, false>(tdy, tx, p, grid, st);
+  if (bn == 128) return pro ? launch_wgrad<128, true>(tdy, tx, p, grid, st) : launch_wgrad<128, false>(tdy, tx, p, grid, st);
+  return pro ? launch_wgrad<256, true>(tdy, tx, p, grid, st) : launch_wgrad<256, false>(tdy, tx, p, grid, st);
 }

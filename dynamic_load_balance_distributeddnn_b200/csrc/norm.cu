@@ -24,12 +24,15 @@ constexpr int kThreads = 256;
 // MODE 0: q0 = x, q1 = x*x                    (inputs: x)
 // MODE 1: q0 = dz, q1 = dz*x, dz = dy*(y>0)   (inputs: x, dy, y)  [relu]
 // MODE 2: q0 = dy, q1 = dy*x                  (inputs: x, dy)     [no relu]
+// MODE 3: as MODE 1 but the ReLU mask is recomputed as (ca[n,c]*x + cb[n,c] > 0) from the forward's affine
+//         coefficients, so the normalised activation y never has to exist in memory
 template <typename T, int V, int MODE>
 __global__ void __launch_bounds__(kThreads)
 nc_reduce2_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy,
                   const T* __restrict__ y, int64_t ldy, float* __restrict__ table, int64_t table_ns,
                   int HW, int C, int rows_per_block, const float* __restrict__ mean,
-                  const float* __restrict__ rstd, int G, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                  const float* __restrict__ rstd, int G, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                  const float* __restrict__ coef_a, const float* __restrict__ coef_b, int64_t coef_ld) {
   extern __shared__ float smem[];            // [2*C]
   const int n = blockIdx.y;
   const int lanes = C / V;                   // channel-vector lanes
@@ -46,6 +49,11 @@ nc_reduce2_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy
 #pragma unroll
       for (int i = 0; i < V; ++i) { a0[i] = 0.f; a1[i] = 0.f; }
       const int c = lane * V;
+      float ka[V], kb[V];
+      if constexpr (MODE == 3) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) { ka[i] = coef_a[(int64_t)n * coef_ld + c + i]; kb[i] = coef_b[(int64_t)n * coef_ld + c + i]; }
+      }
       constexpr int UNR = (MODE == 0) ? 2 : 1;
       for (int rb = r0 + rl; rb < r1; rb += row_lanes * UNR) {
         float xv[UNR][V], gv[UNR][V], yv[UNR][V];
@@ -71,6 +79,7 @@ nc_reduce2_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy
               for (int i = 0; i < V; ++i) {
                 float gz = gv[u][i];
                 if constexpr (MODE == 1) gz = yv[u][i] > 0.f ? gz : 0.f;
+                if constexpr (MODE == 3) gz = fmaf(ka[i], xv[u][i], kb[i]) > 0.f ? gz : 0.f;
                 a0[i] += gz; a1[i] += gz * xv[u][i];
               }
             }
@@ -131,6 +140,32 @@ __global__ void gn_finalize_kernel(const float* __restrict__ table, int64_t tabl
   const float var = fmaxf(ss * m - mu * mu, 0.f);
   mean[idx] = mu;
   rstd[idx] = rsqrtf(var + eps);
+}
+
+// group statistics + per-(sample, channel) affine coefficients for a fused GN prologue:
+//   a[n][c] = gamma[c]*rstd,  b[n][c] = beta[c] - mean*a   (rows padded to `ld` floats, zero filled)
+__global__ void gn_coeff_kernel(const float* __restrict__ table, int64_t table_ns, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float* __restrict__ mean, float* __restrict__ rstd,
+                                float* __restrict__ ca, float* __restrict__ cb, int64_t ld, int C, int G, int HW, float eps) {
+  extern __shared__ float sm[];              // mu[G], rs[G]
+  const int n = blockIdx.x, cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    const float* t = table + (int64_t)n * table_ns + (int64_t)g * cpg * 2;
+    float s = 0.f, ss = 0.f;
+    for (int i = 0; i < cpg; ++i) { s += t[2 * i]; ss += t[2 * i + 1]; }
+    const float m = 1.f / ((float)cpg * (float)HW);
+    const float mu = s * m;
+    const float r = rsqrtf(fmaxf(ss * m - mu * mu, 0.f) + eps);
+    sm[g] = mu; sm[G + g] = r;
+    mean[n * G + g] = mu; rstd[n * G + g] = r;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < ld; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    if (c < C) { const int g = c / cpg; a = gamma[c] * sm[G + g]; b = beta[c] - sm[g] * a; }
+    ca[(int64_t)n * ld + c] = a;
+    cb[(int64_t)n * ld + c] = b;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -220,13 +255,15 @@ gn_fwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
 
 // ---------------------------------------------------------------------------------------------
 // (2b) backward apply: dx (+)= k1[c]*dz + k2[c]*x + k3[c];  optional dres = dz
-template <typename T, int V, bool RELU, bool RES, bool ACC>
+// RELU: 0 = no activation, 1 = mask from the saved output y, 2 = mask recomputed from (coef_a, coef_b)
+template <typename T, int V, int RELU, bool RES, bool ACC>
 __global__ void __launch_bounds__(kThreads)
 gn_bwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy,
                     const T* __restrict__ y, int64_t ldy, T* __restrict__ dx, int64_t lddx,
                     T* __restrict__ dres, int64_t lddr, const float* __restrict__ gamma,
                     const float* __restrict__ mean, const float* __restrict__ rstd,
-                    const float* __restrict__ table, int64_t table_ns, int HW, int C, int G, int rows_per_block) {
+                    const float* __restrict__ table, int64_t table_ns, int HW, int C, int G, int rows_per_block,
+                    const float* __restrict__ coef_a, const float* __restrict__ coef_b, int64_t coef_ld) {
   extern __shared__ float smem[];            // k1[C], k2[C], k3[C], s1[G], s2[G]
   float* k1 = smem;
   float* k2 = smem + C;
@@ -265,9 +302,13 @@ gn_bwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
     const int lane = threadIdx.x % lanes, rl = threadIdx.x / lanes, row_lanes = kThreads / lanes;
     if (rl < row_lanes) {
       const int c = lane * V;
-      float q1[V], q2[V], q3[V];
+      float q1[V], q2[V], q3[V], ka[V], kb[V];
 #pragma unroll
       for (int k = 0; k < V; ++k) { q1[k] = k1[c + k]; q2[k] = k2[c + k]; q3[k] = k3[c + k]; }
+      if constexpr (RELU == 2) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) { ka[k] = coef_a[(int64_t)n * coef_ld + c + k]; kb[k] = coef_b[(int64_t)n * coef_ld + c + k]; }
+      }
       constexpr int UNR = 1;
       for (int rb = r0 + rl; rb < r1; rb += row_lanes * UNR) {
         float xv[UNR][V], gv[UNR][V], yv[UNR][V], old[UNR][V];
@@ -278,7 +319,7 @@ gn_bwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
             const int64_t row = (int64_t)n * HW + r;
             load_vec<T, V>(x + row * ldx + c, xv[u]);
             load_vec<T, V>(dy + row * lddy + c, gv[u]);
-            if constexpr (RELU) load_vec<T, V>(y + row * ldy + c, yv[u]);
+            if constexpr (RELU == 1) load_vec<T, V>(y + row * ldy + c, yv[u]);
             if constexpr (ACC) load_vec<T, V>(dx + row * lddx + c, old[u]);
           }
         }
@@ -291,7 +332,8 @@ gn_bwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
 #pragma unroll
             for (int k = 0; k < V; ++k) {
               float gz = gv[u][k];
-              if constexpr (RELU) gz = yv[u][k] > 0.f ? gz : 0.f;
+              if constexpr (RELU == 1) gz = yv[u][k] > 0.f ? gz : 0.f;
+              if constexpr (RELU == 2) gz = fmaf(ka[k], xv[u][k], kb[k]) > 0.f ? gz : 0.f;
               gv[u][k] = gz;
               out[k] = fmaf(q1[k], gz, fmaf(q2[k], xv[u][k], q3[k]));
               if constexpr (ACC) out[k] += old[u][k];
@@ -312,11 +354,16 @@ gn_bwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
     float xv[V], gv[V], out[V];
     load_vec<T, V>(x + row * ldx + c, xv);
     load_vec<T, V>(dy + row * lddy + c, gv);
-    if constexpr (RELU) {
+    if constexpr (RELU == 1) {
       float yv[V];
       load_vec<T, V>(y + row * ldy + c, yv);
 #pragma unroll
       for (int k = 0; k < V; ++k) gv[k] = yv[k] > 0.f ? gv[k] : 0.f;
+    }
+    if constexpr (RELU == 2) {
+#pragma unroll
+      for (int k = 0; k < V; ++k)
+        gv[k] = fmaf(coef_a[(int64_t)n * coef_ld + c + k], xv[k], coef_b[(int64_t)n * coef_ld + c + k]) > 0.f ? gv[k] : 0.f;
     }
     if constexpr (RES) store_vec<T, V>(dres + row * lddr + c, gv);
 #pragma unroll
@@ -374,14 +421,15 @@ template <typename T, int V>
 int reduce2_launch(int mode, const void* x, int64_t ldx, const void* dy, int64_t lddy, const void* y,
                    int64_t ldy, float* table, int64_t table_ns, int N, int HW, int C, cudaStream_t st,
                    const float* mean = nullptr, const float* rstd = nullptr, int G = 1, float* dgamma = nullptr,
-                   float* dbeta = nullptr) {
+                   float* dbeta = nullptr, const float* ca = nullptr, const float* cb = nullptr, int64_t cld = 0) {
   dim3 grid; int rpb;
   grid_for(N, HW, C, V, grid, rpb);
   const size_t sm = 2 * C * sizeof(float);
   const T* X = (const T*)x; const T* DY = (const T*)dy; const T* Y = (const T*)y;
-  if (mode == 0) nc_reduce2_kernel<T, V, 0><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta);
-  else if (mode == 1) nc_reduce2_kernel<T, V, 1><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta);
-  else nc_reduce2_kernel<T, V, 2><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta);
+  if (mode == 0) nc_reduce2_kernel<T, V, 0><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, cld);
+  else if (mode == 1) nc_reduce2_kernel<T, V, 1><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, cld);
+  else if (mode == 3) nc_reduce2_kernel<T, V, 3><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, cld);
+  else nc_reduce2_kernel<T, V, 2><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, cld);
   return dlb_post_launch();
 }
 
@@ -404,20 +452,18 @@ template <typename T, int V>
 int bwd_apply_launch(const void* x, int64_t ldx, const void* dy, int64_t lddy, const void* y, int64_t ldy,
                      void* dx, int64_t lddx, void* dres, int64_t lddr, const float* gamma,
                      const float* mean, const float* rstd, const float* table, int64_t table_ns, int N, int HW, int C,
-                     int G, int relu, int acc, cudaStream_t st) {
+                     int G, int relu, int acc, cudaStream_t st, const float* ca = nullptr, const float* cb = nullptr,
+                     int64_t cld = 0) {
   dim3 grid; int rpb;
   grid_for(N, HW, C, V, grid, rpb);
   const size_t sm = (3 * C + 2 * G) * sizeof(float);
   const T* X = (const T*)x; const T* DY = (const T*)dy; const T* Y = (const T*)y;
   T* DX = (T*)dx; T* DR = (T*)dres;
-#define GO(RL, RS, AC) gn_bwd_apply_kernel<T, V, RL, RS, AC><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, DX, lddx, DR, lddr, gamma, mean, rstd, table, table_ns, HW, C, G, rpb)
-  if (relu) {
-    if (dres) { if (acc) GO(true, true, true); else GO(true, true, false); }
-    else { if (acc) GO(true, false, true); else GO(true, false, false); }
-  } else {
-    if (dres) { if (acc) GO(false, true, true); else GO(false, true, false); }
-    else { if (acc) GO(false, false, true); else GO(false, false, false); }
-  }
+  const int msrc = !relu ? 0 : (ca ? 2 : 1);
+#define GO(RL, RS, AC) gn_bwd_apply_kernel<T, V, RL, RS, AC><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, DX, lddx, DR, lddr, gamma, mean, rstd, table, table_ns, HW, C, G, rpb, ca, cb, cld)
+#define GO2(RL) do { if (dres) { if (acc) GO(RL, true, true); else GO(RL, true, false); } else { if (acc) GO(RL, false, true); else GO(RL, false, false); } } while (0)
+  if (msrc == 0) GO2(0); else if (msrc == 1) GO2(1); else GO2(2);
+#undef GO2
 #undef GO
   return dlb_post_launch();
 }
@@ -468,11 +514,43 @@ DLB_API int dlb_nc_reduce2_bwd(int relu, int dtype, const void* x, int64_t ldx, 
   return rc;
 }
 
+// Same, with the ReLU mask recomputed from the forward coefficients (no saved activation needed).
+DLB_API int dlb_nc_reduce2_bwd_coef(int dtype, const void* x, int64_t ldx, const void* dy, int64_t lddy, float* table,
+                                    int64_t table_ns, const float* mean, const float* rstd, float* dgamma, float* dbeta,
+                                    const float* ca, const float* cb, int64_t cld, int N, int HW, int C, int G, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C > 6000) return -2;
+  if (table_ns <= 0) table_ns = 2 * (int64_t)C;
+  cudaMemset2DAsync(table, (size_t)table_ns * sizeof(float), 0, (size_t)C * 2 * sizeof(float), (size_t)N, st);
+  if (dgamma) { cudaMemsetAsync(dgamma, 0, C * sizeof(float), st); cudaMemsetAsync(dbeta, 0, C * sizeof(float), st); }
+  const bool vec = vec_ok(dtype, C, {ldx, lddy}, {x, dy});
+  int rc = 0;
+  DISPATCH(dtype, vec, (rc = reduce2_launch<T, V>(3, x, ldx, dy, lddy, nullptr, 0, table, table_ns, N, HW, C, st, mean, rstd, G, dgamma, dbeta, ca, cb, cld)));
+  return rc;
+}
+
+DLB_API int dlb_gn_bwd_apply_coef(int dtype, const void* x, int64_t ldx, const void* dy, int64_t lddy, void* dx, int64_t lddx,
+                                  const float* gamma, const float* mean, const float* rstd, const float* table, int64_t table_ns,
+                                  const float* ca, const float* cb, int64_t cld, int N, int HW, int C, int G, int acc, void* stream) {
+  int rc = 0;
+  if (table_ns <= 0) table_ns = 2 * (int64_t)C;
+  const bool vec = vec_ok(dtype, C, {ldx, lddy, lddx}, {x, dy, dx});
+  DISPATCH(dtype, vec, (rc = bwd_apply_launch<T, V>(x, ldx, dy, lddy, nullptr, 0, dx, lddx, nullptr, 0, gamma, mean, rstd, table, table_ns, N, HW, C, G, 1, acc, (cudaStream_t)stream, ca, cb, cld)));
+  return rc;
+}
+
 DLB_API int dlb_gn_finalize(const float* table, int64_t table_ns, float* mean, float* rstd, int N, int C, int G, int HW,
                             float eps, void* stream) {
   const int total = N * G;
   if (table_ns <= 0) table_ns = 2 * (int64_t)C;
   gn_finalize_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(table, table_ns, mean, rstd, N, C, G, HW, eps);
+  return dlb_post_launch();
+}
+
+DLB_API int dlb_gn_coeff(const float* table, int64_t table_ns, const float* gamma, const float* beta, float* mean, float* rstd,
+                         float* ca, float* cb, int64_t ld, int N, int C, int G, int HW, float eps, void* stream) {
+  if (table_ns <= 0) table_ns = 2 * (int64_t)C;
+  gn_coeff_kernel<<<N, 256, 2 * G * sizeof(float), (cudaStream_t)stream>>>(table, table_ns, gamma, beta, mean, rstd, ca, cb, ld, C, G, HW, eps);
   return dlb_post_launch();
 }
 

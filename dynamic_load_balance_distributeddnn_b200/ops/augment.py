@@ -43,7 +43,7 @@ def augment(images_u8: torch.Tensor, mean: Sequence[float], std: Sequence[float]
     if images_u8.is_cuda and nat.available():
         lib = nat.require()
         if out is None:
-            out = torch.empty((b, c, h, w), dtype=dtype, device=images_u8.device).contiguous(memory_format=torch.channels_last) \
+            out = torch.empty((b, c, h, w), dtype=dtype, device=images_u8.device, memory_format=torch.channels_last) \
                 if c > 1 else torch.empty((b, c, h, w), dtype=dtype, device=images_u8.device)
         mean_a = (ctypes.c_float * 4)(*([float(m) for m in mean] + [0.0] * (4 - c)))
         std_a = (ctypes.c_float * 4)(*([float(s) for s in std] + [1.0] * (4 - c)))

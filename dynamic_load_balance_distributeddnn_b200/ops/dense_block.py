@@ -22,6 +22,7 @@ from typing import List
 import torch
 
 from . import _native as nat
+from . import gemm_tc
 from .norm import _nhwc_view
 
 _CONV_BWD = torch.ops.aten.convolution_backward
@@ -61,7 +62,7 @@ class _DenseBlockFn(torch.autograd.Function):
         g = params[5].shape[0]
         ct = c0 + n_layers * g
         dt = nat.dtype_code(x.dtype)
-        buf = torch.empty((n, ct, h, w), dtype=x.dtype, device=x.device).contiguous(memory_format=torch.channels_last)
+        buf = torch.empty((n, ct, h, w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
         table = torch.empty((n, ct, 2), dtype=torch.float32, device=x.device)
         tns = 2 * ct
         _copy_slice(lib, x, buf[:, ct - c0:], st)
@@ -75,31 +76,61 @@ class _DenseBlockFn(torch.autograd.Function):
                                          n, hw, c, st), "dense.stats")
         stats(ct - c0, c0)
         saved = []
+        fused = x.dtype == torch.bfloat16 and gemm_tc.available() and (n * hw) >= 128
         for l in range(n_layers):
             g1w, g1b, w1, g2w, g2b, w2 = params[6 * l:6 * l + 6]
             cl = c0 + l * g
             off = ct - cl
+            cm = w1.shape[0]
             mean1 = torch.empty(n * groups, dtype=torch.float32, device=x.device)
             rstd1 = torch.empty_like(mean1)
-            nat.check(lib.dlb_gn_finalize(table.data_ptr() + off * 8, tns, mean1.data_ptr(), rstd1.data_ptr(), n, cl, groups,
-                                          hw, eps, st), "dense.fin1")
-            xhat = torch.empty((n, cl, h, w), dtype=x.dtype, device=x.device).contiguous(memory_format=torch.channels_last)
-            nat.check(lib.dlb_gn_fwd_apply(dt, slice_ptr(off), ct, 0, 0, xhat.data_ptr(), cl, g1w.data_ptr(), g1b.data_ptr(),
-                                           mean1.data_ptr(), rstd1.data_ptr(), n, hw, cl, groups, 1, st), "dense.apply1")
-            y = _conv_fwd(xhat, w1, 0)
-            cm = y.shape[1]
             mean2 = torch.empty(n * groups, dtype=torch.float32, device=x.device)
             rstd2 = torch.empty_like(mean2)
-            t2 = torch.empty(n * cm * 2, dtype=torch.float32, device=x.device)
-            yv, _, _, _, ldy = _nhwc_view(y)
-            yhat = torch.empty_like(yv, memory_format=torch.channels_last)
-            nat.check(lib.dlb_gn_forward(dt, yv.data_ptr(), ldy, 0, 0, yhat.data_ptr(), cm, g2w.data_ptr(), g2b.data_ptr(),
-                                         mean2.data_ptr(), rstd2.data_ptr(), t2.data_ptr(), n, hw, cm, groups, eps, 1, 0, st),
-                      "dense.gn2")
+            if fused and w1.dtype == torch.bfloat16:
+                # GN1-apply + ReLU runs as the A-operand prologue of the tcgen05 GEMM; the normalised
+                # activation is never written to HBM.  The epilogue emits the statistics GN2 needs.
+                kpad = (cl + 63) // 64 * 64
+                ca = torch.empty((n, kpad), dtype=torch.float32, device=x.device)
+                cb = torch.empty((n, kpad), dtype=torch.float32, device=x.device)
+                nat.check(lib.dlb_gn_coeff(table.data_ptr() + off * 8, tns, g1w.data_ptr(), g1b.data_ptr(), mean1.data_ptr(),
+                                           rstd1.data_ptr(), ca.data_ptr(), cb.data_ptr(), kpad, n, cl, groups, hw, eps, st),
+                          "dense.coeff")
+                yv = torch.empty((n, cm, h, w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+                epi = hw % 32 == 0
+                t2 = torch.zeros(n * cm * 2, dtype=torch.float32, device=x.device) if epi else \
+                    torch.empty(n * cm * 2, dtype=torch.float32, device=x.device)
+                w1_2d = gemm_tc._w2d(w1)
+                gemm_tc.gemm_raw(slice_ptr(off), ct, w1_2d.data_ptr(), w1_2d.stride(0), yv.data_ptr(), cm, n * hw, cm, cl,
+                                 x.device, ca, cb, hw, t2 if epi else None, 0, 2 * cm)
+                if not epi:
+                    nat.check(lib.dlb_nc_reduce2(0, dt, yv.data_ptr(), cm, 0, 0, 0, 0, t2.data_ptr(), 0, n, hw, cm, st), "dense.y_stats")
+                nat.check(lib.dlb_gn_finalize(t2.data_ptr(), 2 * cm, mean2.data_ptr(), rstd2.data_ptr(), n, cm, groups, hw, eps, st),
+                          "dense.fin2")
+                yhat = torch.empty_like(yv, memory_format=torch.channels_last)
+                nat.check(lib.dlb_gn_fwd_apply(dt, yv.data_ptr(), cm, 0, 0, yhat.data_ptr(), cm, g2w.data_ptr(), g2b.data_ptr(),
+                                               mean2.data_ptr(), rstd2.data_ptr(), n, hw, cm, groups, 1, st), "dense.apply2")
+                xhat = None
+                coefs = (ca, cb)
+            else:
+                nat.check(lib.dlb_gn_finalize(table.data_ptr() + off * 8, tns, mean1.data_ptr(), rstd1.data_ptr(), n, cl, groups,
+                                              hw, eps, st), "dense.fin1")
+                xhat = torch.empty((n, cl, h, w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+                nat.check(lib.dlb_gn_fwd_apply(dt, slice_ptr(off), ct, 0, 0, xhat.data_ptr(), cl, g1w.data_ptr(), g1b.data_ptr(),
+                                               mean1.data_ptr(), rstd1.data_ptr(), n, hw, cl, groups, 1, st), "dense.apply1")
+                coefs = None
+                y = _conv_fwd(xhat, w1, 0)
+                t2 = torch.empty(n * cm * 2, dtype=torch.float32, device=x.device)
+                yv, _, _, _, ldy = _nhwc_view(y)
+                yhat = torch.empty_like(yv, memory_format=torch.channels_last)
+                nat.check(lib.dlb_gn_forward(dt, yv.data_ptr(), ldy, 0, 0, yhat.data_ptr(), cm, g2w.data_ptr(), g2b.data_ptr(),
+                                             mean2.data_ptr(), rstd2.data_ptr(), t2.data_ptr(), n, hw, cm, groups, eps, 1, 0, st),
+                          "dense.gn2")
             new = _conv_fwd(yhat, w2, 1)
             _copy_slice(lib, new, buf[:, off - g:off], st)
             stats(off - g, g)
-            saved += [xhat, yv, yhat, mean1, rstd1, mean2, rstd2]
+            empty = mean1.new_empty(0)
+            saved += [xhat if xhat is not None else empty, yv, yhat, mean1, rstd1, mean2, rstd2,
+                      coefs[0] if coefs else empty, coefs[1] if coefs else empty]
         ctx.save_for_backward(buf, *params, *saved)
         ctx.cfg = (n_layers, n, c0, h, w, g, ct, groups, eps)
         ctx.mark_non_differentiable(table)
@@ -121,11 +152,11 @@ class _DenseBlockFn(torch.autograd.Function):
         grads: List = [None] * (6 * n_layers)
         for l in reversed(range(n_layers)):
             g1w, g1b, w1, g2w, g2b, w2 = params[6 * l:6 * l + 6]
-            xhat, y, yhat, mean1, rstd1, mean2, rstd2 = saved[7 * l:7 * l + 7]
+            xhat, y, yhat, mean1, rstd1, mean2, rstd2, ca, cb = saved[9 * l:9 * l + 9]
             cl = c0 + l * g
             off = ct - cl
             cm = y.shape[1]
-            dnew = torch.empty((n, g, h, w), dtype=buf.dtype, device=buf.device).contiguous(memory_format=torch.channels_last)
+            dnew = torch.empty((n, g, h, w), dtype=buf.dtype, device=buf.device, memory_format=torch.channels_last)
             _copy_slice(lib, dbuf[:, off - g:off], dnew, st)
             w2c = w2 if w2.dtype == yhat.dtype else w2.to(yhat.dtype)
             dyhat, dw2, _ = _CONV_BWD(dnew, yhat, w2c, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [True, True, False])
@@ -138,21 +169,40 @@ class _DenseBlockFn(torch.autograd.Function):
             nat.check(lib.dlb_gn_backward(dt, y.data_ptr(), cm, dyhat.data_ptr(), cm, yhat.data_ptr(), cm, dy.data_ptr(), cm,
                                           0, 0, g2w.data_ptr(), mean2.data_ptr(), rstd2.data_ptr(), t2.data_ptr(),
                                           dg2.data_ptr(), db2.data_ptr(), n, hw, cm, groups, 1, 0, st), "dense.gn2_bwd")
-            w1c = w1 if w1.dtype == xhat.dtype else w1.to(xhat.dtype)
-            dxhat, dw1, _ = _CONV_BWD(dy, xhat, w1c, None, [1, 1], [0, 0], [1, 1], False, [0, 0], 1, [True, True, False])
-            dxhat = dxhat.contiguous(memory_format=torch.channels_last)
-            # GN1 + ReLU backward, accumulated in place into the gradient buffer slice
             t1 = torch.empty(n * cl * 2, dtype=torch.float32, device=buf.device)
             dg1 = torch.empty(cl, dtype=torch.float32, device=buf.device)
             db1 = torch.empty(cl, dtype=torch.float32, device=buf.device)
             xs = buf.data_ptr() + off * esz
             dxs = dbuf.data_ptr() + off * esz
-            nat.check(lib.dlb_gn_backward(dt, xs, ct, dxhat.data_ptr(), cl, xhat.data_ptr(), cl, dxs, ct, 0, 0,
-                                          g1w.data_ptr(), mean1.data_ptr(), rstd1.data_ptr(), t1.data_ptr(),
-                                          dg1.data_ptr(), db1.data_ptr(), n, hw, cl, groups, 1, 1, st), "dense.gn1_bwd")
+            if xhat.numel() == 0:
+                # fused path: relu(GN1(x)) was never materialised.  dgrad and wgrad run on the tcgen05 kernels
+                # (the wgrad re-applies GN+ReLU to the raw buffer slice in its operand prologue) and the GN1
+                # backward recomputes the ReLU mask from the saved affine coefficients.
+                w1_2d = gemm_tc._w2d(w1)
+                w1_t = w1_2d.t().contiguous()                                      # [cl, cm]: B operand of dX = dY * W
+                dxhat = torch.empty((n, cl, h, w), dtype=buf.dtype, device=buf.device, memory_format=torch.channels_last)
+                gemm_tc.gemm_raw(dy.data_ptr(), cm, w1_t.data_ptr(), w1_t.stride(0), dxhat.data_ptr(), cl, n * hw, cl, cm, buf.device)
+                dw1f = torch.zeros((cm, cl), dtype=torch.float32, device=buf.device)
+                gemm_tc.wgrad_raw(dy.data_ptr(), cm, xs, ct, dw1f, n * hw, cm, cl, buf.device, ca, cb, hw)
+                dw1 = dw1f.view(cm, cl, 1, 1)
+                kpad = ca.shape[1]
+                nat.check(lib.dlb_nc_reduce2_bwd_coef(dt, xs, ct, dxhat.data_ptr(), cl, t1.data_ptr(), 0, mean1.data_ptr(),
+                                                      rstd1.data_ptr(), dg1.data_ptr(), db1.data_ptr(), ca.data_ptr(), cb.data_ptr(),
+                                                      kpad, n, hw, cl, groups, st), "dense.gn1_red")
+                nat.check(lib.dlb_gn_bwd_apply_coef(dt, xs, ct, dxhat.data_ptr(), cl, dxs, ct, g1w.data_ptr(), mean1.data_ptr(),
+                                                    rstd1.data_ptr(), t1.data_ptr(), 0, ca.data_ptr(), cb.data_ptr(), kpad,
+                                                    n, hw, cl, groups, 1, st), "dense.gn1_app")
+            else:
+                w1c = w1 if w1.dtype == xhat.dtype else w1.to(xhat.dtype)
+                dxhat, dw1, _ = _CONV_BWD(dy, xhat, w1c, None, [1, 1], [0, 0], [1, 1], False, [0, 0], 1, [True, True, False])
+                dxhat = dxhat.contiguous(memory_format=torch.channels_last)
+                # GN1 + ReLU backward, accumulated in place into the gradient buffer slice
+                nat.check(lib.dlb_gn_backward(dt, xs, ct, dxhat.data_ptr(), cl, xhat.data_ptr(), cl, dxs, ct, 0, 0,
+                                              g1w.data_ptr(), mean1.data_ptr(), rstd1.data_ptr(), t1.data_ptr(),
+                                              dg1.data_ptr(), db1.data_ptr(), n, hw, cl, groups, 1, 1, st), "dense.gn1_bwd")
             grads[6 * l:6 * l + 6] = [dg1.to(g1w.dtype), db1.to(g1b.dtype), dw1.to(w1.dtype), dg2.to(g2w.dtype),
                                       db2.to(g2b.dtype), dw2.to(w2.dtype)]
-        dx = torch.empty((n, c0, h, w), dtype=buf.dtype, device=buf.device).contiguous(memory_format=torch.channels_last)
+        dx = torch.empty((n, c0, h, w), dtype=buf.dtype, device=buf.device, memory_format=torch.channels_last)
         _copy_slice(lib, dbuf[:, ct - c0:], dx, st)
         return (dx, None, None, *grads)
 

@@ -21,6 +21,7 @@ def _lib():
     if not _DECLARED:
         vp, i64, i32 = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
         nat.declare("dlb_gemm_tc", i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, i32, vp, i64, i32, vp])
+        nat.declare("dlb_wgrad_tc", i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, i32, i32, vp])
         _DECLARED = True
     return lib
 
@@ -53,6 +54,25 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, p
     return out
 
 
+def wgrad_raw(dy_ptr: int, lddy: int, x_ptr: int, ldx: int, dw: torch.Tensor, m: int, co: int, ci: int, device,
+              pro_a: Optional[torch.Tensor] = None, pro_b: Optional[torch.Tensor] = None, rows_per_sample: int = 0,
+              sm_limit: int = 0) -> None:
+    """dw[co, ci] (fp32, pre-zeroed or accumulated into) += dy[m, co]^T @ pro(x[m, ci])."""
+    pro_ld = pro_a.shape[1] if pro_a is not None else 0
+    rc = _lib().dlb_wgrad_tc(dy_ptr, lddy, x_ptr, ldx, dw.data_ptr(), dw.stride(0), m, co, ci, nat.ptr(pro_a), nat.ptr(pro_b),
+                             pro_ld, rows_per_sample, sm_limit, nat.stream_ptr(device))
+    nat.check(rc, "wgrad_tc")
+
+
+def wgrad(dy: torch.Tensor, x: torch.Tensor, pro_a=None, pro_b=None, rows_per_sample: int = 0) -> torch.Tensor:
+    """-> fp32 [Co, Ci] = dy[M,Co]^T @ pro(x[M,Ci]); dy/x bf16 2-D with unit inner stride."""
+    m, co = dy.shape
+    ci = x.shape[1]
+    dw = torch.zeros((co, ci), dtype=torch.float32, device=dy.device)
+    wgrad_raw(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dw, m, co, ci, dy.device, pro_a, pro_b, rows_per_sample)
+    return dw
+
+
 def _w2d(weight: torch.Tensor) -> torch.Tensor:
     """[O, I, 1, 1] (any layout) -> contiguous-row [O, I] view."""
     o, i = weight.shape[0], weight.shape[1]
@@ -66,7 +86,7 @@ class _Conv1x1Fn(torch.autograd.Function):
         xv, n, hw, c, ld = _nhwc_view(x)
         o = weight.shape[0]
         h, w = x.shape[2], x.shape[3]
-        y = torch.empty((n, o, h, w), dtype=x.dtype, device=x.device).contiguous(memory_format=torch.channels_last)
+        y = torch.empty((n, o, h, w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
         w2 = _w2d(weight)
         gemm_raw(xv.data_ptr(), ld, w2.data_ptr(), w2.stride(0), y.data_ptr(), o, n * hw, o, c, x.device)
         ctx.save_for_backward(xv, weight)
@@ -81,7 +101,7 @@ class _Conv1x1Fn(torch.autograd.Function):
         dx = dw = None
         w2 = _w2d(weight)
         if ctx.needs_input_grad[0]:
-            dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device).contiguous(memory_format=torch.channels_last)
+            dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
             wt = w2.t().contiguous()                                   # [Cin, Cout]: B operand of dX = dY * W
             gemm_raw(dyv.data_ptr(), lddy, wt.data_ptr(), wt.stride(0), dx.data_ptr(), c, n * hw, c, o, dy.device)
         if ctx.needs_input_grad[1]:

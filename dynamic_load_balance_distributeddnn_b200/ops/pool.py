@@ -12,7 +12,7 @@ class _AvgPoolFn(torch.autograd.Function):
     def forward(ctx, x, k):
         n, c, h, w = x.shape
         x = x.contiguous(memory_format=torch.channels_last)
-        y = torch.empty((n, c, h // k, w // k), dtype=x.dtype, device=x.device).contiguous(memory_format=torch.channels_last)
+        y = torch.empty((n, c, h // k, w // k), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
         nat.check(nat.require().dlb_avgpool_nhwc(0, nat.dtype_code(x.dtype), x.data_ptr(), y.data_ptr(), n, h, w, c, k,
                                                  nat.stream_ptr(x.device)), "avgpool_fwd")
         ctx.cfg = (n, c, h, w, k)
@@ -22,7 +22,7 @@ class _AvgPoolFn(torch.autograd.Function):
     def backward(ctx, dy):
         n, c, h, w, k = ctx.cfg
         dy = dy.contiguous(memory_format=torch.channels_last)
-        dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device).contiguous(memory_format=torch.channels_last)
+        dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
         nat.check(nat.require().dlb_avgpool_nhwc(1, nat.dtype_code(dy.dtype), dy.data_ptr(), dx.data_ptr(), n, h, w, c, k,
                                                  nat.stream_ptr(dy.device)), "avgpool_bwd")
         return dx, None

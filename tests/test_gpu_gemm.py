@@ -92,3 +92,36 @@ def test_conv1x1_autograd(g):
     assert (y.float() - yr).abs().max().item() < 3e-2 * yr.abs().max().item()
     assert (x.grad.float() - xr.grad).abs().max().item() < 3e-2 * xr.grad.abs().max().item()
     assert (w.grad.float() - wr.grad).abs().max().item() < 3e-2 * wr.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("m,co,ci", [(4096, 128, 64), (65536, 128, 256), (8192, 128, 1024), (1000, 128, 96), (3000, 32, 128),
+                                     (512 * 16, 256, 512), (130, 64, 72)])
+def test_wgrad_mn_major(g, m, co, ci):
+    torch.manual_seed(m + co + ci)
+    dy = (torch.randn(m, co, device="cuda") / 8).bfloat16()
+    x = torch.randn(m, ci, device="cuda").bfloat16()
+    dw = g.wgrad(dy, x)
+    torch.cuda.synchronize()
+    r = dy.float().t() @ x.float()
+    err = (dw - r).abs().max().item()
+    assert err < 5e-3 * max(1.0, r.abs().max().item()), (err, r.abs().max().item())
+
+
+@pytest.mark.parametrize("hw,co,ci", [(1024, 128, 64), (256, 128, 200), (64, 128, 512), (16, 128, 1024)])
+def test_wgrad_with_gn_relu_prologue(g, hw, co, ci):
+    torch.manual_seed(7)
+    ns = 6
+    m = ns * hw
+    big = torch.randn(m, ci + 64, device="cuda").bfloat16()
+    x = big[:, 32:32 + ci] if ci % 8 == 0 else big[:, :ci]          # strided operand (channel slice)
+    dy = (torch.randn(m, co, device="cuda") / 8).bfloat16()
+    kp = (ci + 63) // 64 * 64
+    pa = torch.zeros(ns, kp, device="cuda"); pb = torch.zeros(ns, kp, device="cuda")
+    pa[:, :ci] = torch.rand(ns, ci, device="cuda") + 0.5
+    pb[:, :ci] = torch.randn(ns, ci, device="cuda") * 0.3
+    dw = g.wgrad(dy, x, pa, pb, hw)
+    torch.cuda.synchronize()
+    xa = torch.relu(x.float().reshape(ns, hw, ci) * pa[:, None, :ci] + pb[:, None, :ci]).bfloat16().reshape(m, ci)
+    r = dy.float().t() @ xa.float()
+    err = (dw - r).abs().max().item()
+    assert err < 5e-3 * max(1.0, r.abs().max().item()), (err, r.abs().max().item())
