@@ -30,7 +30,7 @@ constexpr int BM = 128;            // UMMA_M (cta_group::1)
 constexpr int BK = 64;             // 64 bf16 = 128 bytes = one SWIZZLE_128B atom row
 constexpr int UMMA_K = 16;
 constexpr int kNumEpiWarps = 4;
-constexpr int kProWarps = 4;       // prologue-transform warps (PRO_GN only)
+constexpr int kProWarps = 8;       // prologue-transform warps (PRO_GN only): 16 KB per stage must clear in < ~380 cycles
 constexpr uint32_t kSpinLimit = 1u << 20;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,23 +121,29 @@ struct GemmParams {
 };
 
 template <int BN> struct Cfg {
-  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 5 : 6);
+  static constexpr int kStages = BN >= 256 ? 3 : (BN >= 128 ? 5 : 6);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  // epilogue staging: per epilogue warp, (BN/64) boxes of [32 rows][64 cols] bf16 = 4 KB each, 128B-swizzled,
+  // drained with cp.async.bulk.tensor stores (fully coalesced, tails clipped by the tensor map)
+  static constexpr int kHalves = (BN + 63) / 64;
+  static constexpr int kEpiBytes = kNumEpiWarps * kHalves * 4096;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator (+ idle), 3 = idle (keeps epilogue warps at
-// warp ids 4..7 so that (warp_id % 4) selects their TMEM lane quadrant), 4..7 = epilogue, 8..11 = prologue transform.
+// warp ids 4..7 so that (warp_id % 4) selects their TMEM lane quadrant), 4..7 = epilogue, 8..15 = prologue transform.
 template <int BN, bool PRO_GN, bool EPI_STATS>
-__global__ void __launch_bounds__(PRO_GN ? 384 : 256, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+__global__ void __launch_bounds__(PRO_GN ? 512 : 256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* bar_base = smem + C::kStages * C::kStageBytes;
+  uint8_t* epi_base = smem + C::kStages * C::kStageBytes;                  // 1024-byte aligned (stage sizes are)
+  uint8_t* bar_base = epi_base + C::kEpiBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);              // TMA bytes landed
   uint64_t* empty_bar = full_bar + C::kStages;                             // MMA done reading the stage
   uint64_t* ready_bar = empty_bar + C::kStages;                            // PRO_GN: transform done
@@ -153,6 +159,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_d) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -227,13 +234,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===================================== epilogue =========================================
     const int q = warp & 3;                                     // TMEM lane quadrant owned by this warp
     int acc = 0; uint32_t acc_phase = 0;
-    __nv_bfloat16* dptr = reinterpret_cast<__nv_bfloat16*>(p.d);
+    uint8_t* stage_buf = epi_base + q * (C::kHalves * 4096);
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m0 = (t / num_n) * BM, n0 = (t % num_n) * BN;
       mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
+      // the previous tile's bulk stores must have finished READING the staging buffers before we overwrite them
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
@@ -245,15 +255,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           packed[j] = *reinterpret_cast<uint32_t*>(&h);
         }
         const int col = n0 + c0;
-        if (row_ok) {
-          __nv_bfloat16* dst = dptr + (long long)row * p.ldd + col;
-          if (col + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        {
+          // box `c0/64`: [32 rows][128 B], 16-byte chunk j of row r at r*128 + ((j ^ (r & 7)) << 4)
+          uint8_t* box = stage_buf + (c0 >> 6) * 4096 + lane * 128;
+          const int jb = (c0 & 32) ? 4 : 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              reinterpret_cast<uint4*>(dst)[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col + j < p.N) dst[j] = reinterpret_cast<__nv_bfloat16*>(packed)[j];
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(box + (((jb + j) ^ (lane & 7)) << 4)) =
+                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          if ((c0 & 32) || c0 + 32 >= BN) {
+            // a 64-column box (or the final partial one) is complete: hand it to the TMA store engine
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && n0 + (c0 & ~63) < p.N && m0 + q * 32 < p.M) {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(&tmap_d), "r"(smem_u32(stage_buf + (c0 >> 6) * 4096)), "r"(n0 + (c0 & ~63)), "r"(m0 + q * 32)
+                           : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
           }
         }
         if constexpr (EPI_STATS) {
@@ -299,31 +318,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output bytes are globally visible
+    __syncwarp();
   } else if (PRO_GN && warp >= 8) {
     // ============================ A-operand prologue: GN-apply + ReLU ========================
     // The TMA wrote a 128-row x 64-col bf16 tile with the 128B swizzle: 16-byte chunk j of row r lives at
     // r*128 + ((j ^ (r & 7)) << 4).  Thread (pw, lane) transforms rows pw*32+lane ... in place.
-    const int pw = warp - 8;
+    // thread -> one 16-byte chunk column (8 channels) and every 16th row: the affine coefficients of its
+    // channels stay in registers while it walks down the rows (reloaded only when the sample changes)
+    const int tp = threadIdx.x - 256;          // 0..255
+    const int cc = tp & 7, r_base = tp >> 3;   // r_base 0..31
     int stage = 0; uint32_t phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m0 = (t / num_n) * BM;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         uint8_t* sa = smem + stage * C::kStageBytes;
-        const int r = pw * 32 + lane;
-        const int grow = m0 + r;
-        const int sample = min(grow, p.M - 1) / p.rows_per_sample;
-        // coefficient rows are padded to a multiple of BK and zero-filled by the host (a = b = 0 beyond K)
-        const float4* ca = reinterpret_cast<const float4*>(p.pro_a + (long long)sample * p.pro_ld + kb * BK);
-        const float4* cb = reinterpret_cast<const float4*>(p.pro_b + (long long)sample * p.pro_ld + kb * BK);
-        const bool live = grow < p.M;
+        int cur = -1;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint4* chunk = reinterpret_cast<uint4*>(sa + r * 128 + ((j ^ (r & 7)) << 4));
+        for (int i = 0; i < 4; ++i) {
+          const int r = r_base + 32 * i;
+          const int grow = m0 + r;
+          const bool live = grow < p.M;
+          const int sample = min(grow, p.M - 1) / p.rows_per_sample;
+          if (sample != cur) {
+            // coefficient rows are padded to a multiple of BK and zero-filled by the host (a = b = 0 beyond K)
+            const float4* ca = reinterpret_cast<const float4*>(p.pro_a + (long long)sample * p.pro_ld + kb * BK + cc * 8);
+            const float4* cb = reinterpret_cast<const float4*>(p.pro_b + (long long)sample * p.pro_ld + kb * BK + cc * 8);
+            a0 = __ldg(ca); a1 = __ldg(ca + 1); b0 = __ldg(cb); b1 = __ldg(cb + 1);
+            cur = sample;
+          }
+          uint4* chunk = reinterpret_cast<uint4*>(sa + r * 128 + ((cc ^ (r & 7)) << 4));
           uint4 raw = *chunk;
           __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
-          const float4 a0 = __ldg(ca + 2 * j), a1 = __ldg(ca + 2 * j + 1);
-          const float4 b0 = __ldg(cb + 2 * j), b1 = __ldg(cb + 2 * j + 1);
           float2 f;
           f = __bfloat1622float2(h[0]);
           h[0] = __floats2bfloat162_rn(fmaxf(fmaf(a0.x, f.x, b0.x), 0.f), fmaxf(fmaf(a0.y, f.y, b0.y), 0.f));
@@ -398,7 +426,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 }
 
 template <int BN, bool PRO_GN>
-__global__ void __launch_bounds__(PRO_GN ? 384 : 256, 1)
+__global__ void __launch_bounds__(PRO_GN ? 512 : 256, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x, const WgradParams p) {
   using C = WCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -532,52 +560,54 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (PRO_GN && warp >= 8) {
-    // X tile: (BN/64) boxes of [64 pixel rows][64 channels]; thread -> one pixel row, half of the boxes
-    const int t = threadIdx.x - 256;           // 0..127
-    const int r = t & 63, half = t >> 6;
+    // X tile: (BN/64) boxes of [64 pixel rows][64 channels].  thread -> one chunk column (8 channels) of one
+    // box and every (256/cols)-th pixel row; coefficients stay in registers down the rows.
+    const int tp = threadIdx.x - 256;          // 0..255
     constexpr int kBoxes = BN / 64;
-    constexpr int kBoxesPerThread = (kBoxes + 1) / 2;
+    constexpr int kCols = kBoxes * 8;          // chunk columns in the tile: 8, 16 or 32
+    constexpr int kRowStep = 256 / kCols;      // 32, 16, 8
+    const int ccg = tp % kCols, r_base = tp / kCols;
+    const int box = ccg >> 3, cc = ccg & 7;
     int stage = 0; uint32_t phase = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
       int sp, co0, ci0; decode(u, sp, co0, ci0);
       const int r0 = sp * p.rows_per_split, r1 = min(p.M, r0 + p.rows_per_split);
+      const int cbase = ci0 + box * 64 + cc * 8;
+      const bool in_range = cbase < p.pro_ld;            // coefficient rows are padded to a multiple of 64
       for (int rr = r0; rr < r1; rr += 64) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
-        uint8_t* sb = smem + stage * C::kStageBytes + C::kABytes;
-        const int grow = rr + r;
-        const bool live = grow < p.M;
-        const int sample = min(grow, p.M - 1) / p.rows_per_sample;
+        uint8_t* sb = smem + stage * C::kStageBytes + C::kABytes + box * C::kBoxBytes;
+        int cur = -1;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
 #pragma unroll
-        for (int bi = 0; bi < kBoxesPerThread; ++bi) {
-          const int box = half * kBoxesPerThread + bi;
-          if (box < kBoxes) {
-            const int cbase = ci0 + box * 64;
+        for (int i = 0; i < 64 / kRowStep; ++i) {
+          const int r = r_base + kRowStep * i;
+          const int grow = rr + r;
+          const bool live = grow < p.M && in_range;
+          const int sample = min(grow, p.M - 1) / p.rows_per_sample;
+          if (sample != cur && in_range) {
             const float4* ca = reinterpret_cast<const float4*>(p.pro_a + (long long)sample * p.pro_ld + cbase);
             const float4* cb = reinterpret_cast<const float4*>(p.pro_b + (long long)sample * p.pro_ld + cbase);
-            const bool in_range = cbase < p.pro_ld;      // coefficient rows are padded to a multiple of 64
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              uint4* chunk = reinterpret_cast<uint4*>(sb + box * C::kBoxBytes + r * 128 + ((j ^ (r & 7)) << 4));
-              uint4 raw = *chunk;
-              if (live && in_range) {
-                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
-                const float4 a0 = __ldg(ca + 2 * j), a1 = __ldg(ca + 2 * j + 1);
-                const float4 b0 = __ldg(cb + 2 * j), b1 = __ldg(cb + 2 * j + 1);
-                float2 f;
-                f = __bfloat1622float2(h[0]);
-                h[0] = __floats2bfloat162_rn(fmaxf(fmaf(a0.x, f.x, b0.x), 0.f), fmaxf(fmaf(a0.y, f.y, b0.y), 0.f));
-                f = __bfloat1622float2(h[1]);
-                h[1] = __floats2bfloat162_rn(fmaxf(fmaf(a0.z, f.x, b0.z), 0.f), fmaxf(fmaf(a0.w, f.y, b0.w), 0.f));
-                f = __bfloat1622float2(h[2]);
-                h[2] = __floats2bfloat162_rn(fmaxf(fmaf(a1.x, f.x, b1.x), 0.f), fmaxf(fmaf(a1.y, f.y, b1.y), 0.f));
-                f = __bfloat1622float2(h[3]);
-                h[3] = __floats2bfloat162_rn(fmaxf(fmaf(a1.z, f.x, b1.z), 0.f), fmaxf(fmaf(a1.w, f.y, b1.w), 0.f));
-              } else {
-                raw = make_uint4(0u, 0u, 0u, 0u);
-              }
-              *chunk = raw;
-            }
+            a0 = __ldg(ca); a1 = __ldg(ca + 1); b0 = __ldg(cb); b1 = __ldg(cb + 1);
+            cur = sample;
           }
+          uint4* chunk = reinterpret_cast<uint4*>(sb + r * 128 + ((cc ^ (r & 7)) << 4));
+          uint4 raw = *chunk;
+          if (live) {
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+            float2 f;
+            f = __bfloat1622float2(h[0]);
+            h[0] = __floats2bfloat162_rn(fmaxf(fmaf(a0.x, f.x, b0.x), 0.f), fmaxf(fmaf(a0.y, f.y, b0.y), 0.f));
+            f = __bfloat1622float2(h[1]);
+            h[1] = __floats2bfloat162_rn(fmaxf(fmaf(a0.z, f.x, b0.z), 0.f), fmaxf(fmaf(a0.w, f.y, b0.w), 0.f));
+            f = __bfloat1622float2(h[2]);
+            h[2] = __floats2bfloat162_rn(fmaxf(fmaf(a1.x, f.x, b1.x), 0.f), fmaxf(fmaf(a1.y, f.y, b1.y), 0.f));
+            f = __bfloat1622float2(h[3]);
+            h[3] = __floats2bfloat162_rn(fmaxf(fmaf(a1.z, f.x, b1.z), 0.f), fmaxf(fmaf(a1.w, f.y, b1.w), 0.f));
+          } else {
+            raw = make_uint4(0u, 0u, 0u, 0u);
+          }
+          *chunk = raw;
         }
         fence_proxy_async();
         mbar_arrive(smem_u32(&ready_bar[stage]));
@@ -623,7 +653,7 @@ int make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, 
 }
 
 template <int BN, bool PRO, bool STATS>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int sms, cudaStream_t st) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p, int sms, cudaStream_t st) {
   using C = Cfg<BN>;
   auto kern = gemm_tc_kernel<BN, PRO, STATS>;
   static bool configured = false;
@@ -634,16 +664,16 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
   }
   const int num_tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   const int grid = num_tiles < sms ? num_tiles : sms;
-  kern<<<grid, PRO ? 384 : 256, C::kSmemBytes, st>>>(ta, tb, p);
+  kern<<<grid, PRO ? 512 : 256, C::kSmemBytes, st>>>(ta, tb, td, p);
   return dlb_post_launch();
 }
 
 template <int BN>
-int dispatch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, bool pro, bool stats, int sms, cudaStream_t st) {
-  if (pro && stats) return launch<BN, true, true>(ta, tb, p, sms, st);
-  if (pro) return launch<BN, true, false>(ta, tb, p, sms, st);
-  if (stats) return launch<BN, false, true>(ta, tb, p, sms, st);
-  return launch<BN, false, false>(ta, tb, p, sms, st);
+int dispatch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p, bool pro, bool stats, int sms, cudaStream_t st) {
+  if (pro && stats) return launch<BN, true, true>(ta, tb, td, p, sms, st);
+  if (pro) return launch<BN, true, false>(ta, tb, td, p, sms, st);
+  if (stats) return launch<BN, false, true>(ta, tb, td, p, sms, st);
+  return launch<BN, false, false>(ta, tb, td, p, sms, st);
 }
 
 }  // namespace
@@ -659,6 +689,7 @@ DLB_API int dlb_gemm_tc(const void* a, long long lda, const void* b, long long l
                         int sm_limit, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((K % 8) || (lda % 8) || (ldb % 8) || ((uintptr_t)a & 15) || ((uintptr_t)b & 15)) return -3;
+  if ((ldd % 8) || ((uintptr_t)d & 15) || (N % 8)) return -6;
   if (stats && (rows_per_sample % 32)) return -4;
   if (pro_a && ((pro_ld % BK) || pro_ld < K || ((uintptr_t)pro_a & 15) || ((uintptr_t)pro_b & 15))) return -5;
   static int sm_count = 0;
@@ -675,6 +706,9 @@ DLB_API int dlb_gemm_tc(const void* a, long long lda, const void* b, long long l
   if (rc) return rc;
   rc = make_map(&tb, b, N, K, ldb, bn);
   if (rc) return rc;
+  CUtensorMap td;
+  rc = make_map(&td, d, M, N, ldd, 32);                 // output boxes: 32 rows x 64 columns, 128B swizzle
+  if (rc) return rc;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.d = d; p.ldd = ldd; p.accumulate_out = 0;
   p.pro_a = pro_a; p.pro_b = pro_b; p.pro_ld = pro_ld; p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : M;
@@ -682,10 +716,10 @@ DLB_API int dlb_gemm_tc(const void* a, long long lda, const void* b, long long l
   cudaStream_t st = (cudaStream_t)stream;
   const bool pro = pro_a != nullptr, sts = stats != nullptr;
   switch (bn) {
-    case 32: return dispatch<32>(ta, tb, p, pro, sts, sms, st);
-    case 64: return dispatch<64>(ta, tb, p, pro, sts, sms, st);
-    case 128: return dispatch<128>(ta, tb, p, pro, sts, sms, st);
-    default: return dispatch<256>(ta, tb, p, pro, sts, sms, st);
+    case 32: return dispatch<32>(ta, tb, td, p, pro, sts, sms, st);
+    case 64: return dispatch<64>(ta, tb, td, p, pro, sts, sms, st);
+    case 128: return dispatch<128>(ta, tb, td, p, pro, sts, sms, st);
+    default: return dispatch<256>(ta, tb, td, p, pro, sts, sms, st);
   }
 }
 
@@ -700,7 +734,7 @@ int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const WgradParam
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  kern<<<grid, PRO ? 384 : 256, C::kSmemBytes, st>>>(tdy, tx, p);
+  kern<<<grid, PRO ? 512 : 256, C::kSmemBytes, st>>>(tdy, tx, p);
   return dlb_post_launch();
 }
 }  // namespace

@@ -31,3 +31,25 @@ for (m, n, k) in shapes:
     byts = (m * k + n * k + m * n) * 2
     print(f"M={m} N={n} K={k}: tcgen05 {t1*1e3:8.1f} us ({byts/t1/1e6:6.0f} GB/s, {100*byts/t1/1e6/PEAK:5.1f}% of measured copy peak, "
           f"{2*m*n*k/t1/1e9:7.1f} TFLOP/s)   cuBLAS {t2*1e3:8.1f} us ({byts/t2/1e6:6.0f} GB/s)", flush=True)
+
+# ---- fused variants on DenseNet shapes: GN+ReLU prologue (+ stats epilogue), and the MN-major wgrad ----
+print("-- fused variants")
+fshapes = [(512, 1024, 128, 256), (512, 256, 128, 512), (512, 64, 128, 1024)] if not quick else [(512, 1024, 128, 256)]
+for (ns, hw, n, k) in fshapes:
+    m = ns * hw
+    a = torch.randn(m, k, device="cuda").bfloat16(); b = torch.randn(n, k, device="cuda").bfloat16()
+    d = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+    pa = torch.rand(ns, k, device="cuda") + 0.5; pb = torch.randn(ns, k, device="cuda") * 0.1
+    table = torch.zeros(ns, n, 2, device="cuda")
+    dy = torch.randn(m, n, device="cuda").bfloat16()
+    byts = (m * k + n * k + m * n) * 2
+    t0 = timeit(lambda: gemm_tc.gemm(a, b, out=d))
+    t1 = timeit(lambda: gemm_tc.gemm(a, b, out=d, pro_a=pa, pro_b=pb, rows_per_sample=hw))
+    t2 = timeit(lambda: gemm_tc.gemm(a, b, out=d, pro_a=pa, pro_b=pb, rows_per_sample=hw, stats=table, stats_ns=2 * n))
+    t3 = timeit(lambda: gemm_tc.gemm(a, b, out=d, rows_per_sample=hw, stats=table, stats_ns=2 * n))
+    dw = torch.zeros(n, k, device="cuda")
+    t4 = timeit(lambda: gemm_tc.wgrad_raw(dy.data_ptr(), n, a.data_ptr(), k, dw, m, n, k, a.device))
+    t5 = timeit(lambda: gemm_tc.wgrad_raw(dy.data_ptr(), n, a.data_ptr(), k, dw, m, n, k, a.device, pa, pb, hw))
+    t6 = timeit(lambda: torch.matmul(dy.t(), a))
+    print(f"N={ns} HW={hw} Cout={n} Cin={k}: plain {t0*1e3:6.1f}  +pro {t1*1e3:6.1f}  +pro+stats {t2*1e3:6.1f}  +stats {t3*1e3:6.1f} us "
+          f"(fwd bytes {byts/1e6:.0f} MB -> {byts/t2/1e6:5.0f} GB/s fused) | wgrad {t4*1e3:6.1f}  +pro {t5*1e3:6.1f}  cuBLAS {t6*1e3:6.1f} us", flush=True)
