@@ -54,6 +54,10 @@ class SelfAttention(nn.Module):
         s, b, d = x.shape
         h, hd = self.nhead, d // self.nhead
         qkv = ops.linear(x, self.in_proj_weight, self.in_proj_bias)          # [S,B,3D]
+        from ..ops import attention as fused_attn
+        if fused_attn.supported(qkv, h):
+            # whole-sequence fused kernel: scores, causal softmax, dropout and PV stay on chip
+            return self.out_proj(fused_attn.causal_attention_packed(qkv, h, self.p if self.training else 0.0))
         q, k, v = qkv.view(s, b, 3, h, hd).permute(2, 1, 3, 0, 4)            # each [B,H,S,hd]
         o = ops.causal_attention(q, k, v, self.p if self.training else 0.0)  # [B,H,S,hd]
         o = o.permute(2, 0, 1, 3).reshape(s, b, d)

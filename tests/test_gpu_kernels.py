@@ -223,3 +223,93 @@ def test_dense_block_fused_matches_unfused(nat, dtype, tol):
     for i, (a, b) in enumerate(zip(g0 + t0, g1 + t1)):
         err, ref = float((a - b).abs().max()), float(a.abs().max())
         assert err < tol * max(1.0, ref), (i, tuple(a.shape), err, ref)
+
+
+@pytest.mark.parametrize("model,dataset,bs", [("mnistnet", "mnist", 32), ("resnet50", "cifar10", 16), ("googlenet", "cifar10", 16),
+                                                ("regnet", "cifar100", 16), ("resnet18", "cifar10", 32)])
+def test_every_family_trains_on_gpu(nat, tmp_path, model, dataset, bs):
+    """bf16 flat-state training step through the fused GN / tcgen05 paths for every CNN family."""
+    from dynamic_load_balance_distributeddnn_b200.config import DBSConfig
+    from dynamic_load_balance_distributeddnn_b200.engine import Trainer
+    from dynamic_load_balance_distributeddnn_b200.utils import init_logger
+    cfg = DBSConfig(debug=False, world_size=1, batch_size=bs, model=model, dataset=dataset, synthetic=True,
+                    train_samples=bs * 6, test_samples=64, epoch_size=1, validate=True, learning_rate=0.02,
+                    log_dir=str(tmp_path / "l"), stats_dir=str(tmp_path / "s"))
+    t = Trainer(cfg, 0, 1, "cuda:0", init_logger(cfg, 0, stream=False))
+    before = t.flat.master.clone()
+    rec = t.run()
+    assert math.isfinite(rec.data["train_loss"][-1]) and math.isfinite(rec.data["val_loss"][-1])
+    assert not torch.equal(before, t.flat.master)
+    t.close()
+
+
+def test_transformer_lm_trains_bf16(nat, tmp_path):
+    from dynamic_load_balance_distributeddnn_b200.config import DBSConfig
+    from dynamic_load_balance_distributeddnn_b200.engine import Trainer
+    from dynamic_load_balance_distributeddnn_b200.utils import init_logger
+    cfg = DBSConfig(debug=False, world_size=1, batch_size=16, model="transformer", dataset="wikitext2", synthetic=True,
+                    train_samples=16 * 35 * 14, test_samples=4000, epoch_size=2, validate=True, learning_rate=0.5,
+                    log_dir=str(tmp_path / "l"), stats_dir=str(tmp_path / "s"))
+    t = Trainer(cfg, 0, 1, "cuda:0", init_logger(cfg, 0, stream=False))
+    rec = t.run()
+    assert rec.data["train_loss"][-1] < rec.data["train_loss"][0] + 0.5 and math.isfinite(rec.data["val_loss"][-1])
+    t.close()
+
+
+def test_linear_cross_entropy_chunked_matches_reference(nat):
+    from dynamic_load_balance_distributeddnn_b200 import ops
+    torch.manual_seed(0)
+    feats = torch.randn(300, 200, device="cuda", requires_grad=True)
+    w = (torch.randn(5000, 200, device="cuda") * 0.05).requires_grad_(True)
+    b = torch.zeros(5000, device="cuda", requires_grad=True)
+    tgt = torch.randint(0, 5000, (300,), device="cuda")
+    l1 = ops.linear_cross_entropy(feats, w, b, tgt, chunk=128)
+    l1.backward()
+    g1 = (feats.grad.clone(), w.grad.clone(), b.grad.clone())
+    feats.grad = w.grad = b.grad = None
+    l2 = ops.linear_cross_entropy_reference(feats, w, b, tgt)
+    l2.backward()
+    assert torch.allclose(l1, l2, atol=1e-4)
+    for a, r in zip(g1, (feats.grad, w.grad, b.grad)):
+        assert torch.allclose(a, r, atol=2e-5, rtol=1e-3), (a - r).abs().max()
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 3e-2)])
+def test_add_layer_norm_native(nat, dtype, tol):
+    from dynamic_load_balance_distributeddnn_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(35, 16, 200, device="cuda").to(dtype).requires_grad_(True)
+    r = torch.randn(35, 16, 200, device="cuda").to(dtype).requires_grad_(True)
+    w = (torch.rand(200, device="cuda") + 0.5).requires_grad_(True)
+    b = torch.randn(200, device="cuda").requires_grad_(True)
+    y = ops.add_layer_norm(x, r, w, b)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xr, rr = x.detach().float().requires_grad_(True), r.detach().float().requires_grad_(True)
+    wr, br = w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    yr = ops.add_layer_norm_reference(xr, rr, wr, br)
+    yr.backward(gy.float())
+    assert torch.allclose(y.float(), yr, atol=tol, rtol=tol)
+    assert torch.allclose(x.grad.float(), xr.grad, atol=tol * 3, rtol=tol * 3) and torch.allclose(r.grad.float(), rr.grad, atol=tol * 3, rtol=tol * 3)
+    assert float((w.grad - wr.grad).abs().max()) < tol * 30 and float((b.grad - br.grad).abs().max()) < tol * 30
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 3e-2)])
+def test_fused_attention_matches_reference(nat, dtype, tol):
+    from dynamic_load_balance_distributeddnn_b200.ops import attention
+    from dynamic_load_balance_distributeddnn_b200 import ops
+    torch.manual_seed(1)
+    s, b, h, hd = 35, 6, 2, 100
+    qkv = (torch.randn(s, b, 3 * h * hd, device="cuda") * 0.5).to(dtype).requires_grad_(True)
+    out = attention.causal_attention_packed(qkv, h, 0.0)
+    go = torch.randn_like(out)
+    out.backward(go)
+    ref_in = qkv.detach().float().requires_grad_(True)
+    q, k, v = ref_in.view(s, b, 3, h, hd).permute(2, 1, 3, 0, 4)
+    o = ops.causal_attention_reference(q, k, v).permute(2, 0, 1, 3).reshape(s, b, h * hd)
+    o.backward(go.float())
+    assert torch.allclose(out.float(), o, atol=tol, rtol=tol), (out.float() - o).abs().max()
+    assert torch.allclose(qkv.grad.float(), ref_in.grad, atol=tol * 2, rtol=tol * 2), (qkv.grad.float() - ref_in.grad).abs().max()
+    # dropout: kept fraction ~ (1-p), rows renormalised by 1/(1-p), same mask regenerated in backward
+    out_d = attention.causal_attention_packed(qkv.detach().requires_grad_(True), h, 0.2)
+    assert torch.isfinite(out_d.float()).all() and (out_d.float() - out.float()).abs().max() > 0
