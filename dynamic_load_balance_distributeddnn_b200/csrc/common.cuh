@@ -39,31 +39,6 @@ __device__ __forceinline__ void load_vec(const T* __restrict__ p, float (&out)[V
   }
 }
 
-// Raw 16-byte staging: issue several independent loads first (4 registers each), unpack on use.  Keeps the
-// register cost of "loads in flight" low so occupancy stays high in the streaming kernels.
-template <typename T, int V> struct RawVec { uint4 r; };
-template <typename T> struct RawVec<T, 1> { T r; };
-
-template <typename T, int V>
-__device__ __forceinline__ void load_raw(const T* __restrict__ p, RawVec<T, V>& out) {
-  if constexpr (V == 1) out.r = p[0];
-  else out.r = *reinterpret_cast<const uint4*>(p);
-}
-
-template <typename T, int V>
-__device__ __forceinline__ void unpack_raw(const RawVec<T, V>& in, float (&out)[V]) {
-  if constexpr (V == 1) {
-    out[0] = (float)in.r;
-  } else if constexpr (sizeof(T) == 4) {
-    out[0] = __uint_as_float(in.r.x); out[1] = __uint_as_float(in.r.y);
-    out[2] = __uint_as_float(in.r.z); out[3] = __uint_as_float(in.r.w);
-  } else {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&in.r);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); out[2 * i] = f.x; out[2 * i + 1] = f.y; }
-  }
-}
-
 template <typename T, int V>
 __device__ __forceinline__ void store_vec(T* __restrict__ p, const float (&in)[V]) {
   if constexpr (V == 1) {

@@ -38,12 +38,6 @@ nc_reduce2_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy
   const int lanes = C / V;                   // channel-vector lanes
   const int row_lanes = max(1, kThreads / lanes);
   for (int i = threadIdx.x; i < 2 * C; i += kThreads) smem[i] = 0.f;
-  if constexpr (MODE == 3) {
-    for (int i = threadIdx.x; i < C; i += kThreads) {
-      smem[2 * C + i] = coef_a[(int64_t)n * coef_ld + i];
-      smem[3 * C + i] = coef_b[(int64_t)n * coef_ld + i];
-    }
-  }
   __syncthreads();
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(HW, r0 + rows_per_block);
@@ -55,44 +49,38 @@ nc_reduce2_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy
 #pragma unroll
       for (int i = 0; i < V; ++i) { a0[i] = 0.f; a1[i] = 0.f; }
       const int c = lane * V;
-      const float* ka = smem + 2 * C + c;      // MODE 3: mask coefficients staged in shared memory
-      const float* kb = smem + 3 * C + c;
-      constexpr int UNR = (MODE == 0) ? 4 : 2;
+      float ka[V], kb[V];
+      if constexpr (MODE == 3) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) { ka[i] = coef_a[(int64_t)n * coef_ld + c + i]; kb[i] = coef_b[(int64_t)n * coef_ld + c + i]; }
+      }
+      constexpr int UNR = (MODE == 0) ? 2 : 1;
       for (int rb = r0 + rl; rb < r1; rb += row_lanes * UNR) {
-        RawVec<T, V> xr[UNR], gr[UNR], yr[UNR];
+        float xv[UNR][V], gv[UNR][V], yv[UNR][V];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
           const int r = rb + u * row_lanes;
           if (r < r1) {
             const int64_t row = (int64_t)n * HW + r;
-            load_raw<T, V>(x + row * ldx + c, xr[u]);
-            if constexpr (MODE != 0) load_raw<T, V>(dy + row * lddy + c, gr[u]);
-            if constexpr (MODE == 1) load_raw<T, V>(y + row * ldy + c, yr[u]);
+            load_vec<T, V>(x + row * ldx + c, xv[u]);
+            if constexpr (MODE != 0) load_vec<T, V>(dy + row * lddy + c, gv[u]);
+            if constexpr (MODE == 1) load_vec<T, V>(y + row * ldy + c, yv[u]);
           }
         }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
           const int r = rb + u * row_lanes;
           if (r < r1) {
-            float xv[V];
-            unpack_raw<T, V>(xr[u], xv);
             if constexpr (MODE == 0) {
 #pragma unroll
-              for (int i = 0; i < V; ++i) { a0[i] += xv[i]; a1[i] = fmaf(xv[i], xv[i], a1[i]); }
+              for (int i = 0; i < V; ++i) { a0[i] += xv[u][i]; a1[i] += xv[u][i] * xv[u][i]; }
             } else {
-              float gv[V];
-              unpack_raw<T, V>(gr[u], gv);
-              if constexpr (MODE == 1) {
-                float yv[V];
-                unpack_raw<T, V>(yr[u], yv);
-#pragma unroll
-                for (int i = 0; i < V; ++i) gv[i] = yv[i] > 0.f ? gv[i] : 0.f;
-              }
 #pragma unroll
               for (int i = 0; i < V; ++i) {
-                float gz = gv[i];
-                if constexpr (MODE == 3) gz = fmaf(ka[i], xv[i], kb[i]) > 0.f ? gz : 0.f;
-                a0[i] += gz; a1[i] = fmaf(gz, xv[i], a1[i]);
+                float gz = gv[u][i];
+                if constexpr (MODE == 1) gz = yv[u][i] > 0.f ? gz : 0.f;
+                if constexpr (MODE == 3) gz = fmaf(ka[i], xv[u][i], kb[i]) > 0.f ? gz : 0.f;
+                a0[i] += gz; a1[i] += gz * xv[u][i];
               }
             }
           }
@@ -209,37 +197,31 @@ gn_fwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
     const int lane = threadIdx.x % lanes, rl = threadIdx.x / lanes, row_lanes = kThreads / lanes;
     if (rl < row_lanes) {
       const int c = lane * V;
-      const float* a = sa + c;               // coefficients are re-read from shared memory (cheap) rather than
-      const float* b = sb + c;               // pinned in registers: registers are spent on loads in flight
-      constexpr int UNR = 4;
+      float a[V], b[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) { a[k] = sa[c + k]; b[k] = sb[c + k]; }
+      constexpr int UNR = 2;
       for (int rb = r0 + rl; rb < r1; rb += row_lanes * UNR) {
-        RawVec<T, V> xr[UNR], rr[UNR];
+        float xv[UNR][V], rv[UNR][V];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
           const int r = rb + u * row_lanes;
           if (r < r1) {
             const int64_t row = (int64_t)n * HW + r;
-            load_raw<T, V>(x + row * ldx + c, xr[u]);
-            if constexpr (RES) load_raw<T, V>(res + row * ldr + c, rr[u]);
+            load_vec<T, V>(x + row * ldx + c, xv[u]);
+            if constexpr (RES) load_vec<T, V>(res + row * ldr + c, rv[u]);
           }
         }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
           const int r = rb + u * row_lanes;
           if (r < r1) {
-            float xv[V], out[V];
-            unpack_raw<T, V>(xr[u], xv);
+            float out[V];
 #pragma unroll
-            for (int k = 0; k < V; ++k) out[k] = fmaf(a[k], xv[k], b[k]);
-            if constexpr (RES) {
-              float rv[V];
-              unpack_raw<T, V>(rr[u], rv);
-#pragma unroll
-              for (int k = 0; k < V; ++k) out[k] += rv[k];
-            }
-            if constexpr (RELU) {
-#pragma unroll
-              for (int k = 0; k < V; ++k) out[k] = fmaxf(out[k], 0.f);
+            for (int k = 0; k < V; ++k) {
+              out[k] = fmaf(a[k], xv[u][k], b[k]);
+              if constexpr (RES) out[k] += rv[u][k];
+              if constexpr (RELU) out[k] = fmaxf(out[k], 0.f);
             }
             store_vec<T, V>(y + ((int64_t)n * HW + r) * ldy + c, out);
           }
@@ -288,15 +270,7 @@ gn_bwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
   float* k3 = smem + 2 * C;
   float* s1 = smem + 3 * C;
   float* s2 = s1 + G;
-  float* s_ka = s2 + G;                        // [C] (RELU == 2 only)
-  float* s_kb = s_ka + C;
   const int n = blockIdx.y, cpg = C / G;
-  if constexpr (RELU == 2) {
-    for (int c = threadIdx.x; c < C; c += kThreads) {
-      s_ka[c] = coef_a[(int64_t)n * coef_ld + c];
-      s_kb[c] = coef_b[(int64_t)n * coef_ld + c];
-    }
-  }
   const float* t = table + (int64_t)n * table_ns;
   for (int g = threadIdx.x; g < G; g += kThreads) {
     const float mu = mean[n * G + g], r = rstd[n * G + g];
@@ -328,23 +302,25 @@ gn_bwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
     const int lane = threadIdx.x % lanes, rl = threadIdx.x / lanes, row_lanes = kThreads / lanes;
     if (rl < row_lanes) {
       const int c = lane * V;
-      const float* q1 = k1 + c;
-      const float* q2 = k2 + c;
-      const float* q3 = k3 + c;
-      const float* ka = s_ka + c;
-      const float* kb = s_kb + c;
-      constexpr int UNR = 2;
+      float q1[V], q2[V], q3[V], ka[V], kb[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) { q1[k] = k1[c + k]; q2[k] = k2[c + k]; q3[k] = k3[c + k]; }
+      if constexpr (RELU == 2) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) { ka[k] = coef_a[(int64_t)n * coef_ld + c + k]; kb[k] = coef_b[(int64_t)n * coef_ld + c + k]; }
+      }
+      constexpr int UNR = 1;
       for (int rb = r0 + rl; rb < r1; rb += row_lanes * UNR) {
-        RawVec<T, V> xr[UNR], gr[UNR], yr[UNR], orw[UNR];
+        float xv[UNR][V], gv[UNR][V], yv[UNR][V], old[UNR][V];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
           const int r = rb + u * row_lanes;
           if (r < r1) {
             const int64_t row = (int64_t)n * HW + r;
-            load_raw<T, V>(x + row * ldx + c, xr[u]);
-            load_raw<T, V>(dy + row * lddy + c, gr[u]);
-            if constexpr (RELU == 1) load_raw<T, V>(y + row * ldy + c, yr[u]);
-            if constexpr (ACC) load_raw<T, V>(dx + row * lddx + c, orw[u]);
+            load_vec<T, V>(x + row * ldx + c, xv[u]);
+            load_vec<T, V>(dy + row * lddy + c, gv[u]);
+            if constexpr (RELU == 1) load_vec<T, V>(y + row * ldy + c, yv[u]);
+            if constexpr (ACC) load_vec<T, V>(dx + row * lddx + c, old[u]);
           }
         }
 #pragma unroll
@@ -352,28 +328,17 @@ gn_bwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
           const int r = rb + u * row_lanes;
           if (r < r1) {
             const int64_t row = (int64_t)n * HW + r;
-            float xv[V], gv[V], out[V];
-            unpack_raw<T, V>(xr[u], xv);
-            unpack_raw<T, V>(gr[u], gv);
-            if constexpr (RELU == 1) {
-              float yv[V];
-              unpack_raw<T, V>(yr[u], yv);
+            float out[V];
 #pragma unroll
-              for (int k = 0; k < V; ++k) gv[k] = yv[k] > 0.f ? gv[k] : 0.f;
+            for (int k = 0; k < V; ++k) {
+              float gz = gv[u][k];
+              if constexpr (RELU == 1) gz = yv[u][k] > 0.f ? gz : 0.f;
+              if constexpr (RELU == 2) gz = fmaf(ka[k], xv[u][k], kb[k]) > 0.f ? gz : 0.f;
+              gv[u][k] = gz;
+              out[k] = fmaf(q1[k], gz, fmaf(q2[k], xv[u][k], q3[k]));
+              if constexpr (ACC) out[k] += old[u][k];
             }
-            if constexpr (RELU == 2) {
-#pragma unroll
-              for (int k = 0; k < V; ++k) gv[k] = fmaf(ka[k], xv[k], kb[k]) > 0.f ? gv[k] : 0.f;
-            }
-#pragma unroll
-            for (int k = 0; k < V; ++k) out[k] = fmaf(q1[k], gv[k], fmaf(q2[k], xv[k], q3[k]));
-            if constexpr (ACC) {
-              float old[V];
-              unpack_raw<T, V>(orw[u], old);
-#pragma unroll
-              for (int k = 0; k < V; ++k) out[k] += old[k];
-            }
-            if constexpr (RES) store_vec<T, V>(dres + row * lddr + c, gv);
+            if constexpr (RES) store_vec<T, V>(dres + row * lddr + c, gv[u]);
             store_vec<T, V>(dx + row * lddx + c, out);
           }
         }
@@ -459,7 +424,7 @@ int reduce2_launch(int mode, const void* x, int64_t ldx, const void* dy, int64_t
                    float* dbeta = nullptr, const float* ca = nullptr, const float* cb = nullptr, int64_t cld = 0) {
   dim3 grid; int rpb;
   grid_for(N, HW, C, V, grid, rpb);
-  const size_t sm = 4 * C * sizeof(float);
+  const size_t sm = 2 * C * sizeof(float);
   const T* X = (const T*)x; const T* DY = (const T*)dy; const T* Y = (const T*)y;
   if (mode == 0) nc_reduce2_kernel<T, V, 0><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, cld);
   else if (mode == 1) nc_reduce2_kernel<T, V, 1><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, cld);
@@ -491,7 +456,7 @@ int bwd_apply_launch(const void* x, int64_t ldx, const void* dy, int64_t lddy, c
                      int64_t cld = 0) {
   dim3 grid; int rpb;
   grid_for(N, HW, C, V, grid, rpb);
-  const size_t sm = (5 * C + 2 * G) * sizeof(float);
+  const size_t sm = (3 * C + 2 * G) * sizeof(float);
   const T* X = (const T*)x; const T* DY = (const T*)dy; const T* Y = (const T*)y;
   T* DX = (T*)dx; T* DR = (T*)dres;
   const int msrc = !relu ? 0 : (ca ? 2 : 1);

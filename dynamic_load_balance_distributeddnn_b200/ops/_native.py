@@ -16,7 +16,7 @@ from typing import Optional
 import torch
 
 _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG_DIR, "libdlb_b200.so")
+LIB_PATH = os.environ.get("DLB_NATIVE_LIB") or os.path.join(_PKG_DIR, "libdlb_b200.so")   # override: A/B two builds
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 
 _lib: Optional[ctypes.CDLL] = None
