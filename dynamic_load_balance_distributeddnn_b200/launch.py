@@ -23,12 +23,14 @@ from .config import DBSConfig
 from .utils import done_marker, init_logger
 
 
-def _backend_for(cfg: DBSConfig) -> str:
-    if cfg.debug:
+def _backend_for(cfg: DBSConfig, from_env: bool = False) -> str:
+    if cfg.debug or cfg.comm == "gloo":
         return "gloo"
+    if from_env and isinstance(cfg.gpu, int):
+        return "nccl"            # torchrun: one rank per GPU (LOCAL_RANK), regardless of the `-gpu` default
     gpus = cfg.gpu if isinstance(cfg.gpu, list) else [cfg.gpu] * cfg.world_size
-    dup = len(set(gpus[:cfg.world_size])) < min(cfg.world_size, len(gpus)) or (isinstance(cfg.gpu, int) and cfg.world_size > 1)
-    if dup or cfg.comm == "gloo":
+    used = [gpus[r % len(gpus)] for r in range(cfg.world_size)]
+    if len(set(used)) < len(used):
         return "gloo"            # several ranks share a GPU (reference `-gpu 0,0,0,1`): NCCL refuses duplicates
     return "nccl"
 
@@ -36,7 +38,7 @@ def _backend_for(cfg: DBSConfig) -> str:
 def worker(rank: int, world: int, cfg: DBSConfig, from_env: bool = False) -> None:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", str(cfg.master_port))
-    backend = _backend_for(cfg)
+    backend = _backend_for(cfg, from_env)
     device = cfg.device_for_rank(rank)
     if from_env and not cfg.debug and isinstance(cfg.gpu, int) and world > 1:
         device = f"cuda:{int(os.environ.get('LOCAL_RANK', rank))}"

@@ -17,6 +17,7 @@ Convolutions go through ``ops.conv`` (tcgen05 implicit GEMM when supported, vend
 """
 from __future__ import annotations
 
+import os
 from typing import List
 
 import torch
@@ -26,6 +27,15 @@ from . import gemm_tc
 from .norm import _nhwc_view
 
 _CONV_BWD = torch.ops.aten.convolution_backward
+_SIDE = {}
+_USE_SIDE = os.environ.get("DLB_SIDE_STREAM", "1") == "1"
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    key = str(device)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device)
+    return _SIDE[key]
 
 
 def supported(stage, x: torch.Tensor) -> bool:
@@ -150,6 +160,8 @@ class _DenseBlockFn(torch.autograd.Function):
         esz = buf.element_size()
         dbuf = dout.clone(memory_format=torch.channels_last)            # one copy: we accumulate into it in place
         grads: List = [None] * (6 * n_layers)
+        main = torch.cuda.current_stream(buf.device)
+        side = _side_stream(buf.device) if (_USE_SIDE and buf.dtype == torch.bfloat16) else None
         for l in reversed(range(n_layers)):
             g1w, g1b, w1, g2w, g2b, w2 = params[6 * l:6 * l + 6]
             xhat, y, yhat, mean1, rstd1, mean2, rstd2, ca, cb = saved[9 * l:9 * l + 9]
@@ -159,7 +171,16 @@ class _DenseBlockFn(torch.autograd.Function):
             dnew = torch.empty((n, g, h, w), dtype=buf.dtype, device=buf.device, memory_format=torch.channels_last)
             _copy_slice(lib, dbuf[:, off - g:off], dnew, st)
             w2c = w2 if w2.dtype == yhat.dtype else w2.to(yhat.dtype)
-            dyhat, dw2, _ = _CONV_BWD(dnew, yhat, w2c, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [True, True, False])
+            if side is not None:
+                # weight gradients are off the critical path: run them on a second stream so they overlap the
+                # dgrad -> GroupNorm-backward chain of the same layer (joined at the end of the layer)
+                ev_in = torch.cuda.Event(); ev_in.record(main)
+                side.wait_event(ev_in)
+                with torch.cuda.stream(side):
+                    _, dw2, _ = _CONV_BWD(dnew, yhat, w2c, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [False, True, False])
+                dyhat, _, _ = _CONV_BWD(dnew, yhat, w2c, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [True, False, False])
+            else:
+                dyhat, dw2, _ = _CONV_BWD(dnew, yhat, w2c, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [True, True, False])
             dyhat = dyhat.contiguous(memory_format=torch.channels_last)
             # GN2 + ReLU backward
             dy = torch.empty_like(y, memory_format=torch.channels_last)
@@ -182,9 +203,17 @@ class _DenseBlockFn(torch.autograd.Function):
                 w1_t = w1_2d.t().contiguous()                                      # [cl, cm]: B operand of dX = dY * W
                 dxhat = torch.empty((n, cl, h, w), dtype=buf.dtype, device=buf.device, memory_format=torch.channels_last)
                 gemm_tc.gemm_raw(dy.data_ptr(), cm, w1_t.data_ptr(), w1_t.stride(0), dxhat.data_ptr(), cl, n * hw, cl, cm, buf.device)
-                dw1f = torch.zeros((cm, cl), dtype=torch.float32, device=buf.device)
-                gemm_tc.wgrad_raw(dy.data_ptr(), cm, xs, ct, dw1f, n * hw, cm, cl, buf.device, ca, cb, hw)
-                dw1 = dw1f.view(cm, cl, 1, 1)
+                if side is not None:
+                    ev_dy = torch.cuda.Event(); ev_dy.record(main)
+                    side.wait_event(ev_dy)
+                    with torch.cuda.stream(side):
+                        dw1f = torch.zeros((cm, cl), dtype=torch.float32, device=buf.device)
+                        gemm_tc.wgrad_raw(dy.data_ptr(), cm, xs, ct, dw1f, n * hw, cm, cl, buf.device, ca, cb, hw)
+                        dw1 = dw1f.view(cm, cl, 1, 1).to(w1.dtype)
+                else:
+                    dw1f = torch.zeros((cm, cl), dtype=torch.float32, device=buf.device)
+                    gemm_tc.wgrad_raw(dy.data_ptr(), cm, xs, ct, dw1f, n * hw, cm, cl, buf.device, ca, cb, hw)
+                    dw1 = dw1f.view(cm, cl, 1, 1)
                 kpad = ca.shape[1]
                 nat.check(lib.dlb_nc_reduce2_bwd_coef(dt, xs, ct, dxhat.data_ptr(), cl, t1.data_ptr(), 0, mean1.data_ptr(),
                                                       rstd1.data_ptr(), dg1.data_ptr(), db1.data_ptr(), ca.data_ptr(), cb.data_ptr(),
@@ -200,6 +229,9 @@ class _DenseBlockFn(torch.autograd.Function):
                 nat.check(lib.dlb_gn_backward(dt, xs, ct, dxhat.data_ptr(), cl, xhat.data_ptr(), cl, dxs, ct, 0, 0,
                                               g1w.data_ptr(), mean1.data_ptr(), rstd1.data_ptr(), t1.data_ptr(),
                                               dg1.data_ptr(), db1.data_ptr(), n, hw, cl, groups, 1, 1, st), "dense.gn1_bwd")
+            if side is not None:
+                ev_out = torch.cuda.Event(); ev_out.record(side)
+                main.wait_event(ev_out)            # per-layer join: every tensor the side stream touched is still referenced here
             grads[6 * l:6 * l + 6] = [dg1.to(g1w.dtype), db1.to(g1b.dtype), dw1.to(w1.dtype), dg2.to(g2w.dtype),
                                       db2.to(g2b.dtype), dw2.to(w2.dtype)]
         dx = torch.empty((n, c0, h, w), dtype=buf.dtype, device=buf.device, memory_format=torch.channels_last)
