@@ -164,17 +164,19 @@ def run_ours(a) -> dict:
         n0 = _native.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        h0 = time.perf_counter()
         run_steps(shard, K, e2e=e2e, sink=sink if e2e else None)
+        host_ms = (time.perf_counter() - h0) * 1e3          # time the HOST needed to issue the K steps
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         ms = e0.elapsed_time(e1)
         wait = tr.comm.device_wait_seconds() if hasattr(tr.comm, "device_wait_seconds") else 0.0
-        return max_over_ranks(ms, device, world), _native.launch_count() - n0, max_over_ranks(wait, device, world)
+        return max_over_ranks(ms, device, world), _native.launch_count() - n0, max_over_ranks(wait, device, world), host_ms
 
-    ms_e2e, _, wait_e2e = timed(True, 3)
-    ms_dev, launches, wait_dev = timed(False, 4)
+    ms_e2e, _, wait_e2e, host_e2e = timed(True, 3)
+    ms_dev, launches, wait_dev, host_dev = timed(False, 4)
     clk = clocks.stop() if rank == 0 else {}
     if hasattr(tr.comm, "check_errors"):
         tr.comm.check_errors()
@@ -197,6 +199,7 @@ def run_ours(a) -> dict:
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
         "straggler_wait_ms_per_step": round(1e3 * wait_dev / K, 4),
+        "host_issue_ms_per_step": {"device_resident": round(host_dev / K, 4), "e2e": round(host_e2e / K, 4)},
         "clocks": {"sm_mhz": clk.get("sm_mhz"), "sm_max_mhz": clk.get("sm_max_mhz"), "reasons": clk.get("reasons", [])},
         "final_loss_acc": loss,
     }

@@ -15,6 +15,8 @@
 // buffer can be read / written in place.
 #include "common.cuh"
 
+static int g_skip_zero = 0;      // callers that pre-zero one big arena set this to skip the per-call memsets
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -32,7 +34,8 @@ nc_reduce2_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy
                   const T* __restrict__ y, int64_t ldy, float* __restrict__ table, int64_t table_ns,
                   int HW, int C, int rows_per_block, const float* __restrict__ mean,
                   const float* __restrict__ rstd, int G, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                  const float* __restrict__ coef_a, const float* __restrict__ coef_b, int64_t coef_ld) {
+                  const float* __restrict__ coef_a, const float* __restrict__ coef_b, int64_t coef_ld,
+                  T* __restrict__ copy_dst, int64_t ldc) {
   extern __shared__ float smem[];            // [2*C]
   const int n = blockIdx.y;
   const int lanes = C / V;                   // channel-vector lanes
@@ -63,6 +66,7 @@ nc_reduce2_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy
           if (r < r1) {
             const int64_t row = (int64_t)n * HW + r;
             load_vec<T, V>(x + row * ldx + c, xv[u]);
+            if constexpr (MODE == 0) { if (copy_dst != nullptr) store_vec<T, V>(copy_dst + row * ldc + c, xv[u]); }
             if constexpr (MODE != 0) load_vec<T, V>(dy + row * lddy + c, gv[u]);
             if constexpr (MODE == 1) load_vec<T, V>(y + row * ldy + c, yv[u]);
           }
@@ -421,15 +425,16 @@ template <typename T, int V>
 int reduce2_launch(int mode, const void* x, int64_t ldx, const void* dy, int64_t lddy, const void* y,
                    int64_t ldy, float* table, int64_t table_ns, int N, int HW, int C, cudaStream_t st,
                    const float* mean = nullptr, const float* rstd = nullptr, int G = 1, float* dgamma = nullptr,
-                   float* dbeta = nullptr, const float* ca = nullptr, const float* cb = nullptr, int64_t cld = 0) {
+                   float* dbeta = nullptr, const float* ca = nullptr, const float* cb = nullptr, int64_t cld = 0,
+                   void* copy_dst = nullptr, int64_t ldc = 0) {
   dim3 grid; int rpb;
   grid_for(N, HW, C, V, grid, rpb);
   const size_t sm = 2 * C * sizeof(float);
   const T* X = (const T*)x; const T* DY = (const T*)dy; const T* Y = (const T*)y;
-  if (mode == 0) nc_reduce2_kernel<T, V, 0><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, cld);
-  else if (mode == 1) nc_reduce2_kernel<T, V, 1><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, cld);
-  else if (mode == 3) nc_reduce2_kernel<T, V, 3><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, cld);
-  else nc_reduce2_kernel<T, V, 2><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, cld);
+  if (mode == 0) nc_reduce2_kernel<T, V, 0><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, cld, (T*)copy_dst, ldc);
+  else if (mode == 1) nc_reduce2_kernel<T, V, 1><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, cld, (T*)copy_dst, ldc);
+  else if (mode == 3) nc_reduce2_kernel<T, V, 3><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, cld, (T*)copy_dst, ldc);
+  else nc_reduce2_kernel<T, V, 2><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, cld, (T*)copy_dst, ldc);
   return dlb_post_launch();
 }
 
@@ -486,13 +491,15 @@ inline bool vec_ok(int dtype, int C, std::initializer_list<int64_t> lds, std::in
            else { using T = float; constexpr int V = 1; CALL; } }                            \
   } while (0)
 
+DLB_API void dlb_norm_skip_zero(int flag) { g_skip_zero = flag; }
+
 // table: fp32 [N][table_ns] with (q0,q1) pairs for C channels starting at `table`; zeroed here.
 DLB_API int dlb_nc_reduce2(int mode, int dtype, const void* x, int64_t ldx, const void* dy, int64_t lddy,
                            const void* y, int64_t ldy, float* table, int64_t table_ns, int N, int HW, int C, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (C > 6000) return -2;
   if (table_ns <= 0) table_ns = 2 * (int64_t)C;
-  cudaMemset2DAsync(table, (size_t)table_ns * sizeof(float), 0, (size_t)C * 2 * sizeof(float), (size_t)N, st);
+  if (!g_skip_zero) cudaMemset2DAsync(table, (size_t)table_ns * sizeof(float), 0, (size_t)C * 2 * sizeof(float), (size_t)N, st);
   const bool vec = vec_ok(dtype, C, {ldx, dy ? lddy : 0, y ? ldy : 0}, {x, dy, y});
   int rc = 0;
   DISPATCH(dtype, vec, (rc = reduce2_launch<T, V>(mode, x, ldx, dy, lddy, y, ldy, table, table_ns, N, HW, C, st)));
@@ -506,8 +513,10 @@ DLB_API int dlb_nc_reduce2_bwd(int relu, int dtype, const void* x, int64_t ldx, 
   cudaStream_t st = (cudaStream_t)stream;
   if (C > 6000) return -2;
   if (table_ns <= 0) table_ns = 2 * (int64_t)C;
-  cudaMemset2DAsync(table, (size_t)table_ns * sizeof(float), 0, (size_t)C * 2 * sizeof(float), (size_t)N, st);
-  if (dgamma) { cudaMemsetAsync(dgamma, 0, C * sizeof(float), st); cudaMemsetAsync(dbeta, 0, C * sizeof(float), st); }
+  if (!g_skip_zero) {
+    cudaMemset2DAsync(table, (size_t)table_ns * sizeof(float), 0, (size_t)C * 2 * sizeof(float), (size_t)N, st);
+    if (dgamma) { cudaMemsetAsync(dgamma, 0, C * sizeof(float), st); cudaMemsetAsync(dbeta, 0, C * sizeof(float), st); }
+  }
   const bool vec = vec_ok(dtype, C, {ldx, lddy, relu ? ldy : 0}, {x, dy, relu ? y : nullptr});
   int rc = 0;
   DISPATCH(dtype, vec, (rc = reduce2_launch<T, V>(relu ? 1 : 2, x, ldx, dy, lddy, y, ldy, table, table_ns, N, HW, C, st, mean, rstd, G, dgamma, dbeta)));
@@ -521,8 +530,10 @@ DLB_API int dlb_nc_reduce2_bwd_coef(int dtype, const void* x, int64_t ldx, const
   cudaStream_t st = (cudaStream_t)stream;
   if (C > 6000) return -2;
   if (table_ns <= 0) table_ns = 2 * (int64_t)C;
-  cudaMemset2DAsync(table, (size_t)table_ns * sizeof(float), 0, (size_t)C * 2 * sizeof(float), (size_t)N, st);
-  if (dgamma) { cudaMemsetAsync(dgamma, 0, C * sizeof(float), st); cudaMemsetAsync(dbeta, 0, C * sizeof(float), st); }
+  if (!g_skip_zero) {
+    cudaMemset2DAsync(table, (size_t)table_ns * sizeof(float), 0, (size_t)C * 2 * sizeof(float), (size_t)N, st);
+    if (dgamma) { cudaMemsetAsync(dgamma, 0, C * sizeof(float), st); cudaMemsetAsync(dbeta, 0, C * sizeof(float), st); }
+  }
   const bool vec = vec_ok(dtype, C, {ldx, lddy}, {x, dy});
   int rc = 0;
   DISPATCH(dtype, vec, (rc = reduce2_launch<T, V>(3, x, ldx, dy, lddy, nullptr, 0, table, table_ns, N, HW, C, st, mean, rstd, G, dgamma, dbeta, ca, cb, cld)));
@@ -536,6 +547,20 @@ DLB_API int dlb_gn_bwd_apply_coef(int dtype, const void* x, int64_t ldx, const v
   if (table_ns <= 0) table_ns = 2 * (int64_t)C;
   const bool vec = vec_ok(dtype, C, {ldx, lddy, lddx}, {x, dy, dx});
   DISPATCH(dtype, vec, (rc = bwd_apply_launch<T, V>(x, ldx, dy, lddy, nullptr, 0, dx, lddx, nullptr, 0, gamma, mean, rstd, table, table_ns, N, HW, C, G, 1, acc, (cudaStream_t)stream, ca, cb, cld)));
+  return rc;
+}
+
+// Per-(sample, channel) statistics of x fused with a strided copy of x into `dst` (moves a conv output into its
+// channel slice of the dense-block buffer and produces its GroupNorm statistics in the same pass).
+DLB_API int dlb_copy_stats(int dtype, const void* x, int64_t ldx, void* dst, int64_t ldd, float* table, int64_t table_ns,
+                           int N, int HW, int C, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C > 6000) return -2;
+  if (table_ns <= 0) table_ns = 2 * (int64_t)C;
+  if (!g_skip_zero) cudaMemset2DAsync(table, (size_t)table_ns * sizeof(float), 0, (size_t)C * 2 * sizeof(float), (size_t)N, st);
+  const bool vec = vec_ok(dtype, C, {ldx, ldd}, {x, dst});
+  int rc = 0;
+  DISPATCH(dtype, vec, (rc = reduce2_launch<T, V>(0, x, ldx, nullptr, 0, nullptr, 0, table, table_ns, N, HW, C, st, nullptr, nullptr, 1, nullptr, nullptr, nullptr, nullptr, 0, dst, ldd)));
   return rc;
 }
 

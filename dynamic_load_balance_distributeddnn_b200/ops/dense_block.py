@@ -64,6 +64,20 @@ def _conv_fwd(x, w, pad):
 class _DenseBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, eps, groups, *params):
+        try:
+            return _DenseBlockFn._forward_impl(ctx, x, eps, groups, *params)
+        finally:
+            nat.require().dlb_norm_skip_zero(0)          # never leave the library in "caller pre-zeroed" mode
+
+    @staticmethod
+    def backward(ctx, dout, _dtable):
+        try:
+            return _DenseBlockFn._backward_impl(ctx, dout, _dtable)
+        finally:
+            nat.require().dlb_norm_skip_zero(0)
+
+    @staticmethod
+    def _forward_impl(ctx, x, eps, groups, *params):
         lib = nat.require()
         st = nat.stream_ptr(x.device)
         n_layers = len(params) // 6
@@ -73,18 +87,25 @@ class _DenseBlockFn(torch.autograd.Function):
         ct = c0 + n_layers * g
         dt = nat.dtype_code(x.dtype)
         buf = torch.empty((n, ct, h, w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
-        table = torch.empty((n, ct, 2), dtype=torch.float32, device=x.device)
+        # every accumulation table of the forward is carved out of ONE zero-initialised arena (one fill kernel
+        # instead of a memset node per reduction: the step is launch-latency bound at small local batches)
+        cm0 = params[2].shape[0]
+        arena = torch.zeros(n * ct * 2 + n_layers * n * cm0 * 2, dtype=torch.float32, device=x.device)
+        table = arena[:n * ct * 2].view(n, ct, 2)
+        t2_all = arena[n * ct * 2:].view(n_layers, n * cm0 * 2)
         tns = 2 * ct
-        _copy_slice(lib, x, buf[:, ct - c0:], st)
         esz = buf.element_size()
 
         def slice_ptr(c_off):
             return buf.data_ptr() + c_off * esz
 
-        def stats(c_off, c):
-            nat.check(lib.dlb_nc_reduce2(0, dt, slice_ptr(c_off), ct, 0, 0, 0, 0, table.data_ptr() + c_off * 8, tns,
-                                         n, hw, c, st), "dense.stats")
-        stats(ct - c0, c0)
+        def copy_in_with_stats(src, c_off, c):
+            """src -> buf[:, c_off:c_off+c] and its per-(sample, channel) (sum, sumsq) in the same pass"""
+            sv, _, _, _, lds = _nhwc_view(src)
+            nat.check(lib.dlb_copy_stats(dt, sv.data_ptr(), lds, slice_ptr(c_off), ct, table.data_ptr() + c_off * 8, tns,
+                                         n, hw, c, st), "dense.copy_stats")
+        lib.dlb_norm_skip_zero(1)
+        copy_in_with_stats(x, ct - c0, c0)
         saved = []
         fused = x.dtype == torch.bfloat16 and gemm_tc.available() and (n * hw) >= 128
         for l in range(n_layers):
@@ -107,8 +128,7 @@ class _DenseBlockFn(torch.autograd.Function):
                           "dense.coeff")
                 yv = torch.empty((n, cm, h, w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
                 epi = hw % 32 == 0
-                t2 = torch.zeros(n * cm * 2, dtype=torch.float32, device=x.device) if epi else \
-                    torch.empty(n * cm * 2, dtype=torch.float32, device=x.device)
+                t2 = t2_all[l]
                 w1_2d = gemm_tc._w2d(w1)
                 gemm_tc.gemm_raw(slice_ptr(off), ct, w1_2d.data_ptr(), w1_2d.stride(0), yv.data_ptr(), cm, n * hw, cm, cl,
                                  x.device, ca, cb, hw, t2 if epi else None, 0, 2 * cm)
@@ -129,25 +149,25 @@ class _DenseBlockFn(torch.autograd.Function):
                                                mean1.data_ptr(), rstd1.data_ptr(), n, hw, cl, groups, 1, st), "dense.apply1")
                 coefs = None
                 y = _conv_fwd(xhat, w1, 0)
-                t2 = torch.empty(n * cm * 2, dtype=torch.float32, device=x.device)
+                t2 = t2_all[l]
                 yv, _, _, _, ldy = _nhwc_view(y)
                 yhat = torch.empty_like(yv, memory_format=torch.channels_last)
                 nat.check(lib.dlb_gn_forward(dt, yv.data_ptr(), ldy, 0, 0, yhat.data_ptr(), cm, g2w.data_ptr(), g2b.data_ptr(),
                                              mean2.data_ptr(), rstd2.data_ptr(), t2.data_ptr(), n, hw, cm, groups, eps, 1, 0, st),
                           "dense.gn2")
             new = _conv_fwd(yhat, w2, 1)
-            _copy_slice(lib, new, buf[:, off - g:off], st)
-            stats(off - g, g)
+            copy_in_with_stats(new, off - g, g)
             empty = mean1.new_empty(0)
             saved += [xhat if xhat is not None else empty, yv, yhat, mean1, rstd1, mean2, rstd2,
                       coefs[0] if coefs else empty, coefs[1] if coefs else empty]
+        lib.dlb_norm_skip_zero(0)
         ctx.save_for_backward(buf, *params, *saved)
         ctx.cfg = (n_layers, n, c0, h, w, g, ct, groups, eps)
         ctx.mark_non_differentiable(table)
         return buf, table
 
     @staticmethod
-    def backward(ctx, dout, _dtable):
+    def _backward_impl(ctx, dout, _dtable):
         lib = nat.require()
         n_layers, n, c0, h, w, g, ct, groups, eps = ctx.cfg
         tensors = ctx.saved_tensors
@@ -160,6 +180,20 @@ class _DenseBlockFn(torch.autograd.Function):
         esz = buf.element_size()
         dbuf = dout.clone(memory_format=torch.channels_last)            # one copy: we accumulate into it in place
         grads: List = [None] * (6 * n_layers)
+        # one zero-initialised arena for every reduction table / parameter-gradient accumulator of the block
+        cm0 = params[2].shape[0]
+        sizes = []
+        for l in range(n_layers):
+            cl_ = c0 + l * g
+            sizes.append((n * cm0 * 2, cm0, cm0, n * cl_ * 2, cl_, cl_))
+        arena = torch.zeros(sum(sum(sz) for sz in sizes), dtype=torch.float32, device=buf.device)
+        dw1_arena = torch.zeros(sum(cm0 * (c0 + l * g) for l in range(n_layers)), dtype=torch.float32, device=buf.device)
+        a_off, w_off = [0], [0]
+        for l in range(n_layers):
+            a_off.append(a_off[-1] + sum(sizes[l]))
+            w_off.append(w_off[-1] + cm0 * (c0 + l * g))
+        lib.dlb_norm_skip_zero(1)
+        dw1_views = [None] * n_layers
         main = torch.cuda.current_stream(buf.device)
         side = _side_stream(buf.device) if (_USE_SIDE and buf.dtype == torch.bfloat16) else None
         for l in reversed(range(n_layers)):
@@ -184,15 +218,16 @@ class _DenseBlockFn(torch.autograd.Function):
             dyhat = dyhat.contiguous(memory_format=torch.channels_last)
             # GN2 + ReLU backward
             dy = torch.empty_like(y, memory_format=torch.channels_last)
-            t2 = torch.empty(n * cm * 2, dtype=torch.float32, device=buf.device)
-            dg2 = torch.empty(cm, dtype=torch.float32, device=buf.device)
-            db2 = torch.empty(cm, dtype=torch.float32, device=buf.device)
+            o = a_off[l]
+            t2 = arena[o:o + sizes[l][0]]; o += sizes[l][0]
+            dg2 = arena[o:o + cm]; o += cm
+            db2 = arena[o:o + cm]; o += cm
+            t1 = arena[o:o + sizes[l][3]]; o += sizes[l][3]
+            dg1 = arena[o:o + cl]; o += cl
+            db1 = arena[o:o + cl]
             nat.check(lib.dlb_gn_backward(dt, y.data_ptr(), cm, dyhat.data_ptr(), cm, yhat.data_ptr(), cm, dy.data_ptr(), cm,
                                           0, 0, g2w.data_ptr(), mean2.data_ptr(), rstd2.data_ptr(), t2.data_ptr(),
                                           dg2.data_ptr(), db2.data_ptr(), n, hw, cm, groups, 1, 0, st), "dense.gn2_bwd")
-            t1 = torch.empty(n * cl * 2, dtype=torch.float32, device=buf.device)
-            dg1 = torch.empty(cl, dtype=torch.float32, device=buf.device)
-            db1 = torch.empty(cl, dtype=torch.float32, device=buf.device)
             xs = buf.data_ptr() + off * esz
             dxs = dbuf.data_ptr() + off * esz
             if xhat.numel() == 0:
@@ -206,14 +241,13 @@ class _DenseBlockFn(torch.autograd.Function):
                 if side is not None:
                     ev_dy = torch.cuda.Event(); ev_dy.record(main)
                     side.wait_event(ev_dy)
+                    dw1f = dw1_arena[w_off[l]:w_off[l + 1]].view(cm, cl)
                     with torch.cuda.stream(side):
-                        dw1f = torch.zeros((cm, cl), dtype=torch.float32, device=buf.device)
                         gemm_tc.wgrad_raw(dy.data_ptr(), cm, xs, ct, dw1f, n * hw, cm, cl, buf.device, ca, cb, hw)
-                        dw1 = dw1f.view(cm, cl, 1, 1).to(w1.dtype)
                 else:
-                    dw1f = torch.zeros((cm, cl), dtype=torch.float32, device=buf.device)
+                    dw1f = dw1_arena[w_off[l]:w_off[l + 1]].view(cm, cl)
                     gemm_tc.wgrad_raw(dy.data_ptr(), cm, xs, ct, dw1f, n * hw, cm, cl, buf.device, ca, cb, hw)
-                    dw1 = dw1f.view(cm, cl, 1, 1)
+                dw1 = None                      # cast for all layers at once after the loop
                 kpad = ca.shape[1]
                 nat.check(lib.dlb_nc_reduce2_bwd_coef(dt, xs, ct, dxhat.data_ptr(), cl, t1.data_ptr(), 0, mean1.data_ptr(),
                                                       rstd1.data_ptr(), dg1.data_ptr(), db1.data_ptr(), ca.data_ptr(), cb.data_ptr(),
@@ -232,8 +266,15 @@ class _DenseBlockFn(torch.autograd.Function):
             if side is not None:
                 ev_out = torch.cuda.Event(); ev_out.record(side)
                 main.wait_event(ev_out)            # per-layer join: every tensor the side stream touched is still referenced here
-            grads[6 * l:6 * l + 6] = [dg1.to(g1w.dtype), db1.to(g1b.dtype), dw1.to(w1.dtype), dg2.to(g2w.dtype),
-                                      db2.to(g2b.dtype), dw2.to(w2.dtype)]
+            grads[6 * l:6 * l + 6] = [dg1.to(g1w.dtype), db1.to(g1b.dtype), dw1.to(w1.dtype) if dw1 is not None else None,
+                                      dg2.to(g2w.dtype), db2.to(g2b.dtype), dw2.to(w2.dtype)]
+        lib.dlb_norm_skip_zero(0)
+        if any(grads[6 * l + 2] is None for l in range(n_layers)):
+            dw1_cast = dw1_arena.to(params[2].dtype)            # ONE cast kernel for every 1x1 weight gradient
+            for l in range(n_layers):
+                if grads[6 * l + 2] is None:
+                    cl_ = c0 + l * g
+                    grads[6 * l + 2] = dw1_cast[w_off[l]:w_off[l + 1]].view(cm0, cl_, 1, 1)
         dx = torch.empty((n, c0, h, w), dtype=buf.dtype, device=buf.device, memory_format=torch.channels_last)
         _copy_slice(lib, dbuf[:, ct - c0:], dx, st)
         return (dx, None, None, *grads)
