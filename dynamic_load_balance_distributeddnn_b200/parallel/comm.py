@@ -163,14 +163,14 @@ class SymmComm(Comm):
 
     # ---- collectives ----------------------------------------------------------------------------
     def pick_algo(self, nbytes: int) -> str:
+        """Measured on 8xB200 (profiles/r1_07): two-shot >= one-shot from 64 KiB up and >= the NVLS variant
+        everywhere; one-shot only wins the latency race for tiny buckets."""
         if self.algo != "auto":
             if self.algo == "nvls" and not self.has_multicast:
                 return "twoshot"
             return self.algo
-        if self.world == 1 or nbytes <= 512 * 1024:
+        if self.world == 1 or nbytes <= 32 * 1024:
             return "oneshot"
-        if self.has_multicast and self.world > 2:
-            return "nvls"
         return "twoshot"
 
     def pick_blocks(self, nbytes: int, algo: str) -> int:
@@ -180,7 +180,9 @@ class SymmComm(Comm):
             return 4
         if nbytes <= 1 << 20:
             return 16
-        return 16 if algo == "nvls" else 32
+        if nbytes <= 32 << 20:
+            return 32
+        return 64
 
     def allreduce_buckets(self, grad_in, grad_out, buckets, weights_dev: Optional[torch.Tensor] = None) -> float:
         st = nat.stream_ptr(self.device)
