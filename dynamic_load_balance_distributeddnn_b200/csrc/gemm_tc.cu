@@ -23,6 +23,8 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -70,6 +72,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       : "memory");
 }
 
+// explicit shared-space accesses: the 1024-byte re-alignment of the dynamic smem base hides the address space
+// from the compiler, which otherwise emits generic LD.E/ST.E (slow path) for the operand-transform loops
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   // K-major, SWIZZLE_128B canonical layout: 8-row groups 1024 B apart (SBO), rows 128 B apart inside a group.
   uint64_t d = 0;
@@ -80,6 +93,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
   return d;
 }
+
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr);
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -135,7 +150,10 @@ template <int BN> struct Cfg {
 
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator (+ idle), 3 = idle (keeps epilogue warps at
 // warp ids 4..7 so that (warp_id % 4) selects their TMEM lane quadrant), 4..7 = epilogue, 8..15 = prologue transform.
-template <int BN, bool PRO_GN, bool EPI_STATS>
+// B_MN: the B operand is given as [K][N] row-major (N contiguous) instead of [N][K] -- e.g. the untransposed weight
+// matrix in a dgrad GEMM dX = dY * W.  Its tiles are loaded as (BN/64) TMA boxes of [64 k-rows][64 n] and consumed
+// through an MN-major shared-memory descriptor, so no transposed copy of the weights is ever made.
+template <int BN, bool PRO_GN, bool EPI_STATS, bool B_MN = false>
 __global__ void __launch_bounds__(PRO_GN ? 512 : 256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
@@ -196,7 +214,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_expect_tx(fb, C::kStageBytes);
           tma_load_2d(sa, &tmap_a, fb, kb * BK, m0);
-          tma_load_2d(sb, &tmap_b, fb, kb * BK, n0);
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int gi = 0; gi < BN / 64; ++gi) tma_load_2d(sb + gi * 8192, &tmap_b, fb, n0 + gi * 64, kb * BK);
+          } else {
+            tma_load_2d(sb, &tmap_b, fb, kb * BK, n0);
+          }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -205,7 +228,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (B_MN ? (1u << 16) : 0u) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -217,11 +241,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
           const uint32_t sb = sa + C::kABytes;
-          const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sb);
+          const uint64_t adesc = make_smem_desc(sa), bdesc = B_MN ? make_smem_desc_mn(sb) : make_smem_desc(sb);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 32 bytes (16 bf16) along K inside the 128-byte swizzle atom: +2 in 16-byte units
-            umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            // K-major: advance 32 bytes (16 bf16) inside the 128-byte swizzle atom: +2 in 16-byte units;
+            // MN-major: advance 16 k-rows of 128 bytes: +128
+            umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)((B_MN ? 128 : 2) * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(smem_u32(&empty_bar[stage]));            // frees the smem stage when these MMAs retire
           if (kb == num_kb - 1) umma_commit(smem_u32(&tmem_full[acc]));
@@ -257,12 +282,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int col = n0 + c0;
         {
           // box `c0/64`: [32 rows][128 B], 16-byte chunk j of row r at r*128 + ((j ^ (r & 7)) << 4)
-          uint8_t* box = stage_buf + (c0 >> 6) * 4096 + lane * 128;
+          const uint32_t box = smem_u32(stage_buf + (c0 >> 6) * 4096 + lane * 128);
           const int jb = (c0 & 32) ? 4 : 0;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(box + (((jb + j) ^ (lane & 7)) << 4)) =
-                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            sts128(box + (((jb + j) ^ (lane & 7)) << 4), make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]));
           if ((c0 & 32) || c0 + 32 >= BN) {
             // a 64-column box (or the final partial one) is complete: hand it to the TMA store engine
             fence_proxy_async();
@@ -333,7 +357,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int m0 = (t / num_n) * BM;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
-        uint8_t* sa = smem + stage * C::kStageBytes;
+        const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+        // issue all shared loads of this thread first (they are independent), then transform and write back:
+        // a load->math->store chain per chunk would expose the shared-memory latency four times per stage
+        uint4 raw[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = r_base + 32 * i;
+          raw[i] = lds128(sa + r * 128 + ((cc ^ (r & 7)) << 4));
+        }
         int cur = -1;
         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
 #pragma unroll
@@ -349,9 +381,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             a0 = __ldg(ca); a1 = __ldg(ca + 1); b0 = __ldg(cb); b1 = __ldg(cb + 1);
             cur = sample;
           }
-          uint4* chunk = reinterpret_cast<uint4*>(sa + r * 128 + ((cc ^ (r & 7)) << 4));
-          uint4 raw = *chunk;
-          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw[i]);
           float2 f;
           f = __bfloat1622float2(h[0]);
           h[0] = __floats2bfloat162_rn(fmaxf(fmaf(a0.x, f.x, b0.x), 0.f), fmaxf(fmaf(a0.y, f.y, b0.y), 0.f));
@@ -361,8 +391,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           h[2] = __floats2bfloat162_rn(fmaxf(fmaf(a1.x, f.x, b1.x), 0.f), fmaxf(fmaf(a1.y, f.y, b1.y), 0.f));
           f = __bfloat1622float2(h[3]);
           h[3] = __floats2bfloat162_rn(fmaxf(fmaf(a1.z, f.x, b1.z), 0.f), fmaxf(fmaf(a1.w, f.y, b1.w), 0.f));
-          if (!live) raw = make_uint4(0u, 0u, 0u, 0u);
-          *chunk = raw;
+          if (!live) raw[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = r_base + 32 * i;
+          sts128(sa + r * 128 + ((cc ^ (r & 7)) << 4), raw[i]);
         }
         fence_proxy_async();                                     // generic-proxy writes -> visible to the MMA (async proxy)
         mbar_arrive(smem_u32(&ready_bar[stage]));
@@ -576,38 +610,51 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
       const bool in_range = cbase < p.pro_ld;            // coefficient rows are padded to a multiple of 64
       for (int rr = r0; rr < r1; rr += 64) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
-        uint8_t* sb = smem + stage * C::kStageBytes + C::kABytes + box * C::kBoxBytes;
+        const uint32_t sb = smem_u32(smem + stage * C::kStageBytes + C::kABytes + box * C::kBoxBytes);
         int cur = -1;
         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+        constexpr int kIters = 64 / kRowStep;          // 2, 4 or 8 chunks per thread per stage
+        constexpr int kBatch = kIters < 4 ? kIters : 4;
 #pragma unroll
-        for (int i = 0; i < 64 / kRowStep; ++i) {
-          const int r = r_base + kRowStep * i;
-          const int grow = rr + r;
-          const bool live = grow < p.M && in_range;
-          const int sample = min(grow, p.M - 1) / p.rows_per_sample;
-          if (sample != cur && in_range) {
-            const float4* ca = reinterpret_cast<const float4*>(p.pro_a + (long long)sample * p.pro_ld + cbase);
-            const float4* cb = reinterpret_cast<const float4*>(p.pro_b + (long long)sample * p.pro_ld + cbase);
-            a0 = __ldg(ca); a1 = __ldg(ca + 1); b0 = __ldg(cb); b1 = __ldg(cb + 1);
-            cur = sample;
+        for (int i0 = 0; i0 < kIters; i0 += kBatch) {
+          uint4 raw[kBatch];
+#pragma unroll
+          for (int j = 0; j < kBatch; ++j) {
+            const int r = r_base + kRowStep * (i0 + j);
+            raw[j] = lds128(sb + r * 128 + ((cc ^ (r & 7)) << 4));
           }
-          uint4* chunk = reinterpret_cast<uint4*>(sb + r * 128 + ((cc ^ (r & 7)) << 4));
-          uint4 raw = *chunk;
-          if (live) {
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
-            float2 f;
-            f = __bfloat1622float2(h[0]);
-            h[0] = __floats2bfloat162_rn(fmaxf(fmaf(a0.x, f.x, b0.x), 0.f), fmaxf(fmaf(a0.y, f.y, b0.y), 0.f));
-            f = __bfloat1622float2(h[1]);
-            h[1] = __floats2bfloat162_rn(fmaxf(fmaf(a0.z, f.x, b0.z), 0.f), fmaxf(fmaf(a0.w, f.y, b0.w), 0.f));
-            f = __bfloat1622float2(h[2]);
-            h[2] = __floats2bfloat162_rn(fmaxf(fmaf(a1.x, f.x, b1.x), 0.f), fmaxf(fmaf(a1.y, f.y, b1.y), 0.f));
-            f = __bfloat1622float2(h[3]);
-            h[3] = __floats2bfloat162_rn(fmaxf(fmaf(a1.z, f.x, b1.z), 0.f), fmaxf(fmaf(a1.w, f.y, b1.w), 0.f));
-          } else {
-            raw = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int j = 0; j < kBatch; ++j) {
+            const int r = r_base + kRowStep * (i0 + j);
+            const int grow = rr + r;
+            const bool live = grow < p.M && in_range;
+            const int sample = min(grow, p.M - 1) / p.rows_per_sample;
+            if (sample != cur && in_range) {
+              const float4* ca = reinterpret_cast<const float4*>(p.pro_a + (long long)sample * p.pro_ld + cbase);
+              const float4* cb = reinterpret_cast<const float4*>(p.pro_b + (long long)sample * p.pro_ld + cbase);
+              a0 = __ldg(ca); a1 = __ldg(ca + 1); b0 = __ldg(cb); b1 = __ldg(cb + 1);
+              cur = sample;
+            }
+            if (live) {
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw[j]);
+              float2 f;
+              f = __bfloat1622float2(h[0]);
+              h[0] = __floats2bfloat162_rn(fmaxf(fmaf(a0.x, f.x, b0.x), 0.f), fmaxf(fmaf(a0.y, f.y, b0.y), 0.f));
+              f = __bfloat1622float2(h[1]);
+              h[1] = __floats2bfloat162_rn(fmaxf(fmaf(a0.z, f.x, b0.z), 0.f), fmaxf(fmaf(a0.w, f.y, b0.w), 0.f));
+              f = __bfloat1622float2(h[2]);
+              h[2] = __floats2bfloat162_rn(fmaxf(fmaf(a1.x, f.x, b1.x), 0.f), fmaxf(fmaf(a1.y, f.y, b1.y), 0.f));
+              f = __bfloat1622float2(h[3]);
+              h[3] = __floats2bfloat162_rn(fmaxf(fmaf(a1.z, f.x, b1.z), 0.f), fmaxf(fmaf(a1.w, f.y, b1.w), 0.f));
+            } else {
+              raw[j] = make_uint4(0u, 0u, 0u, 0u);
+            }
           }
-          *chunk = raw;
+#pragma unroll
+          for (int j = 0; j < kBatch; ++j) {
+            const int r = r_base + kRowStep * (i0 + j);
+            sts128(sb + r * 128 + ((cc ^ (r & 7)) << 4), raw[j]);
+          }
         }
         fence_proxy_async();
         mbar_arrive(smem_u32(&ready_bar[stage]));
@@ -642,6 +689,10 @@ int make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, 
   // inner box is always 64 elements = 128 bytes = the swizzle span
   auto enc = get_encode();
   if (!enc) return -10;
+  // the driver-API encoder needs a current context on THIS thread (autograd runs backward on its own threads,
+  // where a runtime call may not have bound the primary context yet)
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(0); ctx_bound = true; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
@@ -649,13 +700,15 @@ int make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, 
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS && getenv("DLB_DEBUG_TMAP"))
+    fprintf(stderr, "[dlb] cuTensorMapEncodeTiled failed (%d): ptr=%p rows=%lld cols=%lld ld=%lld box_rows=%d\n", (int)r, ptr, rows, cols, ld, box_rows);
   return r == CUDA_SUCCESS ? 0 : -11;
 }
 
-template <int BN, bool PRO, bool STATS>
+template <int BN, bool PRO, bool STATS, bool BMN = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p, int sms, cudaStream_t st) {
   using C = Cfg<BN>;
-  auto kern = gemm_tc_kernel<BN, PRO, STATS>;
+  auto kern = gemm_tc_kernel<BN, PRO, STATS, BMN>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
@@ -669,7 +722,11 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
 }
 
 template <int BN>
-int dispatch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p, bool pro, bool stats, int sms, cudaStream_t st) {
+int dispatch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p, bool pro, bool stats, int sms, cudaStream_t st,
+             bool b_mn = false) {
+  if constexpr (BN >= 64) {
+    if (b_mn) return launch<BN, false, false, true>(ta, tb, td, p, sms, st);
+  }
   if (pro && stats) return launch<BN, true, true>(ta, tb, td, p, sms, st);
   if (pro) return launch<BN, true, false>(ta, tb, td, p, sms, st);
   if (stats) return launch<BN, false, true>(ta, tb, td, p, sms, st);
@@ -677,6 +734,37 @@ int dispatch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td
 }
 
 }  // namespace
+
+// D[M,N] = A[M,K] * B[K,N]   with B given row-major [K][N] (row stride ldb): dgrad of a 1x1 conv / linear
+// (dX = dY * W with W = [Cout=K][Cin=N]) without a transposed weight copy.
+DLB_API int dlb_gemm_tc_bmn(const void* a, long long lda, const void* b, long long ldb, void* d, long long ldd, int M, int N, int K,
+                            int sm_limit, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((K % 8) || (N % 8) || (lda % 8) || (ldb % 8) || (ldd % 8) || ((uintptr_t)a & 15) || ((uintptr_t)b & 15) || ((uintptr_t)d & 15)) return -3;
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int sms = sm_count;
+  if (sm_limit > 0 && sm_limit < sms) sms = sm_limit;
+  const int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  CUtensorMap ta, tb, td;
+  int rc = make_map(&ta, a, M, K, lda, BM);
+  if (rc) return rc - 10;
+  rc = make_map(&tb, b, K, N, ldb, 64);                 // boxes of [64 k-rows][64 n]
+  if (rc) return rc - 20;
+  rc = make_map(&td, d, M, N, ldd, 32);
+  if (rc) return rc - 30;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.d = d; p.ldd = ldd; p.accumulate_out = 0;
+  p.pro_a = nullptr; p.pro_b = nullptr; p.pro_ld = 0; p.rows_per_sample = M; p.stats = nullptr; p.stats_ns = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bn == 64) return dispatch<64>(ta, tb, td, p, false, false, sms, st, true);
+  if (bn == 128) return dispatch<128>(ta, tb, td, p, false, false, sms, st, true);
+  return dispatch<256>(ta, tb, td, p, false, false, sms, st, true);
+}
 
 // D[M,N] (bf16, row stride ldd) = pro(A[M,K] (bf16, row stride lda)) * B[N,K]^T (bf16, row stride ldb).
 //   pro_a/pro_b (optional): fp32 [M / rows_per_sample][K] affine coefficients -> A' = relu(a*A + b)

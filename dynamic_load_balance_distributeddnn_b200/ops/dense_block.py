@@ -234,10 +234,10 @@ class _DenseBlockFn(torch.autograd.Function):
                 # fused path: relu(GN1(x)) was never materialised.  dgrad and wgrad run on the tcgen05 kernels
                 # (the wgrad re-applies GN+ReLU to the raw buffer slice in its operand prologue) and the GN1
                 # backward recomputes the ReLU mask from the saved affine coefficients.
-                w1_2d = gemm_tc._w2d(w1)
-                w1_t = w1_2d.t().contiguous()                                      # [cl, cm]: B operand of dX = dY * W
+                w1_2d = gemm_tc._w2d(w1)                                            # [cm, cl], consumed MN-major: no transpose
                 dxhat = torch.empty((n, cl, h, w), dtype=buf.dtype, device=buf.device, memory_format=torch.channels_last)
-                gemm_tc.gemm_raw(dy.data_ptr(), cm, w1_t.data_ptr(), w1_t.stride(0), dxhat.data_ptr(), cl, n * hw, cl, cm, buf.device)
+                gemm_tc.gemm_bmn_raw(dy.data_ptr(), cm, w1_2d.data_ptr(), w1_2d.stride(0), dxhat.data_ptr(), cl, n * hw, cl, cm,
+                                     buf.device)
                 if side is not None:
                     ev_dy = torch.cuda.Event(); ev_dy.record(main)
                     side.wait_event(ev_dy)

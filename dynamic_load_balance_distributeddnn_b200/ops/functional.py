@@ -31,6 +31,13 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``F.linear``; bf16 shapes the tcgen05 GEMM supports (K, N multiples of 8, >= 128 rows) run on it."""
+    if x.is_cuda and weight.dtype == x.dtype:
+        from . import conv as _conv
+        if _conv._ENABLED and nat.available():
+            from . import gemm_tc
+            if gemm_tc.linear_supported(x, weight):
+                return gemm_tc.linear(x, weight, bias)
     if weight.dtype != x.dtype:
         weight = weight.to(x.dtype)
     if bias is not None and bias.dtype != x.dtype:

@@ -21,6 +21,7 @@ def _lib():
     if not _DECLARED:
         vp, i64, i32 = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
         nat.declare("dlb_gemm_tc", i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, i32, vp, i64, i32, vp])
+        nat.declare("dlb_gemm_tc_bmn", i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp])
         nat.declare("dlb_wgrad_tc", i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, i32, i32, vp])
         _DECLARED = True
     return lib
@@ -51,6 +52,21 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, p
     assert out.stride(1) == 1
     gemm_raw(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), out.stride(0), m, n, k, a.device,
              pro_a, pro_b, rows_per_sample, stats, 0, stats_ns)
+    return out
+
+
+def gemm_bmn_raw(a_ptr: int, lda: int, b_ptr: int, ldb: int, d_ptr: int, ldd: int, m: int, n: int, k: int, device,
+                 sm_limit: int = 0) -> None:
+    """d[m,n] = a[m,k] @ b[k,n] with b row-major [k][n] (no transposed copy; MN-major tensor-core operand)."""
+    nat.check(_lib().dlb_gemm_tc_bmn(a_ptr, lda, b_ptr, ldb, d_ptr, ldd, m, n, k, sm_limit, nat.stream_ptr(device)), "gemm_tc_bmn")
+
+
+def gemm_bmn(a: torch.Tensor, b_kn: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    m, k = a.shape
+    n = b_kn.shape[1]
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.bfloat16, device=a.device)
+    gemm_bmn_raw(a.data_ptr(), a.stride(0), b_kn.data_ptr(), b_kn.stride(0), out.data_ptr(), out.stride(0), m, n, k, a.device)
     return out
 
 
@@ -102,12 +118,12 @@ class _Conv1x1Fn(torch.autograd.Function):
         w2 = _w2d(weight)
         if ctx.needs_input_grad[0]:
             dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
-            wt = w2.t().contiguous()                                   # [Cin, Cout]: B operand of dX = dY * W
-            gemm_raw(dyv.data_ptr(), lddy, wt.data_ptr(), wt.stride(0), dx.data_ptr(), c, n * hw, c, o, dy.device)
+            # dX = dY * W with W = [Cout][Cin] consumed as an MN-major operand: no transposed weight copy
+            gemm_bmn_raw(dyv.data_ptr(), lddy, w2.data_ptr(), w2.stride(0), dx.data_ptr(), c, n * hw, c, o, dy.device)
         if ctx.needs_input_grad[1]:
-            x2 = torch.as_strided(xv, (n * hw, c), (ld, 1))
-            dy2 = torch.as_strided(dyv, (n * hw, o), (lddy, 1))
-            dw = (dy2.t() @ x2).reshape(weight.shape[0], weight.shape[1], 1, 1).to(weight.dtype)
+            dwf = torch.zeros((o, c), dtype=torch.float32, device=dy.device)
+            wgrad_raw(dyv.data_ptr(), lddy, xv.data_ptr(), ld, dwf, n * hw, o, c, dy.device)     # MN-major split-K tcgen05
+            dw = dwf.view(o, c, 1, 1).to(weight.dtype)
         return dx, dw
 
 
@@ -116,7 +132,56 @@ def conv_supported(x, weight, stride, padding, groups) -> bool:
         return False
     return (x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and x.dim() == 4 and groups == 1
             and stride == 1 and padding == 0 and weight.shape[2] == 1 and weight.shape[3] == 1
-            and x.shape[1] % 8 == 0 and x.shape[0] * x.shape[2] * x.shape[3] >= 128)
+            and x.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0 and x.shape[0] * x.shape[2] * x.shape[3] >= 128)
+
+
+class _LinearFn(torch.autograd.Function):
+    """y[T,N] = x[T,K] @ W[N,K]^T on the tcgen05 GEMM; dgrad consumes W as an MN-major operand, wgrad reads dY and X
+    as MN-major operands (reduction over tokens) -- no transposes anywhere."""
+
+    @staticmethod
+    def forward(ctx, x2, weight):
+        t, k = x2.shape
+        n = weight.shape[0]
+        y = torch.empty((t, n), dtype=x2.dtype, device=x2.device)
+        gemm_raw(x2.data_ptr(), x2.stride(0), weight.data_ptr(), weight.stride(0), y.data_ptr(), n, t, n, k, x2.device)
+        ctx.save_for_backward(x2, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight = ctx.saved_tensors
+        t, k = x2.shape
+        n = weight.shape[0]
+        dy = dy.contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((t, k), dtype=dy.dtype, device=dy.device)
+            gemm_bmn_raw(dy.data_ptr(), n, weight.data_ptr(), weight.stride(0), dx.data_ptr(), k, t, k, n, dy.device)
+        if ctx.needs_input_grad[1]:
+            dwf = torch.zeros((n, k), dtype=torch.float32, device=dy.device)
+            wgrad_raw(dy.data_ptr(), n, x2.data_ptr(), x2.stride(0), dwf, t, n, k, dy.device)
+            dw = dwf.to(weight.dtype)
+        return dx, dw
+
+
+def linear_supported(x, weight) -> bool:
+    if not available() or x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16 or weight.dim() != 2:
+        return False
+    n, k = weight.shape
+    tokens = x.numel() // max(1, x.shape[-1])
+    return k % 8 == 0 and n % 8 == 0 and tokens >= 128 and weight.stride(1) == 1 and weight.stride(0) % 8 == 0
+
+
+def linear(x, weight, bias=None):
+    k = x.shape[-1]
+    x2 = x.reshape(-1, k)
+    if x2.stride(1) != 1 or x2.stride(0) % 8 != 0 or (x2.data_ptr() & 15):
+        x2 = x2.contiguous()
+    y = _LinearFn.apply(x2, weight).view(*x.shape[:-1], weight.shape[0])
+    if bias is not None:
+        y = y + bias.to(y.dtype)
+    return y
 
 
 def conv2d(x, weight, bias, stride, padding):

@@ -125,3 +125,33 @@ def test_wgrad_with_gn_relu_prologue(g, hw, co, ci):
     r = dy.float().t() @ xa.float()
     err = (dw - r).abs().max().item()
     assert err < 5e-3 * max(1.0, r.abs().max().item()), (err, r.abs().max().item())
+
+
+@pytest.mark.parametrize("m,n,k", [(4096, 256, 128), (65536, 64, 128), (1000, 200, 72), (8192, 1024, 128), (300, 600, 200)])
+def test_gemm_b_mn_major(g, m, n, k):
+    """D = A[M,K] @ B[K,N] with B row-major [K][N] (dgrad without a transposed weight copy)."""
+    torch.manual_seed(m + n)
+    a = torch.randn(m, k, device="cuda").bfloat16()
+    b = (torch.randn(k, n, device="cuda") / k ** 0.5).bfloat16()
+    d = g.gemm_bmn(a, b)
+    torch.cuda.synchronize()
+    r = a.float() @ b.float()
+    err = (d.float() - r).abs().max().item()
+    assert err < 2e-2 * max(1.0, r.abs().max().item()), err
+
+
+def test_linear_autograd_on_tcgen05(g):
+    torch.manual_seed(5)
+    x = torch.randn(35, 16, 200, device="cuda").bfloat16().requires_grad_(True)
+    w = (torch.randn(600, 200, device="cuda") / 14).bfloat16().requires_grad_(True)
+    b = torch.randn(600, device="cuda").bfloat16().requires_grad_(True)
+    assert g.linear_supported(x, w)
+    y = g.linear(x, w, b)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xr, wr, br = (t.detach().float().requires_grad_(True) for t in (x, w, b))
+    yr = torch.nn.functional.linear(xr, wr, br)
+    yr.backward(gy.float())
+    assert (y.float() - yr).abs().max().item() < 3e-2 * yr.abs().max().item()
+    assert (x.grad.float() - xr.grad).abs().max().item() < 3e-2 * xr.grad.abs().max().item()
+    assert (w.grad.float() - wr.grad).abs().max().item() < 3e-2 * wr.grad.abs().max().item()
