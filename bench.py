@@ -31,6 +31,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# keep stdout to the single JSON line: NCCL's version banner goes to a file instead
+os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/dlb_nccl_%h_%p.log")
 
 METRIC = "densenet121_cifar10_images_per_sec"
 
@@ -47,6 +49,7 @@ def parse():
     p.add_argument("--throttle-ms", type=float, default=3.0, help="extra ms/step on the last rank when N>1")
     p.add_argument("--no-dbs", action="store_true")
     p.add_argument("--no-graphs", action="store_true")
+    p.add_argument("--no-overlap", action="store_true")
     p.add_argument("--comm", default="auto")
     p.add_argument("--algo", default="auto")
     p.add_argument("--dtype", default="bf16")
@@ -99,21 +102,52 @@ def run_ours(a) -> dict:
     W, K = max(3, a.warmup), a.steps
     total_steps = 2 * (W + 8) + 2 * K + 8
     throttle = a.throttle_ms if world > 1 else 0.0
+    lm = a.model == "transformer"
+    if lm:
+        a.dataset = "wikitext2"
     cfg = DBSConfig(debug=False, world_size=world, batch_size=a.batch, model=a.model, dataset=a.dataset, synthetic=True,
-                    train_samples=a.batch * total_steps, test_samples=256, epoch_size=1, validate=False,
+                    train_samples=(a.batch * 36 * (total_steps + 4)) if lm else a.batch * total_steps, test_samples=256,
+                    epoch_size=1, validate=False,
                     dynamic_batch_size=not a.no_dbs, cuda_graphs=not a.no_graphs, comm=a.comm, allreduce_algo=a.algo,
-                    dtype=a.dtype, throttle_rank=world - 1 if throttle > 0 else -1, throttle_ms=throttle,
+                    dtype=a.dtype, overlap_comm=not a.no_overlap, throttle_rank=world - 1 if throttle > 0 else -1, throttle_ms=throttle,
                     throttle_mode="sleep", log_dir="/tmp/dlb_bench/logs", stats_dir="/tmp/dlb_bench/statis")
     logger = init_logger(cfg, rank, stream=False)
     tr = Trainer(cfg, rank, world, device, logger)
     is_lm = tr.is_lm
 
     def make_shard(local_batches, n_steps, seed):
+        if is_lm:
+            return (int(local_batches[rank]), n_steps, seed)
         part = DataPartitioner(len(tr.train_set), local_batches, seed, True, n_steps)
         return part.use(rank)
 
+    lm_cache = {}
+
+    def lm_batches(b, n_steps, seed):
+        """pinned [n_steps][bptt+1, b] token windows cut from the (synthetic) corpus, like Trainer._train_epoch_lm"""
+        key = (b, n_steps, seed)
+        if key not in lm_cache:
+            from dynamic_load_balance_distributeddnn_b200.data import batchify
+            need = b * (cfg.bptt * n_steps + 1)
+            stream = tr.corpus.train
+            off = (seed * 7919 + rank * need) % max(1, stream.numel() - need)
+            lm_cache[key] = batchify(stream[off:off + need], b).pin_memory()
+        return lm_cache[key]
+
     def run_steps(shard, n, e2e=True, sink=None):
         import numpy as np
+        if is_lm:
+            b, n_steps, seed = shard
+            data = lm_batches(b, n_steps, seed)
+            for s in range(n):
+                i = (s if e2e else 0) * cfg.bptt
+                if e2e or s == 0:
+                    src = data[i:i + cfg.bptt].to(device, non_blocking=True)                  # H2D from pinned memory
+                    tgt = data[i + 1:i + 1 + cfg.bptt].reshape(-1).to(device, non_blocking=True)
+                tr.train_step(src, tgt)
+                if e2e and sink is not None:
+                    sink[s % sink.shape[0]].copy_(tr.loss_acc, non_blocking=True)
+            return
         order = np.arange(len(shard))
         for s in range(n):
             if e2e or s == 0:
@@ -180,13 +214,14 @@ def run_ours(a) -> dict:
     clk = clocks.stop() if rank == 0 else {}
     if hasattr(tr.comm, "check_errors"):
         tr.comm.check_errors()
-    h2d = tr.stager.bytes_per_step
+    per_step_items = a.batch * (cfg.bptt if is_lm else 1)          # images, or tokens for the LM
+    h2d = (2 * cfg.bptt * int(lb[rank]) * 8) if is_lm else tr.stager.bytes_per_step
     loss = float(tr.loss_acc.item())
-    value = a.batch * K / (ms_dev * 1e-3)
-    e2e_value = a.batch * K / (ms_e2e * 1e-3)
+    value = per_step_items * K / (ms_dev * 1e-3)
+    e2e_value = per_step_items * K / (ms_e2e * 1e-3)
     out = {
-        "metric": METRIC if a.model == "densenet" else f"{a.model}_{a.dataset}_images_per_sec",
-        "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": K, "warmup": 2 * (W + 8),
+        "metric": METRIC if a.model == "densenet" else (f"{a.model}_{a.dataset}_tokens_per_sec" if is_lm else f"{a.model}_{a.dataset}_images_per_sec"),
+        "value": round(value, 2), "unit": "tokens/s" if is_lm else "images/s", "n_gpus": world, "steps": K, "warmup": 2 * (W + 8),
         "ms_per_step": round(ms_dev / K, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": a.dtype, "data": "synthetic (CIFAR-10-shape uint8 images, random-init weights)", "impl": "ours",
         "config": {"model": "DenseNet-121 (GroupNorm)" if a.model == "densenet" else a.model, "global_batch": a.batch,
@@ -195,7 +230,7 @@ def run_ours(a) -> dict:
                    "throttle": {"rank": world - 1, "ms_per_step": throttle} if throttle > 0 else None,
                    "comm": tr.comm.name, "cuda_graphs": bool(tr._graphs), "optimizer": "SGD momentum 0.9 (in timed region)",
                    "l2": "per-step working set (activations+grads, >1 GB) exceeds the 126 MB L2; no explicit flush"},
-        "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "ms_per_step": round(ms_e2e / K, 4),
+        "e2e": {"value": round(e2e_value, 2), "unit": "tokens/s" if is_lm else "images/s", "ms_per_step": round(ms_e2e / K, 4),
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
         "straggler_wait_ms_per_step": round(1e3 * wait_dev / K, 4),
@@ -234,8 +269,14 @@ def run_reference(a) -> dict:
     os.makedirs(os.path.join(work, "logs"), exist_ok=True)
     os.makedirs(os.path.join(work, "statis"), exist_ok=True)
     os.chdir(work)
+    if not os.path.exists(os.path.join(work, "rnn_data")) and os.path.isdir(os.path.join(ref_dir, "rnn_data")):
+        os.symlink(os.path.join(ref_dir, "rnn_data"), os.path.join(work, "rnn_data"))     # its Corpus path is relative
     sys.path.insert(0, ref_dir)
-    argv = ["dbs.py", "-d", "false", "-ws", str(world), "-b", str(a.batch), "-m", a.model, "-ds", a.dataset, "-e", "2",
+    is_lm = a.model == "transformer"
+    if is_lm:
+        a.dataset = "wikitext2"
+    ref_model = {"resnet50": "resnet"}.get(a.model, a.model)         # its CLI has no resnet50; the class exists (Net/Resnet.py:99)
+    argv = ["dbs.py", "-d", "false", "-ws", str(world), "-b", str(a.batch), "-m", ref_model, "-ds", a.dataset, "-e", "2",
             "-dbs", "false" if a.no_dbs else "true"]
     if world > 1:
         argv += ["-gpu", ",".join(str(i) for i in range(world))]
@@ -298,6 +339,9 @@ def run_reference(a) -> dict:
     elif a.model == "resnet50":
         import Net.Resnet
         model = Net.Resnet.ResNet50(10)
+    elif is_lm:
+        import Net.Transformer
+        model = Net.Transformer.TransformerModel(33278, 200, 2, 200, 2, 0.2)      # literals of reference run() (dbs.py:337-343)
     else:
         import Net.Resnet
         model = Net.Resnet.ResNet101(10)
@@ -306,7 +350,7 @@ def run_reference(a) -> dict:
         dist.all_reduce(p.data, op=dist.ReduceOp.SUM)
         p.data /= float(world)
     optimizer = torch.optim.SGD(model.parameters(), lr=dbs.lr, momentum=0.9)
-    criterion = torch.nn.functional.cross_entropy
+    criterion = torch.nn.functional.nll_loss if is_lm else torch.nn.functional.cross_entropy
     nodes_time = np.array([1.0 for _ in range(world)])
     partition = np.array([1.0 / world for _ in range(world)])
 
@@ -316,13 +360,19 @@ def run_reference(a) -> dict:
             partition = dbs.get_size(nodes_time, partition)
         n_holder["n"] = a.batch * (n_steps + 2)
         train_set, _, bsz = dataloader.partition_dataset(a.dataset, partition, rank, a.batch, 1234)
-        loader = itertools.islice(iter(train_set), n_steps)
+        if is_lm:
+            loader = train_set[: n_steps * 35 + 1]          # exactly n_steps bptt windows of its batchified shard
+        else:
+            loader = itertools.islice(iter(train_set), n_steps)
         if timed:
             dist.barrier()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        t_train, t_sync, loss = dbs.train(loader, model, optimizer, criterion, e, n_steps, partition)
+        if is_lm:
+            t_train, t_sync, loss = dbs.transformer_train(loader, model, optimizer, criterion, e, n_steps, partition, 33278, 35)
+        else:
+            t_train, t_sync, loss = dbs.train(loader, model, optimizer, criterion, e, n_steps, partition)
         ms = 0.0
         if timed:
             e1.record()
@@ -340,11 +390,11 @@ def run_reference(a) -> dict:
     ms, bsz, t_sync, loss = epoch(1, K, True)
     clk = clocks.stop() if rank == 0 else {}
     ms = max_over_ranks(ms, device, world)
-    global_bs = int(sum_over_ranks(float(bsz), device, world))
-    value = global_bs * K / (ms * 1e-3)
+    global_bs = int(sum_over_ranks(float(int(bsz)), device, world))
+    value = global_bs * (35 if is_lm else 1) * K / (ms * 1e-3)
     out = {
-        "metric": METRIC if a.model == "densenet" else f"{a.model}_{a.dataset}_images_per_sec",
-        "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+        "metric": METRIC if a.model == "densenet" else (f"{a.model}_{a.dataset}_tokens_per_sec" if is_lm else f"{a.model}_{a.dataset}_images_per_sec"),
+        "value": round(value, 2), "unit": "tokens/s" if is_lm else "images/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "fp32", "data": "synthetic (CIFAR-10-shape, random-init weights)", "impl": "reference",
         "config": {"model": a.model, "global_batch": a.batch, "effective_global_batch": global_bs, "parallelism": f"dp{world}",

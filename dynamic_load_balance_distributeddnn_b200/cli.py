@@ -106,6 +106,7 @@ def get_parser() -> argparse.ArgumentParser:
     x.add_argument("--throttle_mode", choices=("sleep", "burn"), default="sleep")
     x.add_argument("--cuda_graphs", type=str2bool, default=True)
     x.add_argument("--bucket_mb", type=float, default=8.0)
+    x.add_argument("--overlap_comm", type=str2bool, default=True, help="overlap bucket allreduces with backward")
     x.add_argument("--wire_dtype", choices=("fp32", "bf16"), default="fp32")
     x.add_argument("--allreduce_algo", choices=("auto", "oneshot", "twoshot", "nvls"), default="auto")
     x.add_argument("--max_steps_per_epoch", type=int, default=0)

@@ -61,6 +61,7 @@ class DBSConfig:
     throttle_mode: str = "sleep"         # sleep | burn (device burner kernel)
     cuda_graphs: bool = True
     bucket_mb: float = 8.0
+    overlap_comm: bool = True            # fire bucket collectives from autograd hooks on a side stream
     wire_dtype: str = "fp32"             # fp32 | bf16 wire format of the gradient allreduce
     allreduce_algo: str = "auto"         # auto | oneshot | twoshot | nvls
     max_steps_per_epoch: int = 0         # cap (0 = full epoch)

@@ -355,6 +355,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int stage = 0; uint32_t phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m0 = (t / num_n) * BM;
+      // common case: the whole 128-row tile lies inside one sample and inside M -> one coefficient set per
+      // k-block, no per-row integer division in the inner loop
+      const int s_first = m0 / p.rows_per_sample;
+      const bool uniform = (m0 + BM <= p.M) && ((m0 + BM - 1) / p.rows_per_sample == s_first);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
@@ -368,13 +372,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         int cur = -1;
         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+        if (uniform) {
+          const float4* ca = reinterpret_cast<const float4*>(p.pro_a + (long long)s_first * p.pro_ld + kb * BK + cc * 8);
+          const float4* cb = reinterpret_cast<const float4*>(p.pro_b + (long long)s_first * p.pro_ld + kb * BK + cc * 8);
+          a0 = __ldg(ca); a1 = __ldg(ca + 1); b0 = __ldg(cb); b1 = __ldg(cb + 1);
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = r_base + 32 * i;
           const int grow = m0 + r;
-          const bool live = grow < p.M;
-          const int sample = min(grow, p.M - 1) / p.rows_per_sample;
-          if (sample != cur) {
+          const bool live = uniform || grow < p.M;
+          const int sample = uniform ? s_first : min(grow, p.M - 1) / p.rows_per_sample;
+          if (!uniform && sample != cur) {
             // coefficient rows are padded to a multiple of BK and zero-filled by the host (a = b = 0 beyond K)
             const float4* ca = reinterpret_cast<const float4*>(p.pro_a + (long long)sample * p.pro_ld + kb * BK + cc * 8);
             const float4* cb = reinterpret_cast<const float4*>(p.pro_b + (long long)sample * p.pro_ld + kb * BK + cc * 8);
@@ -613,6 +622,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
         const uint32_t sb = smem_u32(smem + stage * C::kStageBytes + C::kABytes + box * C::kBoxBytes);
         int cur = -1;
         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+        const int s_first = rr / p.rows_per_sample;
+        const bool uniform = in_range && (rr + 64 <= p.M) && ((rr + 63) / p.rows_per_sample == s_first);
+        if (uniform) {
+          const float4* ca = reinterpret_cast<const float4*>(p.pro_a + (long long)s_first * p.pro_ld + cbase);
+          const float4* cb = reinterpret_cast<const float4*>(p.pro_b + (long long)s_first * p.pro_ld + cbase);
+          a0 = __ldg(ca); a1 = __ldg(ca + 1); b0 = __ldg(cb); b1 = __ldg(cb + 1);
+        }
         constexpr int kIters = 64 / kRowStep;          // 2, 4 or 8 chunks per thread per stage
         constexpr int kBatch = kIters < 4 ? kIters : 4;
 #pragma unroll
@@ -627,9 +643,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
           for (int j = 0; j < kBatch; ++j) {
             const int r = r_base + kRowStep * (i0 + j);
             const int grow = rr + r;
-            const bool live = grow < p.M && in_range;
-            const int sample = min(grow, p.M - 1) / p.rows_per_sample;
-            if (sample != cur && in_range) {
+            const bool live = uniform || (grow < p.M && in_range);
+            const int sample = uniform ? s_first : min(grow, p.M - 1) / p.rows_per_sample;
+            if (!uniform && sample != cur && in_range) {
               const float4* ca = reinterpret_cast<const float4*>(p.pro_a + (long long)sample * p.pro_ld + cbase);
               const float4* cb = reinterpret_cast<const float4*>(p.pro_b + (long long)sample * p.pro_ld + cbase);
               a0 = __ldg(ca); a1 = __ldg(ca + 1); b0 = __ldg(cb); b1 = __ldg(cb + 1);

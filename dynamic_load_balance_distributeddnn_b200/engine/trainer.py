@@ -82,6 +82,8 @@ class Trainer:
         self.flat = FlatState(self.model, self.device, self.dtype, self.comm, cfg.learning_rate, cfg.momentum,
                               0.0, cfg.bucket_mb, _DT[cfg.wire_dtype], cfg.resolved_clip() if cfg.clip_mode == "local" else 0.0)
         self.flat.sync_initial_params()
+        if cfg.overlap_comm:
+            self.flat.enable_overlap()
         torch.manual_seed(cfg.seed + 1 + self.rank)
         if self.cuda:
             torch.cuda.manual_seed(cfg.seed + 1 + self.rank)

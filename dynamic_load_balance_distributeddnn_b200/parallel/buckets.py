@@ -73,6 +73,8 @@ class FlatState:
         self._adopt(model)
         self.buckets = self._make_buckets(bucket_mb)
         self._pack_cache = None
+        self._rank = getattr(comm, "rank", 0)
+        self._keep_overlap = []
 
     # ---- parameter adoption -----------------------------------------------------------------------
     def _adopt(self, model: nn.Module) -> None:
@@ -99,19 +101,67 @@ class FlatState:
                     mod._buffers[k] = b.to(self.device)
 
     def _make_buckets(self, bucket_mb: float) -> List[Tuple[int, int]]:
-        """Contiguous (offset, numel) ranges of the flat buffer, ~bucket_mb each, aligned so every
-        rank-chunk is a whole number of 16-byte vectors."""
+        """Contiguous (offset, numel) ranges of the flat buffer, ~bucket_mb each, cut at parameter boundaries
+        (every offset is a multiple of 32 elements, so each range is a whole number of 16-byte vectors).
+        ``self.bucket_params[k]`` lists the parameter indices living in bucket k."""
         esize = 2 if self.wire_dtype == torch.bfloat16 else 4
-        target = max(1, int(bucket_mb * (1 << 20) / esize))
-        world = max(1, self.comm.world)
-        quantum = _ALIGN * world
-        target = max(quantum, target // quantum * quantum)
-        out, off = [], 0
-        while off < self.numel:
-            n = min(target, self.numel - off)
-            out.append((off, n))
-            off += n
+        target = max(_ALIGN, int(bucket_mb * (1 << 20) / esize))
+        out, groups = [], []
+        start, cur = 0, []
+        for i, off in enumerate(self.offsets):
+            end = self.offsets[i + 1] if i + 1 < len(self.offsets) else self.numel
+            cur.append(i)
+            if end - start >= target or i + 1 == len(self.offsets):
+                out.append((start, end - start))
+                groups.append(cur)
+                start, cur = end, []
+        if not out:
+            out, groups = [(0, self.numel)], [list(range(len(self.params)))]
+        self.bucket_params = groups
         return out
+
+    # ---- overlap of the gradient collective with backward -----------------------------------------------
+    def enable_overlap(self) -> bool:
+        """Fire each bucket's pack + fused allreduce on a side stream as soon as autograd has produced the last
+        gradient of the bucket, so the collective overlaps the rest of the backward pass (the reference waits for
+        the whole backward and then blocks on one allreduce per tensor, dbs.py:291-301).  Needs the native path,
+        more than one rank and no *local* clipping (a global norm is only known after the full backward)."""
+        if not self.native or self.comm.world <= 1 or self.clip_norm > 0 or getattr(self, "_overlap", False):
+            return getattr(self, "_overlap", False)
+        self._overlap = True
+        self._comm_stream = torch.cuda.Stream(self.device)
+        self._bucket_of = [0] * len(self.params)
+        for b, idxs in enumerate(self.bucket_params):
+            for i in idxs:
+                self._bucket_of[i] = b
+        self._pending = [len(g) for g in self.bucket_params]
+        self._fired = [False] * len(self.buckets)
+        self._hooks = []
+        for i, p in enumerate(self.params):
+            self._hooks.append(p.register_post_accumulate_grad_hook(lambda _p, i=i: self._on_grad(i)))
+        return True
+
+    def _on_grad(self, i: int) -> None:
+        b = self._bucket_of[i]
+        self._pending[b] -= 1
+        if self._pending[b] == 0 and not self._fired[b]:
+            self._fire(b)
+
+    def _fire(self, b: int) -> None:
+        lib = nat.require()
+        main = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._comm_stream.wait_event(ev)
+        idxs = self.bucket_params[b]
+        with torch.cuda.stream(self._comm_stream):
+            ptrs, offs, numels, dtypes, n, keep = self._grad_lists(idxs)
+            nat.check(lib.dlb_mt_pack(n, ptrs, offs, numels, dtypes, self.grad_in.data_ptr(), nat.dtype_code(self.wire_dtype),
+                                      self.weights_t.data_ptr(), self._rank, None, 0.0,
+                                      nat.stream_ptr(self.device)), "mt_pack")
+            self._keep_overlap.append(keep)
+            self.comm.allreduce_buckets(self.grad_in, self.grad_out, [self.buckets[b]])
+        self._fired[b] = True
 
     # ---- synchronisation helpers ------------------------------------------------------------------
     def sync_initial_params(self) -> None:
@@ -137,9 +187,10 @@ class FlatState:
         self._weights_host = [float(w) for w in weights]
 
     # ---- the post-backward pipeline ---------------------------------------------------------------
-    def _grad_lists(self):
+    def _grad_lists(self, subset=None):
         ptrs, offs, numels, dtypes, keep = [], [], [], [], []
-        for p, off in zip(self.params, self.offsets):
+        it = zip(self.params, self.offsets) if subset is None else ((self.params[i], self.offsets[i]) for i in subset)
+        for p, off in it:
             g = p.grad
             if g is None:
                 g = torch.zeros_like(p)
@@ -164,6 +215,21 @@ class FlatState:
     def _reduce_and_step_native(self, rank: int) -> float:
         lib = nat.require()
         st = nat.stream_ptr(self.device)
+        if getattr(self, "_overlap", False):
+            # buckets were (mostly) fired from the autograd hooks; flush stragglers, join the comm stream, update
+            for b in range(len(self.buckets)):
+                if not self._fired[b]:
+                    self._fire(b)
+            ev = torch.cuda.Event()
+            ev.record(self._comm_stream)
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            g = self.grad_out if self.grad_out.dtype == torch.float32 else self.grad_out.float()
+            nat.check(lib.dlb_sgd_flat(self.master.data_ptr(), self.mom.data_ptr(), g.data_ptr(), nat.ptr(self.shadow), self.numel,
+                                       self.lr_t.data_ptr(), float(self.momentum), float(self.weight_decay), st), "sgd_flat")
+            self._pending = [len(gp) for gp in self.bucket_params]
+            self._fired = [False] * len(self.buckets)
+            self._keep, self._keep_overlap = self._keep_overlap, []
+            return 0.0
         ptrs, offs, numels, dtypes, n, keep = self._grad_lists()
         use_clip = self.clip_norm > 0
         if use_clip:
