@@ -294,3 +294,82 @@ DLB_API int dlb_attention_bwd(int dtype, const void* qkv, const void* dout, cons
   }
   return dlb_post_launch();
 }
+
+// ------------------------------------------------------------------------------------------------
+// Vocabulary cross-entropy over materialised logits, forward AND backward in one pass, in place:
+//   row r:  z = logits[r,:] + bias ;  loss_r = logsumexp(z) - z[target_r]
+//           logits[r,:] <- (softmax(z) - onehot(target_r)) * scale          (= d loss / d z, scale = 1/T)
+// One CTA per row; the row (V = 33 278 for wikitext-2) is staged in shared memory so global memory sees exactly
+// one read and one write of the [T, V] matrix (reference: log_softmax + nll_loss + their backward kernels =
+// ~5 passes over a 2.4 GB fp32 matrix; Net/Transformer.py:94-95, dbs.py:270-271).
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_ce_inplace_kernel(T* __restrict__ logits, int64_t ld, const float* __restrict__ bias,
+                                                                 const long long* __restrict__ target, float* __restrict__ loss_sum,
+                                                                 int V, float scale) {
+  extern __shared__ float row[];            // [V] fp32
+  __shared__ float red[8];
+  __shared__ float bc[2];
+  const int r = blockIdx.x;
+  T* p = logits + (int64_t)r * ld;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < V; i += 256) {
+    const float z = (float)p[i] + (bias ? bias[i] : 0.f);
+    row[i] = z;
+    m = fmaxf(m, z);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    m = red[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffu, m, o));
+    if (threadIdx.x == 0) bc[0] = m;
+  }
+  __syncthreads();
+  m = bc[0];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < V; i += 256) { const float e = __expf(row[i] - m); row[i] = e; s += e; }
+  s = warp_sum(s);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    s = red[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffu, s, o);
+    if (threadIdx.x == 0) bc[1] = s;
+  }
+  __syncthreads();
+  s = bc[1];
+  const float inv = 1.f / s;
+  const int t = (int)target[r];
+  if (threadIdx.x == 0) {
+    // loss_r = log(sum) + m - z_t, with z_t = log(row[t]) + m  ->  log(sum) - log(e_t)
+    atomicAdd(loss_sum, (__logf(s) - __logf(fmaxf(row[t], 1e-38f))) * scale);
+  }
+  for (int i = threadIdx.x; i < V; i += 256) {
+    float g = row[i] * inv;
+    if (i == t) g -= 1.f;
+    p[i] = (T)(g * scale);
+  }
+}
+}  // namespace
+
+DLB_API int dlb_softmax_ce_inplace(int dtype, void* logits, long long ld, const float* bias, const long long* target, float* loss_sum,
+                                   int T_rows, int V, float scale, void* stream) {
+  const size_t smb = (size_t)V * sizeof(float);
+  if (smb > 200 * 1024) return -2;
+  if (dtype == DLB_BF16) {
+    auto kern = softmax_ce_inplace_kernel<__nv_bfloat16>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
+    kern<<<T_rows, 256, smb, (cudaStream_t)stream>>>((__nv_bfloat16*)logits, ld, bias, target, loss_sum, V, scale);
+  } else {
+    auto kern = softmax_ce_inplace_kernel<float>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
+    kern<<<T_rows, 256, smb, (cudaStream_t)stream>>>((float*)logits, ld, bias, target, loss_sum, V, scale);
+  }
+  return dlb_post_launch();
+}

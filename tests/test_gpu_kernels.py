@@ -313,3 +313,24 @@ def test_fused_attention_matches_reference(nat, dtype, tol):
     # dropout: kept fraction ~ (1-p), rows renormalised by 1/(1-p), same mask regenerated in backward
     out_d = attention.causal_attention_packed(qkv.detach().requires_grad_(True), h, 0.2)
     assert torch.isfinite(out_d.float()).all() and (out_d.float() - out.float()).abs().max() > 0
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])
+def test_fused_linear_cross_entropy_native(nat, dtype, tol):
+    from dynamic_load_balance_distributeddnn_b200.ops import lm_native
+    from dynamic_load_balance_distributeddnn_b200 import ops
+    assert lm_native.has_linear_ce()
+    torch.manual_seed(0)
+    t, d, v = 700, 200, 33278
+    feats = torch.randn(t, d, device="cuda").to(dtype).requires_grad_(True)
+    w = (torch.randn(v, d, device="cuda") * 0.05).to(dtype).requires_grad_(True)
+    b = (torch.randn(v, device="cuda") * 0.1).to(dtype).requires_grad_(True)
+    tgt = torch.randint(0, v, (t,), device="cuda")
+    l1 = lm_native.linear_cross_entropy(feats, w, b, tgt)
+    l1.backward()
+    fr, wr, br = (x.detach().float().requires_grad_(True) for x in (feats, w, b))
+    l2 = ops.linear_cross_entropy_reference(fr, wr, br, tgt)
+    l2.backward()
+    assert abs(float(l1) - float(l2)) < tol * max(1.0, float(l2)), (float(l1), float(l2))
+    for a, r in ((feats.grad, fr.grad), (w.grad, wr.grad), (b.grad, br.grad)):
+        assert float((a.float() - r).abs().max()) < tol * max(1e-3, float(r.abs().max())) * 3, (a.float() - r).abs().max()
