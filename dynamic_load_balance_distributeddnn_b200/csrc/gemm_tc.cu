@@ -96,6 +96,19 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 
 __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr);
 
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -133,6 +146,11 @@ struct GemmParams {
   // EPI_STATS: table fp32 [num_samples][table_ns] holding (sum, sumsq) pairs per output channel
   float* stats;
   long long stats_ns;
+  // CONV3 (3x3, stride 1, pad 1, NHWC): A tiles are 4-D TMA boxes {64 ch, W, Hb, Nb} of the activation tensor shifted by
+  // the filter tap; out-of-image pixels come back as zeros from the TMA unit (that IS the padding).
+  int conv_H, conv_W, conv_C;   // input spatial size and channels (K = 9 * conv_C)
+  int conv_kchunks;             // ceil(conv_C / 64)
+  int conv_sign;                // +1 forward (x[h+dy, w+dx]), -1 dgrad (dy[h-dy, w-dx])
 };
 
 template <int BN> struct Cfg {
@@ -153,7 +171,9 @@ template <int BN> struct Cfg {
 // B_MN: the B operand is given as [K][N] row-major (N contiguous) instead of [N][K] -- e.g. the untransposed weight
 // matrix in a dgrad GEMM dX = dY * W.  Its tiles are loaded as (BN/64) TMA boxes of [64 k-rows][64 n] and consumed
 // through an MN-major shared-memory descriptor, so no transposed copy of the weights is ever made.
-template <int BN, bool PRO_GN, bool EPI_STATS, bool B_MN = false>
+// CONV3: implicit-GEMM 3x3 convolution (see GemmParams); with B_MN it is the data-gradient (flipped taps, weights
+// consumed untransposed through a 3-D tensor map {Cin, 9, Cout}).
+template <int BN, bool PRO_GN, bool EPI_STATS, bool B_MN = false, bool CONV3 = false>
 __global__ void __launch_bounds__(PRO_GN ? 512 : 256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
@@ -172,7 +192,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
-  const int num_kb = (p.K + BK - 1) / BK;
+  const int num_kb = CONV3 ? 9 * p.conv_kchunks : (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -213,12 +233,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t sb = sa + C::kABytes;
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_expect_tx(fb, C::kStageBytes);
-          tma_load_2d(sa, &tmap_a, fb, kb * BK, m0);
-          if constexpr (B_MN) {
+          if constexpr (CONV3) {
+            const int tap = kb / p.conv_kchunks, kc = kb - tap * p.conv_kchunks;
+            const int dy = (tap / 3 - 1) * p.conv_sign, dx = (tap % 3 - 1) * p.conv_sign;
+            const int hw = p.conv_H * p.conv_W;
+            const int img = m0 / hw, h0 = (m0 - img * hw) / p.conv_W;
+            tma_load_4d(sa, &tmap_a, fb, kc * BK, dx, h0 + dy, img);
+            if constexpr (B_MN) {
 #pragma unroll
-            for (int gi = 0; gi < BN / 64; ++gi) tma_load_2d(sb + gi * 8192, &tmap_b, fb, n0 + gi * 64, kb * BK);
+              for (int gi = 0; gi < BN / 64; ++gi) tma_load_3d(sb + gi * 8192, &tmap_b, fb, n0 + gi * 64, tap, kc * BK);
+            } else {
+              tma_load_2d(sb, &tmap_b, fb, tap * p.conv_C + kc * BK, n0);
+            }
           } else {
-            tma_load_2d(sb, &tmap_b, fb, kb * BK, n0);
+            tma_load_2d(sa, &tmap_a, fb, kb * BK, m0);
+            if constexpr (B_MN) {
+#pragma unroll
+              for (int gi = 0; gi < BN / 64; ++gi) tma_load_2d(sb + gi * 8192, &tmap_b, fb, n0 + gi * 64, kb * BK);
+            } else {
+              tma_load_2d(sb, &tmap_b, fb, kb * BK, n0);
+            }
           }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
@@ -721,10 +755,27 @@ int make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, 
   return r == CUDA_SUCCESS ? 0 : -11;
 }
 
-template <int BN, bool PRO, bool STATS, bool BMN = false>
+// general rank-n bf16 tensor map (dims/strides innermost first; strides in elements for dims 1..n-1)
+int make_map_nd(CUtensorMap* map, const void* ptr, int rank, const long long* dims, const long long* strides, const int* box) {
+  auto enc = get_encode();
+  if (!enc) return -10;
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(0); ctx_bound = true; }
+  cuuint64_t d[5]; cuuint64_t sbytes[4]; cuuint32_t b[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = (cuuint64_t)dims[i]; b[i] = (cuuint32_t)box[i]; es[i] = 1; }
+  for (int i = 1; i < rank; ++i) sbytes[i - 1] = (cuuint64_t)strides[i] * 2;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), d, sbytes, b, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS && getenv("DLB_DEBUG_TMAP"))
+    fprintf(stderr, "[dlb] cuTensorMapEncodeTiled(rank %d) failed (%d)\n", rank, (int)r);
+  return r == CUDA_SUCCESS ? 0 : -11;
+}
+
+template <int BN, bool PRO, bool STATS, bool BMN = false, bool CONV3 = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p, int sms, cudaStream_t st) {
   using C = Cfg<BN>;
-  auto kern = gemm_tc_kernel<BN, PRO, STATS, BMN>;
+  auto kern = gemm_tc_kernel<BN, PRO, STATS, BMN, CONV3>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
@@ -776,6 +827,7 @@ DLB_API int dlb_gemm_tc_bmn(const void* a, long long lda, const void* b, long lo
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.d = d; p.ldd = ldd; p.accumulate_out = 0;
   p.pro_a = nullptr; p.pro_b = nullptr; p.pro_ld = 0; p.rows_per_sample = M; p.stats = nullptr; p.stats_ns = 0;
+  p.conv_H = p.conv_W = p.conv_C = 0; p.conv_kchunks = 1; p.conv_sign = 1;
   cudaStream_t st = (cudaStream_t)stream;
   if (bn == 64) return dispatch<64>(ta, tb, td, p, false, false, sms, st, true);
   if (bn == 128) return dispatch<128>(ta, tb, td, p, false, false, sms, st, true);
@@ -817,6 +869,7 @@ DLB_API int dlb_gemm_tc(const void* a, long long lda, const void* b, long long l
   p.M = M; p.N = N; p.K = K; p.d = d; p.ldd = ldd; p.accumulate_out = 0;
   p.pro_a = pro_a; p.pro_b = pro_b; p.pro_ld = pro_ld; p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : M;
   p.stats = stats; p.stats_ns = stats_ns;
+  p.conv_H = p.conv_W = p.conv_C = 0; p.conv_kchunks = 1; p.conv_sign = 1;
   cudaStream_t st = (cudaStream_t)stream;
   const bool pro = pro_a != nullptr, sts = stats != nullptr;
   switch (bn) {
@@ -882,4 +935,83 @@ DLB_API int dlb_wgrad_tc(const void* dy, long long lddy, const void* x, long lon
   if (bn == 64) return pro ? launch_wgrad<64, true>(tdy, tx, p, grid, st) : launch_wgrad<64, false>(tdy, tx, p, grid, st);
   if (bn == 128) return pro ? launch_wgrad<128, true>(tdy, tx, p, grid, st) : launch_wgrad<128, false>(tdy, tx, p, grid, st);
   return pro ? launch_wgrad<256, true>(tdy, tx, p, grid, st) : launch_wgrad<256, false>(tdy, tx, p, grid, st);
+}
+
+namespace {
+int sm_count_cached() {
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sm_count;
+}
+// box geometry for 128-pixel tiles made of whole image rows
+bool conv_tile_geometry(int N, int H, int W, int& hb, int& nb) {
+  if (W <= 0 || H <= 0 || 128 % W) return false;
+  const int rows = 128 / W;                   // image rows per tile
+  if (rows <= H) { if (H % rows) return false; hb = rows; nb = 1; }
+  else { if (rows % H) return false; hb = H; nb = rows / H; }
+  return true;
+}
+}  // namespace
+
+// 3x3 / stride 1 / pad 1 convolution, NHWC bf16:  y[N,H,W,Co] (row stride ldy) = conv(x[N,H,W,Ci] (pixel stride ldx), w[Co][3][3][Ci]).
+// dgrad != 0 computes the data gradient instead: x := dY [N,H,W,Co], output := dX [N,H,W,Ci], same weight tensor.
+// stats (optional, forward only): per-(sample, out-channel) (sum, sumsq) table, needs (H*W) % 32 == 0; pre-zeroed.
+DLB_API int dlb_conv3x3_tc(int dgrad, const void* x, long long ldx, const void* w, void* y, long long ldy, int N, int H, int W, int Ci,
+                           int Co, float* stats, long long stats_ns, int sm_limit, void* stream) {
+  const int Cin = dgrad ? Co : Ci;            // channels of the tensor being convolved
+  const int Cout = dgrad ? Ci : Co;           // channels produced
+  int hb, nb;
+  if (!conv_tile_geometry(N, H, W, hb, nb)) return -7;
+  if ((Cin % 8) || (Cout % 8) || (ldx % 8) || (ldy % 8) || ((uintptr_t)x & 15) || ((uintptr_t)w & 15) || ((uintptr_t)y & 15)) return -3;
+  if (stats && ((H * W) % 32)) return -4;
+  const int M = N * H * W;
+  int sms = sm_count_cached();
+  if (sm_limit > 0 && sm_limit < sms) sms = sm_limit;
+  CUtensorMap ta, tb, td;
+  {
+    long long dims[4] = {Cin, W, H, N};
+    long long strides[4] = {1, ldx, (long long)W * ldx, (long long)H * W * ldx};
+    int box[4] = {64, W, hb, nb};
+    int rc = make_map_nd(&ta, x, 4, dims, strides, box);
+    if (rc) return rc - 10;
+  }
+  int bn;
+  if (!dgrad) {
+    bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256));
+    int rc = make_map(&tb, w, Cout, 9LL * Cin, 9LL * Cin, bn);          // [Co][9*Ci], K-major
+    if (rc) return rc - 20;
+  } else {
+    bn = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
+    long long dims[3] = {Ci, 9, Co};                                     // w[co][tap][ci]: {ci (n, contiguous), tap, co (k rows)}
+    long long strides[3] = {1, Ci, 9LL * Ci};
+    int box[3] = {64, 1, 64};
+    int rc = make_map_nd(&tb, w, 3, dims, strides, box);
+    if (rc) return rc - 20;
+  }
+  int rc = make_map(&td, y, M, Cout, ldy, 32);
+  if (rc) return rc - 30;
+  GemmParams p;
+  p.M = M; p.N = Cout; p.K = 9 * Cin; p.d = y; p.ldd = ldy; p.accumulate_out = 0;
+  p.pro_a = nullptr; p.pro_b = nullptr; p.pro_ld = 0; p.rows_per_sample = H * W; p.stats = stats; p.stats_ns = stats_ns;
+  p.conv_H = H; p.conv_W = W; p.conv_C = Cin; p.conv_kchunks = (Cin + 63) / 64; p.conv_sign = dgrad ? -1 : 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dgrad) {
+    if (bn == 64) return launch<64, false, false, true, true>(ta, tb, td, p, sms, st);
+    if (bn == 128) return launch<128, false, false, true, true>(ta, tb, td, p, sms, st);
+    return launch<256, false, false, true, true>(ta, tb, td, p, sms, st);
+  }
+  if (stats) {
+    if (bn == 32) return launch<32, false, true, false, true>(ta, tb, td, p, sms, st);
+    if (bn == 64) return launch<64, false, true, false, true>(ta, tb, td, p, sms, st);
+    if (bn == 128) return launch<128, false, true, false, true>(ta, tb, td, p, sms, st);
+    return launch<256, false, true, false, true>(ta, tb, td, p, sms, st);
+  }
+  if (bn == 32) return launch<32, false, false, false, true>(ta, tb, td, p, sms, st);
+  if (bn == 64) return launch<64, false, false, false, true>(ta, tb, td, p, sms, st);
+  if (bn == 128) return launch<128, false, false, false, true>(ta, tb, td, p, sms, st);
+  return launch<256, false, false, false, true>(ta, tb, td, p, sms, st);
 }

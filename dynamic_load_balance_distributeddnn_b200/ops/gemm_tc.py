@@ -22,6 +22,7 @@ def _lib():
         vp, i64, i32 = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
         nat.declare("dlb_gemm_tc", i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, i32, vp, i64, i32, vp])
         nat.declare("dlb_gemm_tc_bmn", i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp])
+        nat.declare("dlb_conv3x3_tc", i32, [i32, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, vp, i64, i32, vp])
         nat.declare("dlb_wgrad_tc", i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, i32, i32, vp])
         _DECLARED = True
     return lib
@@ -89,6 +90,61 @@ def wgrad(dy: torch.Tensor, x: torch.Tensor, pro_a=None, pro_b=None, rows_per_sa
     return dw
 
 
+def conv3x3_geometry_ok(h: int, w: int) -> bool:
+    if w <= 0 or 128 % w:
+        return False
+    rows = 128 // w
+    return (h % rows == 0) if rows <= h else (rows % h == 0)
+
+
+def conv3x3_raw(dgrad: bool, x_ptr: int, ldx: int, w_ptr: int, y_ptr: int, ldy: int, n: int, h: int, w: int, ci: int, co: int,
+                device, stats_ptr: int = 0, stats_ns: int = 0, sm_limit: int = 0) -> None:
+    """3x3/s1/p1 NHWC conv on tcgen05: forward (x[N,H,W,ci] -> y[N,H,W,co]) or data gradient (x := dY[..,co] -> y := dX[..,ci]).
+    Weight memory must be [co][3][3][ci] (channels-last OIHW).  ldx / ldy are pixel strides in elements."""
+    rc = _lib().dlb_conv3x3_tc(int(dgrad), x_ptr, ldx, w_ptr, y_ptr, ldy, n, h, w, ci, co, stats_ptr, stats_ns, sm_limit,
+                               nat.stream_ptr(device))
+    nat.check(rc, "conv3x3_tc")
+
+
+def _w_ohwi(weight: torch.Tensor) -> torch.Tensor:
+    """weight [O,I,3,3] -> tensor whose memory is [O][3][3][I] (no copy when already channels-last)."""
+    return weight if weight.is_contiguous(memory_format=torch.channels_last) else weight.contiguous(memory_format=torch.channels_last)
+
+
+class _Conv3x3Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight):
+        xv, n, hw, c, ld = _nhwc_view(x)
+        o = weight.shape[0]
+        h, w = x.shape[2], x.shape[3]
+        wk = _w_ohwi(weight)
+        y = torch.empty((n, o, h, w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        conv3x3_raw(False, xv.data_ptr(), ld, wk.data_ptr(), y.data_ptr(), o, n, h, w, c, o, x.device)
+        ctx.save_for_backward(xv, weight)
+        ctx.cfg = (n, h, w, c, ld, o)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xv, weight = ctx.saved_tensors
+        n, h, w, c, ld, o = ctx.cfg
+        dyv, _, _, _, lddy = _nhwc_view(dy)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            wk = _w_ohwi(weight)
+            dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
+            conv3x3_raw(True, dyv.data_ptr(), lddy, wk.data_ptr(), dx.data_ptr(), c, n, h, w, c, o, dy.device)
+        if ctx.needs_input_grad[1]:
+            # weight gradient of the 3x3: vendor kernel (a 9-tap MN-major split-K tcgen05 variant is future work)
+            x4 = torch.as_strided(xv, (n, c, h, w), (h * w * ld, 1, w * ld, ld))
+            _, dw, _ = torch.ops.aten.convolution_backward(dyv if dyv.is_contiguous(memory_format=torch.channels_last) else
+                                                           dyv.contiguous(memory_format=torch.channels_last),
+                                                           x4 if ld == c else x4.contiguous(memory_format=torch.channels_last),
+                                                           weight, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
+                                                           [False, True, False])
+        return dx, dw
+
+
 def _w2d(weight: torch.Tensor) -> torch.Tensor:
     """[O, I, 1, 1] (any layout) -> contiguous-row [O, I] view."""
     o, i = weight.shape[0], weight.shape[1]
@@ -130,6 +186,10 @@ class _Conv1x1Fn(torch.autograd.Function):
 def conv_supported(x, weight, stride, padding, groups) -> bool:
     if not available():
         return False
+    if (weight.dim() == 4 and weight.shape[2] == 3 and weight.shape[3] == 3 and stride == 1 and padding == 1 and groups == 1
+            and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and x.dim() == 4):
+        return (x.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0 and conv3x3_geometry_ok(x.shape[2], x.shape[3])
+                and hasattr(nat.get(), "dlb_conv3x3_tc") and x.shape[0] * x.shape[2] * x.shape[3] >= 128)
     return (x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and x.dim() == 4 and groups == 1
             and stride == 1 and padding == 0 and weight.shape[2] == 1 and weight.shape[3] == 1
             and x.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0 and x.shape[0] * x.shape[2] * x.shape[3] >= 128)
@@ -185,7 +245,7 @@ def linear(x, weight, bias=None):
 
 
 def conv2d(x, weight, bias, stride, padding):
-    y = _Conv1x1Fn.apply(x, weight)
+    y = _Conv3x3Fn.apply(x, weight) if weight.shape[2] == 3 else _Conv1x1Fn.apply(x, weight)
     if bias is not None:
         y = y + bias.to(y.dtype).view(1, -1, 1, 1)
     return y

@@ -155,3 +155,42 @@ def test_linear_autograd_on_tcgen05(g):
     assert (y.float() - yr).abs().max().item() < 3e-2 * yr.abs().max().item()
     assert (x.grad.float() - xr.grad).abs().max().item() < 3e-2 * xr.grad.abs().max().item()
     assert (w.grad.float() - wr.grad).abs().max().item() < 3e-2 * wr.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("n,c,o,hw", [(8, 128, 32, 32), (6, 128, 32, 16), (9, 128, 32, 8), (21, 128, 32, 4), (4, 64, 64, 32),
+                                        (5, 96, 160, 16), (3, 256, 256, 8)])
+def test_conv3x3_tcgen05_fwd_dgrad(g, n, c, o, hw):
+    """implicit-GEMM 3x3 (4-D TMA boxes shifted per tap, zero padding from TMA OOB fill) vs F.conv2d"""
+    torch.manual_seed(n + c + o)
+    x = torch.randn(n, c, hw, hw, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    w = (torch.randn(o, c, 3, 3, device="cuda") / (3 * c ** 0.5)).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    assert g.conv_supported(x, w, 1, 1, 1)
+    y = g.conv2d(x, w, None, 1, 1)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xr, wr = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+    yr = torch.nn.functional.conv2d(xr, wr, padding=1)
+    yr.backward(gy.float())
+    assert (y.float() - yr).abs().max().item() < 3e-2 * max(1.0, yr.abs().max().item())
+    assert (x.grad.float() - xr.grad).abs().max().item() < 3e-2 * max(1.0, xr.grad.abs().max().item())
+    assert (w.grad.float() - wr.grad).abs().max().item() < 5e-2 * max(1.0, wr.grad.abs().max().item())
+
+
+def test_conv3x3_strided_io_and_stats(g):
+    """input read from / output written into channel slices of wider buffers, with the GN-statistics epilogue"""
+    torch.manual_seed(11)
+    n, c, o, hw = 6, 128, 32, 16
+    xin = torch.randn(n, hw, hw, 192, device="cuda").bfloat16()
+    x = xin[..., 32:160]
+    w = (torch.randn(o, 3, 3, c, device="cuda") / 34).bfloat16()                  # [O][3][3][I] memory
+    out = torch.zeros(n, hw, hw, 96, device="cuda", dtype=torch.bfloat16)
+    table = torch.zeros(n, 96, 2, device="cuda")
+    g.conv3x3_raw(False, x.data_ptr(), 192, w.data_ptr(), out[..., 16:48].data_ptr(), 96, n, hw, hw, c, o, x.device,
+                  table[:, 16:48].data_ptr(), 2 * 96)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1)
+    got = out[..., 16:48].float()
+    assert (got - ref).abs().max().item() < 3e-2 * ref.abs().max().item()
+    assert out[..., :16].abs().sum().item() == 0 and out[..., 48:].abs().sum().item() == 0
+    assert torch.allclose(table[:, 16:48, 0], got.sum((1, 2)), atol=5e-2, rtol=5e-3)
+    assert torch.allclose(table[:, 16:48, 1], (got * got).sum((1, 2)), atol=5e-2, rtol=5e-3)
