@@ -303,20 +303,49 @@ DLB_API int dlb_attention_bwd(int dtype, const void* qkv, const void* dout, cons
 // one read and one write of the [T, V] matrix (reference: log_softmax + nll_loss + their backward kernels =
 // ~5 passes over a 2.4 GB fp32 matrix; Net/Transformer.py:94-95, dbs.py:270-271).
 namespace {
-template <typename T>
+// VEC: the row stride `ld` is a multiple of the 16-byte vector width and rows are 16-byte aligned, so the row is
+// streamed with 16-byte loads/stores, several in flight per thread.  Columns in [V, ld) are padding: they are
+// excluded from the softmax and get a zero gradient.
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) softmax_ce_inplace_kernel(T* __restrict__ logits, int64_t ld, const float* __restrict__ bias,
                                                                  const long long* __restrict__ target, float* __restrict__ loss_sum,
                                                                  int V, float scale) {
-  extern __shared__ float row[];            // [V] fp32
+  extern __shared__ float row[];            // [V rounded up to the vector width] fp32
   __shared__ float red[8];
   __shared__ float bc[2];
+  constexpr int W = 16 / sizeof(T);
   const int r = blockIdx.x;
   T* p = logits + (int64_t)r * ld;
   float m = -INFINITY;
-  for (int i = threadIdx.x; i < V; i += 256) {
-    const float z = (float)p[i] + (bias ? bias[i] : 0.f);
-    row[i] = z;
-    m = fmaxf(m, z);
+  if constexpr (VEC) {
+    const int nvec = (V + W - 1) / W;
+    for (int v0 = threadIdx.x; v0 < nvec; v0 += 256 * 4) {
+      float x[4][W];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int v = v0 + u * 256;
+        if (v < nvec) load_vec<T, W>(p + (int64_t)v * W, x[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int v = v0 + u * 256;
+        if (v < nvec) {
+#pragma unroll
+          for (int k = 0; k < W; ++k) {
+            const int i = v * W + k;
+            const float z = i < V ? x[u][k] + (bias ? bias[i] : 0.f) : -INFINITY;
+            row[i] = z;
+            m = fmaxf(m, z);
+          }
+        }
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < V; i += 256) {
+      const float z = (float)p[i] + (bias ? bias[i] : 0.f);
+      row[i] = z;
+      m = fmaxf(m, z);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -346,30 +375,44 @@ __global__ void __launch_bounds__(256) softmax_ce_inplace_kernel(T* __restrict__
   s = bc[1];
   const float inv = 1.f / s;
   const int t = (int)target[r];
-  if (threadIdx.x == 0) {
-    // loss_r = log(sum) + m - z_t, with z_t = log(row[t]) + m  ->  log(sum) - log(e_t)
-    atomicAdd(loss_sum, (__logf(s) - __logf(fmaxf(row[t], 1e-38f))) * scale);
-  }
-  for (int i = threadIdx.x; i < V; i += 256) {
-    float g = row[i] * inv;
-    if (i == t) g -= 1.f;
-    p[i] = (T)(g * scale);
+  if (threadIdx.x == 0) atomicAdd(loss_sum, (__logf(s) - __logf(fmaxf(row[t], 1e-38f))) * scale);
+  if constexpr (VEC) {
+    const int nvec = (int)(ld / W);
+    for (int v = threadIdx.x; v < nvec; v += 256) {
+      float g[W];
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        const int i = v * W + k;
+        float gi = i < V ? row[i] * inv : 0.f;
+        if (i == t) gi -= 1.f;
+        g[k] = gi * scale;
+      }
+      store_vec<T, W>(p + (int64_t)v * W, g);
+    }
+  } else {
+    for (int i = threadIdx.x; i < V; i += 256) {
+      float g = row[i] * inv;
+      if (i == t) g -= 1.f;
+      p[i] = (T)(g * scale);
+    }
   }
 }
 }  // namespace
 
 DLB_API int dlb_softmax_ce_inplace(int dtype, void* logits, long long ld, const float* bias, const long long* target, float* loss_sum,
                                    int T_rows, int V, float scale, void* stream) {
-  const size_t smb = (size_t)V * sizeof(float);
+  const size_t smb = (size_t)(V + 8) * sizeof(float);
   if (smb > 200 * 1024) return -2;
-  if (dtype == DLB_BF16) {
-    auto kern = softmax_ce_inplace_kernel<__nv_bfloat16>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
-    kern<<<T_rows, 256, smb, (cudaStream_t)stream>>>((__nv_bfloat16*)logits, ld, bias, target, loss_sum, V, scale);
-  } else {
-    auto kern = softmax_ce_inplace_kernel<float>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
-    kern<<<T_rows, 256, smb, (cudaStream_t)stream>>>((float*)logits, ld, bias, target, loss_sum, V, scale);
-  }
+  const int W = dtype == DLB_BF16 ? 8 : 4;
+  const bool vec = (ld % W == 0) && (((uintptr_t)logits & 15) == 0) && ld >= (long long)((V + W - 1) / W) * W;
+#define GO(TT, VV)                                                                                         \
+  do {                                                                                                     \
+    auto kern = softmax_ce_inplace_kernel<TT, VV>;                                                         \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);                     \
+    kern<<<T_rows, 256, smb, (cudaStream_t)stream>>>((TT*)logits, ld, bias, target, loss_sum, V, scale);   \
+  } while (0)
+  if (dtype == DLB_BF16) { if (vec) GO(__nv_bfloat16, true); else GO(__nv_bfloat16, false); }
+  else { if (vec) GO(float, true); else GO(float, false); }
+#undef GO
   return dlb_post_launch();
 }

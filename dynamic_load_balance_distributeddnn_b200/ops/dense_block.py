@@ -29,6 +29,7 @@ from .norm import _nhwc_view
 _CONV_BWD = torch.ops.aten.convolution_backward
 _SIDE = {}
 _USE_SIDE = os.environ.get("DLB_SIDE_STREAM", "1") == "1"
+_USE_CONV3 = os.environ.get("DLB_TC_CONV3", "1") == "1"
 
 
 def _side_stream(device) -> torch.cuda.Stream:
@@ -108,6 +109,7 @@ class _DenseBlockFn(torch.autograd.Function):
         copy_in_with_stats(x, ct - c0, c0)
         saved = []
         fused = x.dtype == torch.bfloat16 and gemm_tc.available() and (n * hw) >= 128
+        conv3_ok = fused and gemm_tc.conv3x3_profitable(h, w) and _USE_CONV3 and hasattr(nat.get(), "dlb_conv3x3_tc")
         for l in range(n_layers):
             g1w, g1b, w1, g2w, g2b, w2 = params[6 * l:6 * l + 6]
             cl = c0 + l * g
@@ -155,8 +157,20 @@ class _DenseBlockFn(torch.autograd.Function):
                 nat.check(lib.dlb_gn_forward(dt, yv.data_ptr(), ldy, 0, 0, yhat.data_ptr(), cm, g2w.data_ptr(), g2b.data_ptr(),
                                              mean2.data_ptr(), rstd2.data_ptr(), t2.data_ptr(), n, hw, cm, groups, eps, 1, 0, st),
                           "dense.gn2")
-            new = _conv_fwd(yhat, w2, 1)
-            copy_in_with_stats(new, off - g, g)
+            if fused and conv3_ok and w2.dtype == torch.bfloat16:
+                # 3x3 conv on the tcgen05 implicit-GEMM kernel: its TMA-store epilogue writes the g new channels
+                # straight into their slice of the block buffer and (when H*W % 32 == 0) accumulates their
+                # GroupNorm statistics -- no staging tensor, no copy, no separate statistics pass
+                w2k = gemm_tc._w_ohwi(w2)
+                epi2 = hw % 32 == 0
+                gemm_tc.conv3x3_raw(False, yhat.data_ptr(), cm, w2k.data_ptr(), slice_ptr(off - g), ct, n, h, w, cm, g, x.device,
+                                    (table.data_ptr() + (off - g) * 8) if epi2 else 0, tns)
+                if not epi2:
+                    nat.check(lib.dlb_nc_reduce2(0, dt, slice_ptr(off - g), ct, 0, 0, 0, 0, table.data_ptr() + (off - g) * 8, tns,
+                                                 n, hw, g, st), "dense.new_stats")
+            else:
+                new = _conv_fwd(yhat, w2, 1)
+                copy_in_with_stats(new, off - g, g)
             empty = mean1.new_empty(0)
             saved += [xhat if xhat is not None else empty, yv, yhat, mean1, rstd1, mean2, rstd2,
                       coefs[0] if coefs else empty, coefs[1] if coefs else empty]
@@ -196,6 +210,8 @@ class _DenseBlockFn(torch.autograd.Function):
         dw1_views = [None] * n_layers
         main = torch.cuda.current_stream(buf.device)
         side = _side_stream(buf.device) if (_USE_SIDE and buf.dtype == torch.bfloat16) else None
+        conv3_ok = (buf.dtype == torch.bfloat16 and gemm_tc.available() and gemm_tc.conv3x3_profitable(h, w) and _USE_CONV3
+                    and hasattr(nat.get(), "dlb_conv3x3_tc") and n * h * w >= 128)
         for l in reversed(range(n_layers)):
             g1w, g1b, w1, g2w, g2b, w2 = params[6 * l:6 * l + 6]
             xhat, y, yhat, mean1, rstd1, mean2, rstd2, ca, cb = saved[9 * l:9 * l + 9]
@@ -212,7 +228,13 @@ class _DenseBlockFn(torch.autograd.Function):
                 side.wait_event(ev_in)
                 with torch.cuda.stream(side):
                     _, dw2, _ = _CONV_BWD(dnew, yhat, w2c, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [False, True, False])
-                dyhat, _, _ = _CONV_BWD(dnew, yhat, w2c, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [True, False, False])
+                if conv3_ok and w2.dtype == torch.bfloat16:
+                    # data gradient on the tcgen05 3x3 kernel, reading dY in place from the gradient-buffer slice
+                    dyhat = torch.empty((n, cm, h, w), dtype=buf.dtype, device=buf.device, memory_format=torch.channels_last)
+                    gemm_tc.conv3x3_raw(True, dbuf.data_ptr() + (off - g) * esz, ct, gemm_tc._w_ohwi(w2).data_ptr(), dyhat.data_ptr(),
+                                        cm, n, h, w, cm, g, buf.device)
+                else:
+                    dyhat, _, _ = _CONV_BWD(dnew, yhat, w2c, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [True, False, False])
             else:
                 dyhat, dw2, _ = _CONV_BWD(dnew, yhat, w2c, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [True, True, False])
             dyhat = dyhat.contiguous(memory_format=torch.channels_last)

@@ -90,11 +90,21 @@ def wgrad(dy: torch.Tensor, x: torch.Tensor, pro_a=None, pro_b=None, rows_per_sa
     return dw
 
 
+CONV3_MAX_HW = int(os.environ.get("DLB_TC_CONV3_MAX_HW", "64"))
+
+
 def conv3x3_geometry_ok(h: int, w: int) -> bool:
     if w <= 0 or 128 % w:
         return False
     rows = 128 // w
     return (h % rows == 0) if rows <= h else (rows % h == 0)
+
+
+def conv3x3_profitable(h: int, w: int) -> bool:
+    """Measured on B200 (tools/bench_gemm.py, 128->32 channels): the tap-by-tap implicit GEMM re-reads its input tile
+    nine times from L2, which the vendor kernel avoids; it wins or ties at 8x8 / 4x4 feature maps and loses 1.3-1.9x
+    at 16x16 / 32x32.  Dispatch accordingly (override with DLB_TC_CONV3_MAX_HW)."""
+    return conv3x3_geometry_ok(h, w) and h * w <= CONV3_MAX_HW
 
 
 def conv3x3_raw(dgrad: bool, x_ptr: int, ldx: int, w_ptr: int, y_ptr: int, ldy: int, n: int, h: int, w: int, ci: int, co: int,
@@ -188,7 +198,7 @@ def conv_supported(x, weight, stride, padding, groups) -> bool:
         return False
     if (weight.dim() == 4 and weight.shape[2] == 3 and weight.shape[3] == 3 and stride == 1 and padding == 1 and groups == 1
             and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and x.dim() == 4):
-        return (x.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0 and conv3x3_geometry_ok(x.shape[2], x.shape[3])
+        return (x.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0 and conv3x3_profitable(x.shape[2], x.shape[3])
                 and hasattr(nat.get(), "dlb_conv3x3_tc") and x.shape[0] * x.shape[2] * x.shape[3] >= 128)
     return (x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and x.dim() == 4 and groups == 1
             and stride == 1 and padding == 0 and weight.shape[2] == 1 and weight.shape[3] == 1

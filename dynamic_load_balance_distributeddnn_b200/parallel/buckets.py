@@ -57,7 +57,14 @@ class FlatState:
         off = 0
         for p in self.params:
             self.offsets.append(off)
-            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+            n_alloc = p.numel()
+            if p.dim() == 2 and p.shape[0] % 8 != 0:
+                # reserve zero rows up to a multiple of 8 behind the matrix (e.g. the 33 278-row vocabulary projection):
+                # kernels may then treat it as an aligned [rows_pad, cols] operand; the pad rows receive zero gradients
+                rows_pad = (p.shape[0] + 7) // 8 * 8
+                n_alloc = rows_pad * p.shape[1]
+                p._dlb_padded_rows = rows_pad
+            off += (n_alloc + _ALIGN - 1) // _ALIGN * _ALIGN
         world = max(1, comm.world)
         pad_to = _ALIGN * world
         self.numel = (off + pad_to - 1) // pad_to * pad_to

@@ -53,3 +53,17 @@ for (ns, hw, n, k) in fshapes:
     t6 = timeit(lambda: torch.matmul(dy.t(), a))
     print(f"N={ns} HW={hw} Cout={n} Cin={k}: plain {t0*1e3:6.1f}  +pro {t1*1e3:6.1f}  +pro+stats {t2*1e3:6.1f}  +stats {t3*1e3:6.1f} us "
           f"(fwd bytes {byts/1e6:.0f} MB -> {byts/t2/1e6:5.0f} GB/s fused) | wgrad {t4*1e3:6.1f}  +pro {t5*1e3:6.1f}  cuBLAS {t6*1e3:6.1f} us", flush=True)
+
+# ---- tcgen05 implicit-GEMM 3x3 (DenseNet 128 -> 32 bottleneck conv) vs the vendor library ----
+print("-- conv3x3 128->32")
+import torch.nn.functional as F
+for (n, hw) in ([(512, 32), (512, 16), (512, 8), (512, 4), (64, 32), (64, 16)] if not quick else [(512, 32)]):
+    x = torch.randn(n, 128, hw, hw, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(32, 128, 3, 3, device="cuda") / 34).bfloat16().contiguous(memory_format=torch.channels_last)
+    y = torch.empty(n, 32, hw, hw, device="cuda", dtype=torch.bfloat16, memory_format=torch.channels_last)
+    dy = torch.randn_like(y); dx = torch.empty_like(x)
+    t1 = timeit(lambda: gemm_tc.conv3x3_raw(False, x.data_ptr(), 128, w.data_ptr(), y.data_ptr(), 32, n, hw, hw, 128, 32, x.device))
+    t2 = timeit(lambda: F.conv2d(x, w, padding=1))
+    t3 = timeit(lambda: gemm_tc.conv3x3_raw(True, dy.data_ptr(), 32, w.data_ptr(), dx.data_ptr(), 128, n, hw, hw, 128, 32, x.device))
+    t4 = timeit(lambda: torch.ops.aten.convolution_backward(dy, x, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [True, False, False]))
+    print(f"N={n} {hw}x{hw}: fwd tcgen05 {t1*1e3:6.1f} us vs cuDNN {t2*1e3:6.1f} | dgrad tcgen05 {t3*1e3:6.1f} us vs cuDNN {t4*1e3:6.1f}", flush=True)
