@@ -136,13 +136,16 @@ class _DenseBlockFn(torch.autograd.Function):
                                  x.device, ca, cb, hw, t2 if epi else None, 0, 2 * cm)
                 if not epi:
                     nat.check(lib.dlb_nc_reduce2(0, dt, yv.data_ptr(), cm, 0, 0, 0, 0, t2.data_ptr(), 0, n, hw, cm, st), "dense.y_stats")
-                nat.check(lib.dlb_gn_finalize(t2.data_ptr(), 2 * cm, mean2.data_ptr(), rstd2.data_ptr(), n, cm, groups, hw, eps, st),
-                          "dense.fin2")
+                kpad2 = (cm + 63) // 64 * 64
+                ca2 = torch.empty((n, kpad2), dtype=torch.float32, device=x.device)
+                cb2 = torch.empty((n, kpad2), dtype=torch.float32, device=x.device)
+                nat.check(lib.dlb_gn_coeff(t2.data_ptr(), 2 * cm, g2w.data_ptr(), g2b.data_ptr(), mean2.data_ptr(), rstd2.data_ptr(),
+                                           ca2.data_ptr(), cb2.data_ptr(), kpad2, n, cm, groups, hw, eps, st), "dense.coeff2")
                 yhat = torch.empty_like(yv, memory_format=torch.channels_last)
                 nat.check(lib.dlb_gn_fwd_apply(dt, yv.data_ptr(), cm, 0, 0, yhat.data_ptr(), cm, g2w.data_ptr(), g2b.data_ptr(),
                                                mean2.data_ptr(), rstd2.data_ptr(), n, hw, cm, groups, 1, st), "dense.apply2")
                 xhat = None
-                coefs = (ca, cb)
+                coefs = (ca, cb, ca2, cb2)
             else:
                 nat.check(lib.dlb_gn_finalize(table.data_ptr() + off * 8, tns, mean1.data_ptr(), rstd1.data_ptr(), n, cl, groups,
                                               hw, eps, st), "dense.fin1")
@@ -173,7 +176,8 @@ class _DenseBlockFn(torch.autograd.Function):
                 copy_in_with_stats(new, off - g, g)
             empty = mean1.new_empty(0)
             saved += [xhat if xhat is not None else empty, yv, yhat, mean1, rstd1, mean2, rstd2,
-                      coefs[0] if coefs else empty, coefs[1] if coefs else empty]
+                      coefs[0] if coefs else empty, coefs[1] if coefs else empty,
+                      coefs[2] if coefs else empty, coefs[3] if coefs else empty]
         lib.dlb_norm_skip_zero(0)
         ctx.save_for_backward(buf, *params, *saved)
         ctx.cfg = (n_layers, n, c0, h, w, g, ct, groups, eps)
@@ -214,7 +218,7 @@ class _DenseBlockFn(torch.autograd.Function):
                     and hasattr(nat.get(), "dlb_conv3x3_tc") and n * h * w >= 128)
         for l in reversed(range(n_layers)):
             g1w, g1b, w1, g2w, g2b, w2 = params[6 * l:6 * l + 6]
-            xhat, y, yhat, mean1, rstd1, mean2, rstd2, ca, cb = saved[9 * l:9 * l + 9]
+            xhat, y, yhat, mean1, rstd1, mean2, rstd2, ca, cb, ca2, cb2 = saved[11 * l:11 * l + 11]
             cl = c0 + l * g
             off = ct - cl
             cm = y.shape[1]
@@ -247,9 +251,19 @@ class _DenseBlockFn(torch.autograd.Function):
             t1 = arena[o:o + sizes[l][3]]; o += sizes[l][3]
             dg1 = arena[o:o + cl]; o += cl
             db1 = arena[o:o + cl]
-            nat.check(lib.dlb_gn_backward(dt, y.data_ptr(), cm, dyhat.data_ptr(), cm, yhat.data_ptr(), cm, dy.data_ptr(), cm,
-                                          0, 0, g2w.data_ptr(), mean2.data_ptr(), rstd2.data_ptr(), t2.data_ptr(),
-                                          dg2.data_ptr(), db2.data_ptr(), n, hw, cm, groups, 1, 0, st), "dense.gn2_bwd")
+            if ca2.numel() > 0:
+                # ReLU mask recomputed from the forward's affine coefficients: yhat is not re-read by the GN2 backward
+                kp2 = ca2.shape[1]
+                nat.check(lib.dlb_nc_reduce2_bwd_coef(dt, y.data_ptr(), cm, dyhat.data_ptr(), cm, t2.data_ptr(), 0, mean2.data_ptr(),
+                                                      rstd2.data_ptr(), dg2.data_ptr(), db2.data_ptr(), ca2.data_ptr(), cb2.data_ptr(),
+                                                      kp2, n, hw, cm, groups, st), "dense.gn2_red")
+                nat.check(lib.dlb_gn_bwd_apply_coef(dt, y.data_ptr(), cm, dyhat.data_ptr(), cm, dy.data_ptr(), cm, g2w.data_ptr(),
+                                                    mean2.data_ptr(), rstd2.data_ptr(), t2.data_ptr(), 0, ca2.data_ptr(), cb2.data_ptr(),
+                                                    kp2, n, hw, cm, groups, 0, st), "dense.gn2_app")
+            else:
+                nat.check(lib.dlb_gn_backward(dt, y.data_ptr(), cm, dyhat.data_ptr(), cm, yhat.data_ptr(), cm, dy.data_ptr(), cm,
+                                              0, 0, g2w.data_ptr(), mean2.data_ptr(), rstd2.data_ptr(), t2.data_ptr(),
+                                              dg2.data_ptr(), db2.data_ptr(), n, hw, cm, groups, 1, 0, st), "dense.gn2_bwd")
             xs = buf.data_ptr() + off * esz
             dxs = dbuf.data_ptr() + off * esz
             if xhat.numel() == 0:
