@@ -10,6 +10,25 @@
 enum DlbDtype : int { DLB_F32 = 0, DLB_BF16 = 1 };
 
 extern unsigned long long g_dlb_launches;   // host-side count of kernels launched by this library
+extern int g_dlb_pdl;                        // programmatic dependent launch on/off (optim.cu; DLB_PDL env / dlb_set_pdl)
+
+// Programmatic dependent launch: with the attribute set, a kernel may be scheduled while its predecessor in the
+// stream is still draining; it must not touch the predecessor's outputs before `dlb_pdl_wait()`.  Every kernel of
+// this library calls dlb_pdl_wait() first thing, so only the launch latency / block scheduling is overlapped --
+// which is what bounds the step at small per-rank batches (~1 700 graph nodes of a few microseconds each).
+__device__ __forceinline__ void dlb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t dlb_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_dlb_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 static inline int dlb_post_launch(int n = 1) {
   g_dlb_launches += (unsigned long long)n;
   return (int)cudaPeekAtLastError();

@@ -220,6 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  dlb_pdl_wait();            // everything above (smem carve-up, mbarrier init, TMEM alloc) overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -545,6 +546,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  dlb_pdl_wait();            // everything above (smem carve-up, mbarrier init, TMEM alloc) overlapped the previous kernel's tail
 
   // unit u -> (split, co tile, ci tile); splits vary fastest so neighbouring CTAs stream disjoint pixel ranges
   auto decode = [&](int u, int& sp, int& co0, int& ci0) {
@@ -784,7 +786,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
   }
   const int num_tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   const int grid = num_tiles < sms ? num_tiles : sms;
-  kern<<<grid, PRO ? 512 : 256, C::kSmemBytes, st>>>(ta, tb, td, p);
+  dlb_launch(kern, dim3(grid), dim3(PRO ? 512 : 256), (size_t)C::kSmemBytes, st, ta, tb, td, p);
   return dlb_post_launch();
 }
 
@@ -891,7 +893,7 @@ int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const WgradParam
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  kern<<<grid, PRO ? 512 : 256, C::kSmemBytes, st>>>(tdy, tx, p);
+  dlb_launch(kern, dim3(grid), dim3(PRO ? 512 : 256), (size_t)C::kSmemBytes, st, tdy, tx, p);
   return dlb_post_launch();
 }
 }  // namespace

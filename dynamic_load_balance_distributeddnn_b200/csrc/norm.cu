@@ -36,6 +36,7 @@ nc_reduce2_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy
                   const float* __restrict__ rstd, int G, float* __restrict__ dgamma, float* __restrict__ dbeta,
                   const float* __restrict__ coef_a, const float* __restrict__ coef_b, int64_t coef_ld,
                   T* __restrict__ copy_dst, int64_t ldc) {
+  dlb_pdl_wait();
   extern __shared__ float smem[];            // [2*C]
   const int n = blockIdx.y;
   const int lanes = C / V;                   // channel-vector lanes
@@ -133,6 +134,7 @@ nc_reduce2_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy
 // group statistics from the table:  mean/rstd [N][G]
 __global__ void gn_finalize_kernel(const float* __restrict__ table, int64_t table_ns, float* __restrict__ mean,
                                    float* __restrict__ rstd, int N, int C, int G, int HW, float eps) {
+  dlb_pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * G) return;
   const int n = idx / G, g = idx % G, cpg = C / G;
@@ -151,6 +153,7 @@ __global__ void gn_finalize_kernel(const float* __restrict__ table, int64_t tabl
 __global__ void gn_coeff_kernel(const float* __restrict__ table, int64_t table_ns, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float* __restrict__ mean, float* __restrict__ rstd,
                                 float* __restrict__ ca, float* __restrict__ cb, int64_t ld, int C, int G, int HW, float eps) {
+  dlb_pdl_wait();
   extern __shared__ float sm[];              // mu[G], rs[G]
   const int n = blockIdx.x, cpg = C / G;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
@@ -180,6 +183,7 @@ gn_fwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
                     T* __restrict__ y, int64_t ldy, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ mean,
                     const float* __restrict__ rstd, int HW, int C, int G, int rows_per_block) {
+  dlb_pdl_wait();
   extern __shared__ float smem[];            // a[C], b[C]
   float* sa = smem;
   float* sb = smem + C;
@@ -268,6 +272,7 @@ gn_bwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
                     const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ table, int64_t table_ns, int HW, int C, int G, int rows_per_block,
                     const float* __restrict__ coef_a, const float* __restrict__ coef_b, int64_t coef_ld) {
+  dlb_pdl_wait();
   extern __shared__ float smem[];            // k1[C], k2[C], k3[C], s1[G], s2[G]
   float* k1 = smem;
   float* k2 = smem + C;
@@ -431,10 +436,10 @@ int reduce2_launch(int mode, const void* x, int64_t ldx, const void* dy, int64_t
   grid_for(N, HW, C, V, grid, rpb);
   const size_t sm = 2 * C * sizeof(float);
   const T* X = (const T*)x; const T* DY = (const T*)dy; const T* Y = (const T*)y;
-  if (mode == 0) nc_reduce2_kernel<T, V, 0><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, cld, (T*)copy_dst, ldc);
-  else if (mode == 1) nc_reduce2_kernel<T, V, 1><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, cld, (T*)copy_dst, ldc);
-  else if (mode == 3) nc_reduce2_kernel<T, V, 3><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, cld, (T*)copy_dst, ldc);
-  else nc_reduce2_kernel<T, V, 2><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, table, table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, cld, (T*)copy_dst, ldc);
+  if (mode == 0) dlb_launch(nc_reduce2_kernel<T, V, 0>, grid, dim3(kThreads), sm, st, X, (int64_t)ldx, DY, (int64_t)lddy, Y, (int64_t)ldy, table, (int64_t)table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, (int64_t)cld, (T*)copy_dst, (int64_t)ldc);
+  else if (mode == 1) dlb_launch(nc_reduce2_kernel<T, V, 1>, grid, dim3(kThreads), sm, st, X, (int64_t)ldx, DY, (int64_t)lddy, Y, (int64_t)ldy, table, (int64_t)table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, (int64_t)cld, (T*)copy_dst, (int64_t)ldc);
+  else if (mode == 3) dlb_launch(nc_reduce2_kernel<T, V, 3>, grid, dim3(kThreads), sm, st, X, (int64_t)ldx, DY, (int64_t)lddy, Y, (int64_t)ldy, table, (int64_t)table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, (int64_t)cld, (T*)copy_dst, (int64_t)ldc);
+  else dlb_launch(nc_reduce2_kernel<T, V, 2>, grid, dim3(kThreads), sm, st, X, (int64_t)ldx, DY, (int64_t)lddy, Y, (int64_t)ldy, table, (int64_t)table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, (int64_t)cld, (T*)copy_dst, (int64_t)ldc);
   return dlb_post_launch();
 }
 
@@ -446,7 +451,7 @@ int fwd_apply_launch(const void* x, int64_t ldx, const void* res, int64_t ldr, v
   grid_for(N, HW, C, V, grid, rpb);
   const size_t sm = 2 * C * sizeof(float);
   const T* X = (const T*)x; const T* R = (const T*)res; T* Y = (T*)y;
-#define GO(RL, RS) gn_fwd_apply_kernel<T, V, RL, RS><<<grid, kThreads, sm, st>>>(X, ldx, R, ldr, Y, ldy, gamma, beta, mean, rstd, HW, C, G, rpb)
+#define GO(RL, RS) dlb_launch(gn_fwd_apply_kernel<T, V, RL, RS>, grid, dim3(kThreads), sm, st, X, (int64_t)ldx, R, (int64_t)ldr, Y, (int64_t)ldy, gamma, beta, mean, rstd, HW, C, G, rpb)
   if (relu) { if (res) GO(true, true); else GO(true, false); }
   else { if (res) GO(false, true); else GO(false, false); }
 #undef GO
@@ -465,7 +470,7 @@ int bwd_apply_launch(const void* x, int64_t ldx, const void* dy, int64_t lddy, c
   const T* X = (const T*)x; const T* DY = (const T*)dy; const T* Y = (const T*)y;
   T* DX = (T*)dx; T* DR = (T*)dres;
   const int msrc = !relu ? 0 : (ca ? 2 : 1);
-#define GO(RL, RS, AC) gn_bwd_apply_kernel<T, V, RL, RS, AC><<<grid, kThreads, sm, st>>>(X, ldx, DY, lddy, Y, ldy, DX, lddx, DR, lddr, gamma, mean, rstd, table, table_ns, HW, C, G, rpb, ca, cb, cld)
+#define GO(RL, RS, AC) dlb_launch(gn_bwd_apply_kernel<T, V, RL, RS, AC>, grid, dim3(kThreads), sm, st, X, (int64_t)ldx, DY, (int64_t)lddy, Y, (int64_t)ldy, DX, (int64_t)lddx, DR, (int64_t)lddr, gamma, mean, rstd, table, (int64_t)table_ns, HW, C, G, rpb, ca, cb, (int64_t)cld)
 #define GO2(RL) do { if (dres) { if (acc) GO(RL, true, true); else GO(RL, true, false); } else { if (acc) GO(RL, false, true); else GO(RL, false, false); } } while (0)
   if (msrc == 0) GO2(0); else if (msrc == 1) GO2(1); else GO2(2);
 #undef GO2
@@ -568,14 +573,14 @@ DLB_API int dlb_gn_finalize(const float* table, int64_t table_ns, float* mean, f
                             float eps, void* stream) {
   const int total = N * G;
   if (table_ns <= 0) table_ns = 2 * (int64_t)C;
-  gn_finalize_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(table, table_ns, mean, rstd, N, C, G, HW, eps);
+  dlb_launch(gn_finalize_kernel, dim3((total + 127) / 128), dim3(128), 0, (cudaStream_t)stream, table, (int64_t)table_ns, mean, rstd, N, C, G, HW, eps);
   return dlb_post_launch();
 }
 
 DLB_API int dlb_gn_coeff(const float* table, int64_t table_ns, const float* gamma, const float* beta, float* mean, float* rstd,
                          float* ca, float* cb, int64_t ld, int N, int C, int G, int HW, float eps, void* stream) {
   if (table_ns <= 0) table_ns = 2 * (int64_t)C;
-  gn_coeff_kernel<<<N, 256, 2 * G * sizeof(float), (cudaStream_t)stream>>>(table, table_ns, gamma, beta, mean, rstd, ca, cb, ld, C, G, HW, eps);
+  dlb_launch(gn_coeff_kernel, dim3(N), dim3(256), 2 * G * sizeof(float), (cudaStream_t)stream, table, (int64_t)table_ns, gamma, beta, mean, rstd, ca, cb, (int64_t)ld, C, G, HW, eps);
   return dlb_post_launch();
 }
 

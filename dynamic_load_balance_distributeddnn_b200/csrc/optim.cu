@@ -7,6 +7,9 @@
 #include "common.cuh"
 
 unsigned long long g_dlb_launches = 0;
+int g_dlb_pdl = 0;
+DLB_API void dlb_set_pdl(int on) { g_dlb_pdl = on; }
+DLB_API int dlb_get_pdl() { return g_dlb_pdl; }
 
 DLB_API unsigned long long dlb_launch_count() { return g_dlb_launches; }
 DLB_API void dlb_launch_count_add(unsigned long long n) { g_dlb_launches += n; }

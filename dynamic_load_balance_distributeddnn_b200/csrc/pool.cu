@@ -9,6 +9,7 @@ namespace {
 template <typename T, int V>
 __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W,
                                                           int C, int k) {
+  dlb_pdl_wait();
   const int Ho = H / k, Wo = W / k, lanes = C / V;
   const int64_t total = (int64_t)N * Ho * Wo * lanes;
   const float inv = 1.f / (float)(k * k);
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const T* __restrict__ 
 template <typename T, int V>
 __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int H, int W,
                                                           int C, int k) {
+  dlb_pdl_wait();
   const int Ho = H / k, Wo = W / k, lanes = C / V;
   const int64_t total = (int64_t)N * H * W * lanes;
   const float inv = 1.f / (float)(k * k);
@@ -66,8 +68,8 @@ int launch(bool fwd, const void* in, void* out, int N, int H, int W, int C, int 
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
   if (blocks < 1) return 0;
-  if (fwd) avgpool_fwd_kernel<T, V><<<(int)blocks, 256, 0, st>>>((const T*)in, (T*)out, N, H, W, C, k);
-  else avgpool_bwd_kernel<T, V><<<(int)blocks, 256, 0, st>>>((const T*)in, (T*)out, N, H, W, C, k);
+  if (fwd) dlb_launch(avgpool_fwd_kernel<T, V>, dim3((int)blocks), dim3(256), 0, st, (const T*)in, (T*)out, N, H, W, C, k);
+  else dlb_launch(avgpool_bwd_kernel<T, V>, dim3((int)blocks), dim3(256), 0, st, (const T*)in, (T*)out, N, H, W, C, k);
   return dlb_post_launch();
 }
 
@@ -94,6 +96,7 @@ namespace {
 template <int VB>
 __global__ void __launch_bounds__(256) copy2d_kernel(const unsigned char* __restrict__ src, int64_t lds_b,
                                                      unsigned char* __restrict__ dst, int64_t ldd_b, int64_t rows, int row_bytes) {
+  dlb_pdl_wait();
   const int lanes = row_bytes / VB;
   const int64_t total = rows * lanes;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -112,7 +115,7 @@ DLB_API int dlb_copy2d(const void* src, int64_t lds_bytes, void* dst, int64_t ld
   const int64_t total = rows * (v16 ? row_bytes / 16 : row_bytes);
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  if (v16) copy2d_kernel<16><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)src, lds_bytes, (unsigned char*)dst, ldd_bytes, rows, row_bytes);
-  else copy2d_kernel<1><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)src, lds_bytes, (unsigned char*)dst, ldd_bytes, rows, row_bytes);
+  if (v16) dlb_launch(copy2d_kernel<16>, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, (const unsigned char*)src, (int64_t)lds_bytes, (unsigned char*)dst, (int64_t)ldd_bytes, (int64_t)rows, row_bytes);
+  else dlb_launch(copy2d_kernel<1>, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, (const unsigned char*)src, (int64_t)lds_bytes, (unsigned char*)dst, (int64_t)ldd_bytes, (int64_t)rows, row_bytes);
   return dlb_post_launch();
 }

@@ -115,6 +115,10 @@ def get() -> Optional[ctypes.CDLL]:
             return None
     _lib = ctypes.CDLL(LIB_PATH)
     _declare(_lib)
+    if hasattr(_lib, "dlb_set_pdl"):
+        _lib.dlb_set_pdl.argtypes = [c_int]
+        _lib.dlb_set_pdl.restype = None
+        _lib.dlb_set_pdl(1 if os.environ.get("DLB_PDL", "1") == "1" else 0)     # programmatic dependent launch
     return _lib
 
 
