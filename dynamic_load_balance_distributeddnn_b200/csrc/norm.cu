@@ -418,6 +418,12 @@ inline void grid_for(int N, int HW, int C, int V, dim3& grid, int& rows_per_bloc
   const int row_lanes = lanes >= kThreads ? 1 : kThreads / lanes;
   int chunks = (148 * 8 + N - 1) / N;                     // about one full wave of resident blocks
   int max_chunks = HW / (row_lanes * 4);                  // keep >= 4 rows per row-lane per block
+  // every block pays a per-sample preamble (coefficients / zeroing / 2C atomics): give it >= ~48 KB of rows to
+  // stream, otherwise small per-rank batches drown in fixed cost (profiles: 16 us reduce kernels at batch 128)
+  const long long bytes_per_sample = (long long)HW * C * (V == 4 ? 4 : 2);
+  int by_work = (int)(bytes_per_sample / (48 * 1024));
+  if (by_work < 1) by_work = 1;
+  if (chunks > by_work) chunks = by_work;
   if (max_chunks < 1) max_chunks = 1;
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
