@@ -14,6 +14,7 @@
 // Rows are pixels (n, h, w); `ld*` are row strides in elements so channel slices of a wider
 // buffer can be read / written in place.
 #include "common.cuh"
+#include <stdlib.h>
 
 static int g_skip_zero = 0;      // callers that pre-zero one big arena set this to skip the per-call memsets
 
@@ -418,10 +419,12 @@ inline void grid_for(int N, int HW, int C, int V, dim3& grid, int& rows_per_bloc
   const int row_lanes = lanes >= kThreads ? 1 : kThreads / lanes;
   int chunks = (148 * 8 + N - 1) / N;                     // about one full wave of resident blocks
   int max_chunks = HW / (row_lanes * 4);                  // keep >= 4 rows per row-lane per block
-  // every block pays a per-sample preamble (coefficients / zeroing / 2C atomics): give it >= ~48 KB of rows to
+  // every block pays a per-sample preamble (coefficients / zeroing / 2C atomics): give it >= ~96 KB (tuned: 24/48/96/192/384 KB sweep on B200) of rows to
   // stream, otherwise small per-rank batches drown in fixed cost (profiles: 16 us reduce kernels at batch 128)
   const long long bytes_per_sample = (long long)HW * C * (V == 4 ? 4 : 2);
-  int by_work = (int)(bytes_per_sample / (48 * 1024));
+  static int min_kb = 0;
+  if (!min_kb) { const char* e = getenv("DLB_GN_MIN_KB"); min_kb = e ? atoi(e) : 96; if (min_kb < 1) min_kb = 96; }
+  int by_work = (int)(bytes_per_sample / ((long long)min_kb * 1024));
   if (by_work < 1) by_work = 1;
   if (chunks > by_work) chunks = by_work;
   if (max_chunks < 1) max_chunks = 1;

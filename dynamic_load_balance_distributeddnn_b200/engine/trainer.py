@@ -54,6 +54,7 @@ class Trainer:
         self.comm = comm if comm is not None else make_comm(cfg.resolved_comm(device), self.device)
         self.is_lm = cfg.is_lm
         self.log_every = 10
+        self.max_cached_graphs = 4
         self._graphs: Dict[int, "GraphedStep"] = {}
         self._eager_steps_at: Dict[int, int] = {}
         self._build()
@@ -157,6 +158,10 @@ class Trainer:
                     self.global_step += 1
                     return
                 from .graph_step import GraphedStep
+                while len(self._graphs) >= self.max_cached_graphs:      # DBS keeps moving the local batch: bound the
+                    old = next(iter(self._graphs))                      # number of captured graphs (each owns a memory pool)
+                    del self._graphs[old]
+                    self._eager_steps_at.pop(old, None)
                 g = GraphedStep(self, xb, yb)
                 self._graphs[b] = g
             slept = self.injector.host_delay()
