@@ -128,3 +128,30 @@ def test_fault_injector_reference_semantics():
     assert inj.begin_epoch(until + 1, 50) == 0.0 and not inj.waiting  # phase over, luck says no
     fixed = StragglerInjector(2, throttle_rank=2, throttle_ms=5.0)
     assert fixed.begin_epoch(0, 10) == 0.005 and StragglerInjector(1, throttle_rank=2, throttle_ms=5.0).begin_epoch(0, 10) == 0.0
+
+
+def test_flat_state_layout_and_buckets():
+    """Flat layout: 32-element aligned offsets, padded rows for the vocabulary matrix, channels-last conv storage, buckets
+    cut at parameter boundaries and covering the whole buffer."""
+    import torch
+    from dynamic_load_balance_distributeddnn_b200.models import build_model
+    from dynamic_load_balance_distributeddnn_b200.parallel import FlatState, SingleComm
+    m = build_model("transformer", ntoken=1003)
+    ref = {k: v.clone() for k, v in m.state_dict().items()}
+    flat = FlatState(m, "cpu", torch.float32, SingleComm(), lr=0.1, bucket_mb=0.25)
+    assert all(o % 32 == 0 for o in flat.offsets)
+    assert getattr(m.decoder.weight, "_dlb_padded_rows", 0) == 1008            # 1003 rows -> next multiple of 8
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, ref[k]), k                                          # adoption preserves values
+    cover = 0
+    for (off, n), idxs in zip(flat.buckets, flat.bucket_params):
+        assert off == cover and n > 0 and len(idxs) > 0
+        assert flat.offsets[idxs[0]] == off
+        cover += n
+    assert cover == flat.numel and sum(len(g) for g in flat.bucket_params) == len(flat.params)
+    r = build_model("resnet18", 10)
+    w = r.conv1.weight.detach().clone()
+    fr = FlatState(r, "cpu", torch.float32, SingleComm(), lr=0.1)
+    assert torch.equal(r.conv1.weight, w) and r.conv1.weight.is_contiguous(memory_format=torch.channels_last)
+    o, i, kh, kw = w.shape
+    assert torch.equal(fr.master[:w.numel()].view(o, kh, kw, i), w.permute(0, 2, 3, 1))   # stored [O][kh][kw][I]
