@@ -183,8 +183,8 @@ class Trainer:
         self.tracker.reset()
         self.loss_acc.zero_()
         if self.cuda:
-            self.comm.device_wait_seconds(reset=True) if hasattr(self.comm, "device_wait_seconds") else None
-        running_mark, epoch_loss = 0.0, 0.0
+            self.comm.device_wait_seconds(reset=True)
+        running_mark = 0.0
         for step in range(steps):
             idx = shard.batch_indices(step, order)
             xb, yb = self.stager.stage(idx)
@@ -204,7 +204,7 @@ class Trainer:
         self.comm.barrier()
         self.tracker.reset()
         self.loss_acc.zero_()
-        if self.cuda and hasattr(self.comm, "device_wait_seconds"):
+        if self.cuda:
             self.comm.device_wait_seconds(reset=True)
         running_mark = 0.0
         for step in range(steps):
@@ -223,8 +223,6 @@ class Trainer:
 
     def _finish_epoch(self, epoch: int, steps: int):
         compute_s, sync_s, wall_s = self.tracker.finish()
-        if self.cuda and isinstance(self.comm.device_wait_seconds(), float):
-            pass
         dev_wait = self.comm.device_wait_seconds() if self.cuda else 0.0
         if dev_wait > 0:
             # graph replays time the whole step on the device; the in-kernel entry-barrier wait is the
@@ -233,8 +231,7 @@ class Trainer:
             if self._graphs:
                 compute_s = max(0.0, compute_s - dev_wait)
         loss = float(self.loss_acc.item()) / max(1, steps)
-        if hasattr(self.comm, "check_errors"):
-            self.comm.check_errors()
+        self.comm.check_errors()
         self.logger.info(f"Rank {self.rank}, epoch {epoch}, train_time {wall_s}, train_loss {loss}")
         return compute_s, sync_s, loss, wall_s
 

@@ -52,8 +52,10 @@ class Comm:
         g = torch.zeros(numel, dtype=dtype, device=device)
         return g, g
 
-    def device_wait_seconds(self) -> float:
+    def device_wait_seconds(self, reset: bool = True) -> float:
         return 0.0
+
+    def check_errors(self) -> None: ...
 
     def close(self) -> None: ...
 

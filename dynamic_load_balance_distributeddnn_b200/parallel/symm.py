@@ -64,12 +64,13 @@ class SymmetricAllocator:
     def _alloc_torch_symm(self, name: str, nbytes: int) -> SymmBuffer:
         import torch.distributed._symmetric_memory as symm_mem
         group = self.group if self.group is not None else dist.group.WORLD
-        try:
-            symm_mem.enable_symm_mem_for_group(group.group_name)      # no-op / deprecated on new torch
-        except Exception:
-            pass
         t = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
-        hdl = symm_mem.rendezvous(t, group=group)
+        try:
+            hdl = symm_mem.rendezvous(t, group=group)
+        except Exception:
+            # older torch needs the group enabled explicitly (deprecated no-op on 2.11)
+            symm_mem.enable_symm_mem_for_group(group.group_name)
+            hdl = symm_mem.rendezvous(t, group=group)
         t.zero_()
         ptrs = [int(p) for p in hdl.buffer_ptrs]
         try:
