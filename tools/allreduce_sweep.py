@@ -64,6 +64,11 @@ while size <= max_bytes:
         ms = timed(lambda: comm.allreduce_buckets(gin, gout, [(0, n)], w), iters)
         res[algo + "_us"] = ms * 1e3
         res[algo + "_busbw"] = n * 4 / (ms * 1e-3) / 1e9 * 2 * (world - 1) / world
+        if algo == "nvls":
+            # training applies the DBS weight in the pack kernel, so the collective itself runs unweighted (no staging pass)
+            ms = timed(lambda: comm.allreduce_buckets(gin, gout, [(0, n)], None), iters)
+            res["nvls_noscale_us"] = ms * 1e3
+            res["nvls_noscale_busbw"] = n * 4 / (ms * 1e-3) / 1e9 * 2 * (world - 1) / world
     scale = 1.0 / world
 
     def nccl_path():
