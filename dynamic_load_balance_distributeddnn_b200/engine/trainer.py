@@ -147,7 +147,8 @@ class Trainer:
     def train_step(self, xb, yb) -> None:
         """Dispatch: CUDA-graph replay when enabled and warmed up for this batch size, else eager."""
         b = int(yb.shape[0]) if not self.is_lm else int(xb.shape[1])
-        use_graph = self.cuda and self.cfg.cuda_graphs and ops._native.available()
+        # gloo collectives (several ranks sharing a GPU, reference `-gpu 0,0,0,1`) cannot be stream-captured
+        use_graph = self.cuda and self.cfg.cuda_graphs and ops._native.available() and self.comm.name != "gloo"
         if use_graph:
             g = self._graphs.get(b)
             if g is None:

@@ -10,7 +10,10 @@ import torch
 
 
 def checkpoint_path(cfg) -> str:
-    return os.path.join(cfg.checkpoint_dir, cfg.experiment_id("ckpt") + ".pt")
+    """One file per experiment, independent of the epoch budget (so ``-e 5`` can be resumed with ``-e 10``)."""
+    import re
+    stem = re.sub(r"-ep\d+", "", cfg.experiment_id("ckpt"))
+    return os.path.join(cfg.checkpoint_dir, stem + ".pt")
 
 
 def save_checkpoint(cfg, epoch: int, flat_state, reallocator, extra: Optional[dict] = None) -> str:
