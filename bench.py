@@ -33,6 +33,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 # keep stdout to the single JSON line: NCCL's version banner goes to a file instead
 os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/dlb_nccl_%h_%p.log")
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+    os.environ["NCCL_DEBUG"] = "NONE"      # the version banner is printed to stdout at these levels
 
 METRIC = "densenet121_cifar10_images_per_sec"
 
@@ -412,6 +414,10 @@ def run_reference(a) -> dict:
 
 
 def main():
+    # stdout carries exactly ONE line (the JSON result): everything libraries print there (e.g. the NCCL version banner)
+    # is re-routed to stderr; the result is written to the saved descriptor at the end
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         try:
@@ -425,7 +431,8 @@ def main():
     else:
         out = run_ours(a)
     if out:
-        print(json.dumps(out), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
 
 
 if __name__ == "__main__":

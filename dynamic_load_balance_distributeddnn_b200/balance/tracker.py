@@ -36,6 +36,7 @@ class TimeTracker:
         self._t0: Optional[float] = None
         self._wall0 = time.perf_counter()
         self.steps = 0
+        self.unsteady = 0
 
     # ---- compute region -------------------------------------------------------------
     def start_compute(self) -> None:
@@ -46,7 +47,14 @@ class TimeTracker:
         else:
             self._t0 = time.perf_counter()
 
-    def stop_compute(self) -> None:
+    def stop_compute(self, steady: bool = True) -> None:
+        """``steady=False`` marks a step whose duration is not representative of this rank's throughput (eager warm-up
+        before a CUDA graph exists for a new local batch size): it is excluded from the feedback signal and the epoch
+        total is extrapolated from the steady steps, otherwise a rank that has just been re-sized looks slow, gets
+        shrunk again, is re-sized again ... and the split runs away."""
+        if not steady:
+            self.unsteady += 1
+            return
         if self.cuda:
             e = torch.cuda.Event(enable_timing=True)
             e.record()
@@ -70,4 +78,6 @@ class TimeTracker:
                 self._compute_s += a.elapsed_time(b) * 1e-3
             self._pairs.clear()
         wall = time.perf_counter() - self._wall0
+        if self.unsteady and self.steps:
+            self._compute_s *= (self.steps + self.unsteady) / self.steps
         return self._compute_s, self._sync_s, wall

@@ -126,15 +126,15 @@ class Trainer:
         return ops.augment(imgs_u8, ds.mean, ds.std, ds.pad, ds.flip, self.cfg.seed + self.rank, self.global_step,
                            self.dtype, step_tensor=self.step_t if (self.cuda and ops._native.available()) else None)
 
-    def _eager_step(self, xb, yb) -> torch.Tensor:
+    def _eager_step(self, xb, yb, steady: bool = True) -> torch.Tensor:
         self.model.train()
         self.tracker.start_compute()
         x = xb if self.is_lm else self._prepare_images(xb)
         loss = self._forward_backward(x, yb)
         slept = self.injector.host_delay()             # between backward and allreduce (reference dbs.py:236)
         self.injector.device_delay()
-        self.tracker.stop_compute()
-        if slept and self.cuda:
+        self.tracker.stop_compute(steady)
+        if slept and self.cuda and steady:
             self.tracker.add_compute(slept)
         waited = self.flat.reduce_and_step(self.rank)
         self.flat.zero_grad()
@@ -155,7 +155,7 @@ class Trainer:
                 n = self._eager_steps_at.get(b, 0)
                 if n < 3:                                   # warm-up steps at a new size run eagerly
                     self._eager_steps_at[b] = n + 1
-                    self._eager_step(xb, yb)
+                    self._eager_step(xb, yb, steady=False)
                     self.global_step += 1
                     return
                 from .graph_step import GraphedStep
