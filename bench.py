@@ -171,9 +171,7 @@ def run_ours(a) -> dict:
     if hasattr(tr.comm, "device_wait_seconds"):
         tr.comm.device_wait_seconds()
     run_steps(make_shard(lb, W + 8, 1), W + 8)
-    compute_s, sync_s, _ = tr.tracker.finish()
-    dev_wait = tr.comm.device_wait_seconds() if hasattr(tr.comm, "device_wait_seconds") else 0.0
-    compute_s = max(1e-6, compute_s - dev_wait) if tr._graphs else compute_s
+    compute_s, sync_s, _ = tr.epoch_times()          # same device-side accounting the trainer feeds to the DBS reallocator
     times = tr.comm.gather_times(compute_s)
     lb0 = [int(x) for x in lb]
     if world > 1 and not a.no_dbs:

@@ -156,6 +156,7 @@ class Trainer:
                 if n < 3:                                   # warm-up steps at a new size run eagerly
                     self._eager_steps_at[b] = n + 1
                     self._eager_step(xb, yb, steady=False)
+                    self.comm.device_wait_seconds(reset=True)      # waits of warm-up steps are not part of the signal either
                     self.global_step += 1
                     return
                 from .graph_step import GraphedStep
@@ -223,18 +224,27 @@ class Trainer:
         return self._finish_epoch(epoch, steps)
 
     def _finish_epoch(self, epoch: int, steps: int):
-        compute_s, sync_s, wall_s = self.tracker.finish()
-        dev_wait = self.comm.device_wait_seconds() if self.cuda else 0.0
-        if dev_wait > 0:
-            # graph replays time the whole step on the device; the in-kernel entry-barrier wait is the
-            # sync share (same definition as the reference: compute = wall − Σ wait, dbs.py:250)
-            sync_s += dev_wait
-            if self._graphs:
-                compute_s = max(0.0, compute_s - dev_wait)
+        compute_s, sync_s, wall_s = self.epoch_times()
         loss = float(self.loss_acc.item()) / max(1, steps)
         self.comm.check_errors()
         self.logger.info(f"Rank {self.rank}, epoch {epoch}, train_time {wall_s}, train_loss {loss}")
         return compute_s, sync_s, loss, wall_s
+
+    def epoch_times(self):
+        """(compute_s, sync_s, wall_s) of the steps since the last tracker reset.  Graph replays time the whole step on
+        the device, so the in-kernel entry-barrier wait is subtracted to get the pure compute time — the same definition
+        as the reference (compute = wall − Σ wait, dbs.py:250).  Both are measured over steady steps only and
+        extrapolated to the full step count."""
+        steady, unsteady = self.tracker.steps, self.tracker.unsteady
+        compute_s, sync_s, wall_s = self.tracker.finish()
+        dev_wait = self.comm.device_wait_seconds() if self.cuda else 0.0
+        if dev_wait > 0:
+            if steady and unsteady:
+                dev_wait *= (steady + unsteady) / steady
+            sync_s += dev_wait
+            if self._graphs:
+                compute_s = max(1e-6, compute_s - dev_wait)
+        return compute_s, sync_s, wall_s
 
     # ------------------------------------------------------------------------------------------------
     @torch.no_grad()

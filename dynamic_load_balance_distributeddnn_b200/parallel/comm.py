@@ -165,14 +165,18 @@ class SymmComm(Comm):
 
     # ---- collectives ----------------------------------------------------------------------------
     def pick_algo(self, nbytes: int) -> str:
-        """Measured on 8xB200 (profiles/r1_07): two-shot >= one-shot from 64 KiB up and >= the NVLS variant
-        everywhere; one-shot only wins the latency race for tiny buckets."""
+        """Measured on 8xB200 (profiles/r1_11): with the DBS weight already applied by the pack kernel the NVLS variant
+        (multimem.ld_reduce / multimem.st, no staging pass) is the fastest from 1 MiB up (809 GB/s busbw at 256 MiB vs
+        598 for scale+NCCL); two-shot P2P is next (and the choice without a multicast mapping); one-shot only wins the
+        latency race for tiny buckets."""
         if self.algo != "auto":
             if self.algo == "nvls" and not self.has_multicast:
                 return "twoshot"
             return self.algo
         if self.world == 1 or nbytes <= 32 * 1024:
             return "oneshot"
+        if self.has_multicast and nbytes >= 512 * 1024:
+            return "nvls"
         return "twoshot"
 
     def pick_blocks(self, nbytes: int, algo: str) -> int:

@@ -43,6 +43,14 @@ for wire in (torch.float32, torch.bfloat16):
         dist.all_gather(lst, chk)
         assert all(torch.equal(lst[0], x) for x in lst), (algo, wire)
         if rank == 0: print("ok", algo, wire, "err", err, flush=True)
+        # unweighted flavour (what training uses: the DBS weight is applied by the pack kernel)
+        gin.copy_((local * w[rank]).to(wire)); gout.zero_()
+        torch.cuda.synchronize(); dist.barrier()
+        c.allreduce_buckets(gin, gout, [(0, n)], None)
+        torch.cuda.synchronize(); c.check_errors()
+        ref2 = (local * w[rank]).to(wire).float().clone(); dist.all_reduce(ref2)
+        err2 = (gout.float() - ref2).abs().max().item()
+        assert err2 < tol * max(1.0, ref2.abs().max().item()), (algo, wire, "unweighted", err2)
 t = c.gather_times(10.0 + rank)
 assert t == [10.0 + r for r in range(world)], t
 t = c.gather_times(20.0 + rank)
