@@ -49,6 +49,9 @@ def parse():
     p.add_argument("--dataset", default="cifar10")
     p.add_argument("--batch", type=int, default=512, help="GLOBAL batch")
     p.add_argument("--throttle-ms", type=float, default=3.0, help="extra ms/step on the last rank when N>1")
+    p.add_argument("--throttle-mode", choices=("burn", "sleep"), default="burn",
+                   help="own arm: 'burn' = device-side spin kernel inside the step graph (a genuinely slower GPU); a host "
+                        "'sleep' is absorbed by the asynchronous engine and would not straggle at all")
     p.add_argument("--no-dbs", action="store_true")
     p.add_argument("--no-graphs", action="store_true")
     p.add_argument("--no-overlap", action="store_true")
@@ -112,7 +115,7 @@ def run_ours(a) -> dict:
                     epoch_size=1, validate=False,
                     dynamic_batch_size=not a.no_dbs, cuda_graphs=not a.no_graphs, comm=a.comm, allreduce_algo=a.algo,
                     dtype=a.dtype, overlap_comm=not a.no_overlap, throttle_rank=world - 1 if throttle > 0 else -1, throttle_ms=throttle,
-                    throttle_mode="sleep", log_dir="/tmp/dlb_bench/logs", stats_dir="/tmp/dlb_bench/statis")
+                    throttle_mode=a.throttle_mode, log_dir="/tmp/dlb_bench/logs", stats_dir="/tmp/dlb_bench/statis")
     logger = init_logger(cfg, rank, stream=False)
     tr = Trainer(cfg, rank, world, device, logger)
     is_lm = tr.is_lm
@@ -167,9 +170,7 @@ def run_ours(a) -> dict:
     tr.flat.set_weights(tr.realloc.weights())
     tr.injector.begin_epoch(0, W + 8)
     tr.comm.barrier()
-    tr.tracker.reset()
-    if hasattr(tr.comm, "device_wait_seconds"):
-        tr.comm.device_wait_seconds()
+    tr.reset_timers()
     run_steps(make_shard(lb, W + 8, 1), W + 8)
     compute_s, sync_s, _ = tr.epoch_times()          # same device-side accounting the trainer feeds to the DBS reallocator
     times = tr.comm.gather_times(compute_s)
@@ -193,8 +194,7 @@ def run_ours(a) -> dict:
             dist.barrier()
         tr.comm.barrier()
         torch.cuda.synchronize()
-        if hasattr(tr.comm, "device_wait_seconds"):
-            tr.comm.device_wait_seconds()
+        tr.reset_timers()
         n0 = _native.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -206,7 +206,8 @@ def run_ours(a) -> dict:
         if world > 1:
             dist.barrier()
         ms = e0.elapsed_time(e1)
-        wait = tr.comm.device_wait_seconds() if hasattr(tr.comm, "device_wait_seconds") else 0.0
+        # straggler wait = part of the step this rank did NOT spend on its own compute (device-side stamps)
+        wait = max(0.0, ms * 1e-3 - float(tr.ts[1].item()) * 1e-9) if tr._dev_timers else 0.0
         return max_over_ranks(ms, device, world), _native.launch_count() - n0, max_over_ranks(wait, device, world), host_ms
 
     ms_e2e, _, wait_e2e, host_e2e = timed(True, 3)
@@ -227,7 +228,7 @@ def run_ours(a) -> dict:
         "config": {"model": "DenseNet-121 (GroupNorm)" if a.model == "densenet" else a.model, "global_batch": a.batch,
                    "image": "3x32x32", "parallelism": f"dp{world}", "dbs": not a.no_dbs,
                    "local_batches_before": lb0, "local_batches": [int(x) for x in lb],
-                   "throttle": {"rank": world - 1, "ms_per_step": throttle} if throttle > 0 else None,
+                   "throttle": {"rank": world - 1, "ms_per_step": throttle, "mode": a.throttle_mode} if throttle > 0 else None,
                    "comm": tr.comm.name, "cuda_graphs": bool(tr._graphs), "optimizer": "SGD momentum 0.9 (in timed region)",
                    "l2": "per-step working set (activations+grads, >1 GB) exceeds the 126 MB L2; no explicit flush"},
         "e2e": {"value": round(e2e_value, 2), "unit": "tokens/s" if is_lm else "images/s", "ms_per_step": round(ms_e2e / K, 4),

@@ -77,3 +77,23 @@ DLB_API int dlb_burn(const float* usec_ptr, float usec, void* stream) {
   burn_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(usec_ptr, usec, nullptr);
   return dlb_post_launch();
 }
+
+// ------------------------------------------------------------------------------------------------
+// Device-side step timers (graph-capturable): `stamp` stores %globaltimer, `stamp_acc` adds (now - *start) to an
+// accumulator.  The trainer brackets the compute part of a step (augment -> forward -> backward -> injected straggle)
+// with them on the main stream, BEFORE it joins the communication stream, so the DBS feedback signal is the rank's
+// pure compute time even though bucket collectives overlap the backward pass (their in-kernel barrier waits overlap
+// compute and must not be subtracted from the step time).
+namespace {
+__global__ void stamp_kernel(unsigned long long* slot) { *slot = dlb_globaltimer(); }
+__global__ void stamp_acc_kernel(const unsigned long long* start, unsigned long long* acc) { *acc += dlb_globaltimer() - *start; }
+}  // namespace
+
+DLB_API int dlb_stamp(unsigned long long* slot, void* stream) {
+  stamp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(slot);
+  return dlb_post_launch();
+}
+DLB_API int dlb_stamp_acc(const unsigned long long* start, unsigned long long* acc, void* stream) {
+  stamp_acc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(start, acc);
+  return dlb_post_launch();
+}

@@ -28,9 +28,11 @@ class GraphedStep:
         torch.cuda.synchronize(t.device)
         launches0 = ops._native.launch_count()
         with torch.cuda.graph(self.graph):
+            t._stamp_start()
             x = self.x if t.is_lm else t._prepare_images(self.x)
             loss = t._forward_backward(x, self.y)
             t.injector.device_delay()
+            t._stamp_compute_end()
             t.flat.reduce_and_step(t.rank)
             t.flat.zero_grad()
             t.loss_acc += loss.float()

@@ -55,6 +55,7 @@ class Trainer:
         self.is_lm = cfg.is_lm
         self.log_every = 10
         self.max_cached_graphs = 4
+        self._host_sleep_s = 0.0
         self._graphs: Dict[int, "GraphedStep"] = {}
         self._eager_steps_at: Dict[int, int] = {}
         self._build()
@@ -108,10 +109,23 @@ class Trainer:
         self.total_train_time = 0.0
         self.global_step = 0
         self.step_t = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.ts = torch.zeros(2, dtype=torch.int64, device=self.device)      # [0] step-start stamp, [1] accumulated compute ns
+        self._dev_timers = self.cuda and ops._native.available() and hasattr(ops._native.get(), "dlb_stamp")
         self.loss_acc = torch.zeros(1, dtype=torch.float32, device=self.device)
 
     # ------------------------------------------------------------------------------------------------
     # one optimisation step, eager flavour (CPU, or CUDA before a graph exists for this batch size)
+    def _stamp_start(self) -> None:
+        if self._dev_timers:
+            nat = ops._native
+            nat.check(nat.get().dlb_stamp(self.ts.data_ptr(), nat.stream_ptr(self.device)), "stamp")
+
+    def _stamp_compute_end(self) -> None:
+        """End of this rank's compute on the main stream (before it joins the communication stream)."""
+        if self._dev_timers:
+            nat = ops._native
+            nat.check(nat.get().dlb_stamp_acc(self.ts.data_ptr(), self.ts.data_ptr() + 8, nat.stream_ptr(self.device)), "stamp_acc")
+
     def _forward_backward(self, x, y) -> torch.Tensor:
         if self.is_lm:
             loss = self.model.forward_loss(x, y)
@@ -129,13 +143,18 @@ class Trainer:
     def _eager_step(self, xb, yb, steady: bool = True) -> torch.Tensor:
         self.model.train()
         self.tracker.start_compute()
+        if steady:
+            self._stamp_start()
         x = xb if self.is_lm else self._prepare_images(xb)
         loss = self._forward_backward(x, yb)
         slept = self.injector.host_delay()             # between backward and allreduce (reference dbs.py:236)
         self.injector.device_delay()
+        if steady:
+            self._stamp_compute_end()
         self.tracker.stop_compute(steady)
         if slept and self.cuda and steady:
             self.tracker.add_compute(slept)
+            self._host_sleep_s += slept
         waited = self.flat.reduce_and_step(self.rank)
         self.flat.zero_grad()
         self.tracker.add_sync(waited)
@@ -169,6 +188,7 @@ class Trainer:
             slept = self.injector.host_delay()
             if slept:
                 self.tracker.add_compute(slept)
+                self._host_sleep_s += slept
             self.tracker.start_compute()
             g.replay(xb, yb)
             self.tracker.stop_compute()
@@ -182,10 +202,8 @@ class Trainer:
         g = torch.Generator().manual_seed(cfg.seed * 7919 + epoch * 131 + self.rank)
         order = torch.randperm(len(shard), generator=g).numpy()          # DataLoader(shuffle=True)
         self.comm.barrier()
-        self.tracker.reset()
+        self.reset_timers()
         self.loss_acc.zero_()
-        if self.cuda:
-            self.comm.device_wait_seconds(reset=True)
         running_mark = 0.0
         for step in range(steps):
             idx = shard.batch_indices(step, order)
@@ -204,10 +222,8 @@ class Trainer:
         if self.cuda:
             data = data.pin_memory()
         self.comm.barrier()
-        self.tracker.reset()
+        self.reset_timers()
         self.loss_acc.zero_()
-        if self.cuda:
-            self.comm.device_wait_seconds(reset=True)
         running_mark = 0.0
         for step in range(steps):
             i = step * cfg.bptt
@@ -230,21 +246,28 @@ class Trainer:
         self.logger.info(f"Rank {self.rank}, epoch {epoch}, train_time {wall_s}, train_loss {loss}")
         return compute_s, sync_s, loss, wall_s
 
+    def reset_timers(self) -> None:
+        self.tracker.reset()
+        self._host_sleep_s = 0.0
+        if self.cuda:
+            self.ts.zero_()
+            self.comm.device_wait_seconds(reset=True)
+
     def epoch_times(self):
-        """(compute_s, sync_s, wall_s) of the steps since the last tracker reset.  Graph replays time the whole step on
-        the device, so the in-kernel entry-barrier wait is subtracted to get the pure compute time — the same definition
-        as the reference (compute = wall − Σ wait, dbs.py:250).  Both are measured over steady steps only and
-        extrapolated to the full step count."""
+        """(compute_s, sync_s, wall_s) of the steps since the last tracker reset.
+
+        compute = this rank's own work per step (augment -> forward -> backward -> injected straggle), taken from the
+        device-side stamps that bracket it on the main stream; sync = the rest of the step (waiting for peers inside the
+        collectives + the optimizer).  The reference uses the same split (compute = wall − Σ wait, dbs.py:250) but with
+        host clocks around asynchronous launches.  Only steady steps are measured; totals are extrapolated."""
         steady, unsteady = self.tracker.steps, self.tracker.unsteady
-        compute_s, sync_s, wall_s = self.tracker.finish()
-        dev_wait = self.comm.device_wait_seconds() if self.cuda else 0.0
-        if dev_wait > 0:
-            if steady and unsteady:
-                dev_wait *= (steady + unsteady) / steady
-            sync_s += dev_wait
-            if self._graphs:
-                compute_s = max(1e-6, compute_s - dev_wait)
-        return compute_s, sync_s, wall_s
+        total_s, host_sync_s, wall_s = self.tracker.finish()
+        scale = (steady + unsteady) / steady if (steady and unsteady) else 1.0
+        if self._dev_timers and (self._graphs or self.cuda):
+            compute_s = float(self.ts[1].item()) * 1e-9 * scale + self._host_sleep_s
+            sync_s = max(0.0, total_s - compute_s) + host_sync_s
+            return max(1e-6, compute_s), sync_s, wall_s
+        return total_s, host_sync_s, wall_s
 
     # ------------------------------------------------------------------------------------------------
     @torch.no_grad()

@@ -75,6 +75,8 @@ def _declare(lib: ctypes.CDLL) -> None:
         "dlb_zero_f32": (i32, [vp, i64, vp]),
         "dlb_augment": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, c_uint, vp, vp]),
         "dlb_burn": (i32, [vp, c_float, vp]),
+        "dlb_stamp": (i32, [vp, vp]),
+        "dlb_stamp_acc": (i32, [vp, vp, vp]),
         "dlb_comm_create": (vp, [i32, i32, vp, vp, vp, c_ulonglong, c_ulonglong, c_ulonglong, c_ulonglong]),
         "dlb_comm_destroy": (None, [vp]),
         "dlb_comm_set_timeout": (None, [vp, c_double]),
