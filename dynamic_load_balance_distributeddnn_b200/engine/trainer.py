@@ -266,6 +266,10 @@ class Trainer:
         if self._dev_timers and (self._graphs or self.cuda):
             compute_s = float(self.ts[1].item()) * 1e-9 * scale + self._host_sleep_s
             sync_s = max(0.0, total_s - compute_s) + host_sync_s
+            if not self._graphs:
+                # eager steps time only the compute region with events; the collective's barrier wait comes from the
+                # in-kernel counter instead
+                sync_s += self.comm.device_wait_seconds() * scale
             return max(1e-6, compute_s), sync_s, wall_s
         return total_s, host_sync_s, wall_s
 

@@ -94,3 +94,17 @@ def test_static_when_disabled():
     assert list(b) == [128] * 4
     assert np.allclose(r.weights(), 0.25)
     assert np.allclose(r.weights(uniform=True), 0.25)
+
+
+def test_time_tracker_extrapolates_over_unsteady_steps():
+    import time
+    from dynamic_load_balance_distributeddnn_b200.balance import TimeTracker
+    t = TimeTracker("cpu")
+    for i in range(5):
+        t.start_compute()
+        time.sleep(0.01)
+        t.stop_compute(steady=(i >= 2))           # two warm-up steps are not part of the signal
+    assert t.steps == 3 and t.unsteady == 2
+    compute_s, sync_s, wall_s = t.finish()
+    assert 0.045 < compute_s < 0.08               # ~3 x 10 ms measured, scaled by 5/3
+    assert sync_s == 0.0 and wall_s >= 0.05
