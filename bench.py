@@ -53,6 +53,7 @@ def parse():
                    help="own arm: 'burn' = device-side spin kernel inside the step graph (a genuinely slower GPU); a host "
                         "'sleep' is absorbed by the asynchronous engine and would not straggle at all")
     p.add_argument("--no-dbs", action="store_true")
+    p.add_argument("--dbs-rounds", type=int, default=2, help="untimed measure->rebalance rounds before the timed region")
     p.add_argument("--no-graphs", action="store_true")
     p.add_argument("--no-overlap", action="store_true")
     p.add_argument("--comm", default="auto")
@@ -105,7 +106,7 @@ def run_ours(a) -> dict:
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(device), timeout=datetime.timedelta(seconds=300))
     W, K = max(3, a.warmup), a.steps
-    total_steps = 2 * (W + 8) + 2 * K + 8
+    total_steps = 4 * (W + 8) + 2 * K + 8
     throttle = a.throttle_ms if world > 1 else 0.0
     lm = a.model == "transformer"
     if lm:
@@ -165,22 +166,25 @@ def run_ours(a) -> dict:
         if not e2e:
             tr.stager.release()
 
-    # ---- phase 1: uniform split, warm-up + measure compute time --------------------------------------
+    # ---- phase 1: start from the uniform split; each DBS round = run a short "epoch", exchange the measured compute
+    # times with the P2P-store all-gather kernel, re-split (exactly what Trainer.run does once per epoch) --------------
     fractions, lb = tr.realloc.step()
     tr.flat.set_weights(tr.realloc.weights())
     tr.injector.begin_epoch(0, W + 8)
-    tr.comm.barrier()
-    tr.reset_timers()
-    run_steps(make_shard(lb, W + 8, 1), W + 8)
-    compute_s, sync_s, _ = tr.epoch_times()          # same device-side accounting the trainer feeds to the DBS reallocator
-    times = tr.comm.gather_times(compute_s)
     lb0 = [int(x) for x in lb]
-    if world > 1 and not a.no_dbs:
-        tr.realloc.observe(times)
-        fractions, lb = tr.realloc.step()
-        tr.flat.set_weights(tr.realloc.weights())
-    # ---- phase 2: warm-up at the rebalanced local batch (graph re-capture) ------------------------------
-    run_steps(make_shard(lb, W + 8, 2), W + 8)
+    rounds = a.dbs_rounds if (world > 1 and not a.no_dbs) else 1
+    for rnd in range(rounds):
+        tr.comm.barrier()
+        tr.reset_timers()
+        run_steps(make_shard(lb, W + 8, 1 + rnd), W + 8)
+        compute_s, sync_s, _ = tr.epoch_times()      # the device-side accounting the trainer feeds to the DBS reallocator
+        times = tr.comm.gather_times(compute_s)
+        if world > 1 and not a.no_dbs:
+            tr.realloc.observe(times)
+            fractions, lb = tr.realloc.step()
+            tr.flat.set_weights(tr.realloc.weights())
+    # ---- phase 2: warm-up at the final local batch (graph re-capture) ------------------------------------------------
+    run_steps(make_shard(lb, W + 8, 9), W + 8)
     torch.cuda.synchronize()
 
     sink = torch.zeros(8, 1, dtype=torch.float32).pin_memory()
@@ -222,7 +226,8 @@ def run_ours(a) -> dict:
     e2e_value = per_step_items * K / (ms_e2e * 1e-3)
     out = {
         "metric": METRIC if a.model == "densenet" else (f"{a.model}_{a.dataset}_tokens_per_sec" if is_lm else f"{a.model}_{a.dataset}_images_per_sec"),
-        "value": round(value, 2), "unit": "tokens/s" if is_lm else "images/s", "n_gpus": world, "steps": K, "warmup": 2 * (W + 8),
+        "value": round(value, 2), "unit": "tokens/s" if is_lm else "images/s", "n_gpus": world, "steps": K,
+        "warmup": (rounds + 1) * (W + 8),
         "ms_per_step": round(ms_dev / K, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": a.dtype, "data": "synthetic (CIFAR-10-shape uint8 images, random-init weights)", "impl": "ours",
         "config": {"model": "DenseNet-121 (GroupNorm)" if a.model == "densenet" else a.model, "global_batch": a.batch,
