@@ -1,0 +1,77 @@
+"""Artifacts and compatibility surface: log line format / file names, stats schema, Net aliases,
+run.sh interface, launcher backend selection."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+
+from dynamic_load_balance_distributeddnn_b200.config import DBSConfig
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_log_line_format_and_file_names(tmp_path):
+    from dynamic_load_balance_distributeddnn_b200.utils import done_marker, init_logger, log_path
+    cfg = DBSConfig(model="densenet", dataset="cifar10", debug=True, world_size=4, batch_size=512, log_dir=str(tmp_path / "logs"))
+    lg = init_logger(cfg, 2, stream=False)
+    lg.info("Rank 2, epoch 0: 10, train_loss 3.21")
+    for h in lg.logger.handlers:
+        h.flush()
+    path = log_path(cfg, 2)
+    assert os.path.basename(path) == "densenet-cifar10-debug1-n4-bs512-lr0.0100-ep10-dbs1-ft0-ftc0.100000-node2-ocp0.log"
+    line = open(path).read().strip()
+    # "<asctime> [ws:lr:dbs_x:ft_y] [file:line] LEVEL message"   (reference dbs_logging.py:21-22)
+    assert re.match(r"^\d{4}-\d\d-\d\d \d\d:\d\d:\d\d,\d{3} \[4:0\.01:dbs_enabled:ft_disabled\] \[\w+\.py:\d+\] INFO Rank 2, epoch 0: 10, train_loss 3\.21$", line), line
+    assert done_marker(cfg).endswith("node0-ocp0.done")
+    init_logger(cfg, 2, stream=False)            # re-initialising must not fail (race-free mkdir, handler reset)
+
+
+def test_stats_schema_matches_reference(tmp_path):
+    from dynamic_load_balance_distributeddnn_b200.utils import StatsRecorder, load_stats
+    cfg = DBSConfig(stats_dir=str(tmp_path / "statis"))
+    rec = StatsRecorder(cfg)
+    rec.append(epoch=0, train_loss=1.0, train_time=2.0, sync_time=0.1, val_loss=0.9, accuracy=50.0, partition=np.array([.5, .5]),
+               node_time=[2.0, 2.1], wallclock_time=2.2, local_batches=[32, 32], samples_per_sec=10.0,
+               straggler_wait_ms_per_step=0.3, steps=7, lr=0.01)
+    path = rec.save()
+    d = load_stats(path)
+    for k in ("epoch", "train_loss", "train_time", "sync_time", "val_loss", "accuracy", "partition", "node_time", "wallclock_time"):
+        assert k in d and len(d[k]) == 1, k        # reference dbs.py:317-326
+    assert os.path.isfile(path.replace(".npy", ".json"))
+
+
+def test_net_aliases_import_like_the_reference():
+    sys.path.insert(0, ROOT)
+    import Net.Densenet
+    import Net.GoogleNet
+    import Net.MnistNet
+    import Net.RegNet
+    import Net.Resnet
+    import Net.Transformer
+    assert sum(p.numel() for p in Net.Densenet.DenseNet121(10).parameters()) == 6956298
+    assert sum(p.numel() for p in Net.Resnet.ResNet50(10).parameters()) == 23520842
+    assert Net.MnistNet.MnistNet and Net.GoogleNet.GoogLeNet and Net.RegNet.RegNetY_400MF and Net.Transformer.TransformerModel
+
+
+def test_run_sh_usage():
+    r = subprocess.run(["bash", os.path.join(ROOT, "run.sh")], capture_output=True, text=True)
+    assert r.returncode == 0 and "Usage: ./run.sh [WORLD_SIZE] [BATCH_SIZE] [EPOCH_SIZE] [LEARNING_RATE] [GPUSET]" in r.stdout
+
+
+def test_launcher_backend_selection():
+    from dynamic_load_balance_distributeddnn_b200.launch import _backend_for
+    assert _backend_for(DBSConfig(debug=True)) == "gloo"
+    assert _backend_for(DBSConfig(debug=False, world_size=4, gpu=[0, 1, 2, 3])) == "nccl"
+    assert _backend_for(DBSConfig(debug=False, world_size=4, gpu=[0, 0, 0, 1])) == "gloo"      # shared GPU: NCCL refuses duplicates
+    assert _backend_for(DBSConfig(debug=False, world_size=2, gpu=0)) == "gloo"
+    assert _backend_for(DBSConfig(debug=False, world_size=2, gpu=0), from_env=True) == "nccl"  # torchrun: LOCAL_RANK devices
+    assert _backend_for(DBSConfig(debug=False, world_size=1, gpu=0)) == "nccl"
+
+
+def test_print_layer_and_prepare_data(tmp_path, capsys):
+    from dynamic_load_balance_distributeddnn_b200.models import build_model
+    from dynamic_load_balance_distributeddnn_b200.utils import print_layer
+    m = build_model("mnistnet")
+    assert print_layer(m, "fc2.bias") is m.fc2.bias and print_layer(m, "nope") is None
