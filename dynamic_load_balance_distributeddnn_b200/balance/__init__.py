@@ -1,5 +1,5 @@
-from .reallocator import Reallocator, get_size, integer_split, reference_split, throughput_shares
+from .reallocator import AffineReallocator, Reallocator, get_size, integer_split, reference_split, throughput_shares
 from .tracker import TimeTracker
 
-__all__ = ["Reallocator", "get_size", "integer_split", "reference_split", "throughput_shares",
+__all__ = ["AffineReallocator", "Reallocator", "get_size", "integer_split", "reference_split", "throughput_shares",
            "TimeTracker"]

@@ -53,6 +53,7 @@ class DBSConfig:
     batch_quantum: int = 1
     rebalance_every: int = 0             # 0 = once per epoch (reference); N>0 = every N steps
     time_ema: float = 0.0                # EMA on per-rank compute time (0 = off = reference)
+    dbs_model: str = "proportional"      # proportional (reference get_size) | affine (t = alpha + beta*b, latency-aware)
     lr_policy: str = "one_cycle"         # one_cycle | legacy (the reference's live decay-only curve)
     clip_grad_norm: float = -1.0         # <0: model default (0.25 for transformer, none for CNNs)
     clip_mode: str = "local"             # local (reference, pre-allreduce) | global (post-reduce)

@@ -31,7 +31,7 @@ import torch.distributed as dist
 import torch.nn.functional as F
 
 from .. import ops
-from ..balance import Reallocator, TimeTracker
+from ..balance import AffineReallocator, Reallocator, TimeTracker
 from ..config import DBSConfig
 from ..data import (BatchStager, DataPartitioner, batchify, load_corpus, load_image_dataset, split_token_stream)
 from ..fault import StragglerInjector
@@ -90,7 +90,8 @@ class Trainer:
         if self.cuda:
             torch.cuda.manual_seed(cfg.seed + 1 + self.rank)
         # ---- balancer, injector, recorder ----
-        self.realloc = Reallocator(self.world, cfg.batch_size, cfg.dynamic_batch_size, cfg.rounding,
+        realloc_cls = AffineReallocator if cfg.dbs_model == "affine" else Reallocator
+        self.realloc = realloc_cls(self.world, cfg.batch_size, cfg.dynamic_batch_size, cfg.rounding,
                                    cfg.min_local_batch, cfg.batch_quantum, cfg.time_ema)
         self.injector = StragglerInjector(self.rank, cfg.fault_tolerance, cfg.fault_tolerance_chance,
                                           cfg.throttle_rank, cfg.throttle_ms, cfg.throttle_mode, self.device,

@@ -108,3 +108,40 @@ def test_time_tracker_extrapolates_over_unsteady_steps():
     compute_s, sync_s, wall_s = t.finish()
     assert 0.045 < compute_s < 0.08               # ~3 x 10 ms measured, scaled by 5/3
     assert sync_s == 0.0 and wall_s >= 0.05
+
+
+def test_affine_reallocator_handles_fixed_cost_stragglers():
+    """Latency-bound regime: t_r(b) = alpha_r + beta_r*b with a fixed straggler cost.  The affine model jumps to the split
+    that equalises step times as soon as it is identifiable; with a completely flat T(b) the proportional (reference) rule
+    runs the slow rank down to the minimum batch for no gain, the affine one leaves it alone."""
+    from dynamic_load_balance_distributeddnn_b200.balance import AffineReallocator, Reallocator
+    alpha = np.array([4.0, 4.0, 4.0, 7.0])          # ms: rank 3 carries +3 ms of fixed cost
+    beta = np.full(4, 0.034)                        # ms per sample
+    B = 512
+
+    def simulate(r, epochs, alpha, beta):
+        for _ in range(epochs):
+            _, lb = r.step()
+            r.observe(alpha + beta * lb)
+        r.step()
+        return r.local_batches
+
+    # optimum: b_r = (tau - alpha_r)/beta_r -> the slow rank gets 3/0.034 ~ 88 fewer samples than each fast rank
+    opt = np.array([150, 150, 150, 62])
+    lb_aff = simulate(AffineReallocator(4, B), 2, alpha, beta)     # two observations at different batches suffice
+    lb_pro = simulate(Reallocator(4, B), 2, alpha, beta)
+    assert lb_aff.sum() == B and np.abs(lb_aff - opt).max() <= 3, lb_aff
+    assert np.abs(lb_pro - opt).max() > np.abs(lb_aff - opt).max()
+    # both converge to the same fixed point eventually
+    assert np.abs(simulate(Reallocator(4, B), 30, alpha, beta) - opt).max() <= 3
+    # flat T(b): proportional runs away, affine holds
+    flat = np.zeros(4)
+    lb_pro = simulate(Reallocator(4, B), 10, alpha, flat)
+    lb_aff = simulate(AffineReallocator(4, B), 10, alpha, flat)
+    assert lb_pro[3] < 8 and lb_aff[3] > 60 and lb_aff.sum() == B, (lb_pro, lb_aff)
+    # proportional data (alpha = 0): both rules agree
+    zero = np.zeros(4)
+    slope = np.array([0.03, 0.03, 0.06, 0.03])
+    a = simulate(AffineReallocator(4, B), 6, zero, slope)
+    p = simulate(Reallocator(4, B), 6, zero, slope)
+    assert np.abs(a - p).max() <= 4, (a, p)
