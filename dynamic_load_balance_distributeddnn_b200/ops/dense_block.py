@@ -271,9 +271,11 @@ class _DenseBlockFn(torch.autograd.Function):
                 # (the wgrad re-applies GN+ReLU to the raw buffer slice in its operand prologue) and the GN1
                 # backward recomputes the ReLU mask from the saved affine coefficients.
                 w1_2d = gemm_tc._w2d(w1)                                            # [cm, cl], consumed MN-major: no transpose
-                dxhat = torch.empty((n, cl, h, w), dtype=buf.dtype, device=buf.device, memory_format=torch.channels_last)
-                gemm_tc.gemm_bmn_raw(dy.data_ptr(), cm, w1_2d.data_ptr(), w1_2d.stride(0), dxhat.data_ptr(), cl, n * hw, cl, cm,
-                                     buf.device)
+                fuse_dg = gemm_tc.FUSED_DGRAD and hw % 32 == 0 and gemm_tc.dgrad_gn_available()
+                if not fuse_dg:
+                    dxhat = torch.empty((n, cl, h, w), dtype=buf.dtype, device=buf.device, memory_format=torch.channels_last)
+                    gemm_tc.gemm_bmn_raw(dy.data_ptr(), cm, w1_2d.data_ptr(), w1_2d.stride(0), dxhat.data_ptr(), cl, n * hw, cl, cm,
+                                         buf.device)
                 if side is not None:
                     ev_dy = torch.cuda.Event(); ev_dy.record(main)
                     side.wait_event(ev_dy)
@@ -285,12 +287,23 @@ class _DenseBlockFn(torch.autograd.Function):
                     gemm_tc.wgrad_raw(dy.data_ptr(), cm, xs, ct, dw1f, n * hw, cm, cl, buf.device, ca, cb, hw)
                 dw1 = None                      # cast for all layers at once after the loop
                 kpad = ca.shape[1]
-                nat.check(lib.dlb_nc_reduce2_bwd_coef(dt, xs, ct, dxhat.data_ptr(), cl, t1.data_ptr(), 0, mean1.data_ptr(),
-                                                      rstd1.data_ptr(), dg1.data_ptr(), db1.data_ptr(), ca.data_ptr(), cb.data_ptr(),
-                                                      kpad, n, hw, cl, groups, st), "dense.gn1_red")
-                nat.check(lib.dlb_gn_bwd_apply_coef(dt, xs, ct, dxhat.data_ptr(), cl, dxs, ct, g1w.data_ptr(), mean1.data_ptr(),
-                                                    rstd1.data_ptr(), t1.data_ptr(), 0, ca.data_ptr(), cb.data_ptr(), kpad,
-                                                    n, hw, cl, groups, 1, st), "dense.gn1_app")
+                if fuse_dg:
+                    # experimental: the dgrad GEMM runs twice (K = cm is small) and dA never touches HBM --
+                    # pass 1 accumulates the GroupNorm-backward sums in its epilogue, pass 2 applies them onto dX in place
+                    gemm_tc.dgrad_gn_raw(1, dy.data_ptr(), cm, w1_2d.data_ptr(), w1_2d.stride(0), xs, ct, 0, 0, n * hw, cl, cm, hw,
+                                         ca, cb, None, None, t1.data_ptr(), 2 * cl, buf.device)
+                    k23 = torch.empty((2, n, kpad), dtype=torch.float32, device=buf.device)
+                    gemm_tc.gn_bwd_coeff_raw(t1.data_ptr(), 2 * cl, g1w, mean1, rstd1, k23[0], k23[1], dg1.data_ptr(), db1.data_ptr(),
+                                             n, cl, groups, hw, buf.device)
+                    gemm_tc.dgrad_gn_raw(2, dy.data_ptr(), cm, w1_2d.data_ptr(), w1_2d.stride(0), xs, ct, dxs, ct, n * hw, cl, cm, hw,
+                                         ca, cb, k23[0], k23[1], 0, 0, buf.device)
+                else:
+                    nat.check(lib.dlb_nc_reduce2_bwd_coef(dt, xs, ct, dxhat.data_ptr(), cl, t1.data_ptr(), 0, mean1.data_ptr(),
+                                                          rstd1.data_ptr(), dg1.data_ptr(), db1.data_ptr(), ca.data_ptr(),
+                                                          cb.data_ptr(), kpad, n, hw, cl, groups, st), "dense.gn1_red")
+                    nat.check(lib.dlb_gn_bwd_apply_coef(dt, xs, ct, dxhat.data_ptr(), cl, dxs, ct, g1w.data_ptr(), mean1.data_ptr(),
+                                                        rstd1.data_ptr(), t1.data_ptr(), 0, ca.data_ptr(), cb.data_ptr(), kpad,
+                                                        n, hw, cl, groups, 1, st), "dense.gn1_app")
             else:
                 w1c = w1 if w1.dtype == xhat.dtype else w1.to(xhat.dtype)
                 dxhat, dw1, _ = _CONV_BWD(dy, xhat, w1c, None, [1, 1], [0, 0], [1, 1], False, [0, 0], 1, [True, True, False])

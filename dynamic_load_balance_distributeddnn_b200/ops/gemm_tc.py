@@ -24,6 +24,9 @@ def _lib():
         nat.declare("dlb_gemm_tc_bmn", i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp])
         nat.declare("dlb_conv3x3_tc", i32, [i32, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, vp, i64, i32, vp])
         nat.declare("dlb_wgrad_tc", i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, i32, i32, vp])
+        nat.declare("dlb_dgrad_gn", i32, [i32, vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, i64, vp, i64,
+                                          i32, vp])
+        nat.declare("dlb_gn_bwd_coeff", i32, [vp, i64, vp, vp, vp, vp, vp, i64, vp, vp, i32, i32, i32, i32, vp])
         _DECLARED = True
     return lib
 
@@ -88,6 +91,33 @@ def wgrad(dy: torch.Tensor, x: torch.Tensor, pro_a=None, pro_b=None, rows_per_sa
     dw = torch.zeros((co, ci), dtype=torch.float32, device=dy.device)
     wgrad_raw(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dw, m, co, ci, dy.device, pro_a, pro_b, rows_per_sample)
     return dw
+
+
+# ---- experimental (DLB_FUSED_DGRAD=1): dgrad GEMM fused with the GroupNorm(+ReLU) backward, csrc/dgrad_gn.cu ----------
+FUSED_DGRAD = os.environ.get("DLB_FUSED_DGRAD", "0") == "1"
+
+
+def dgrad_gn_available() -> bool:
+    return available() and hasattr(nat.get(), "dlb_dgrad_gn")
+
+
+def dgrad_gn_raw(mode: int, dy_ptr: int, lddy: int, w_ptr: int, ldw: int, x_ptr: int, ldx: int, dx_ptr: int, lddx: int,
+                 m: int, n: int, k: int, rows_per_sample: int, ca: torch.Tensor, cb: torch.Tensor,
+                 k2: Optional[torch.Tensor], k3: Optional[torch.Tensor], table_ptr: int, table_ns: int, device,
+                 sm_limit: int = 0) -> None:
+    """mode 1: table += per-(sample, channel) (sum dz, sum dz*x) with dz = (dy @ w) * [ca*x + cb > 0];
+    mode 2: dx += ca*dz + k2*x + k3 in place.  dy [m,k], w [k,n] row-major, x/dx [m,n] with free row strides."""
+    rc = _lib().dlb_dgrad_gn(mode, dy_ptr, lddy, w_ptr, ldw, x_ptr, ldx, dx_ptr, lddx, m, n, k, rows_per_sample, ca.data_ptr(),
+                             cb.data_ptr(), nat.ptr(k2), nat.ptr(k3), ca.shape[1], table_ptr, table_ns, sm_limit,
+                             nat.stream_ptr(device))
+    nat.check(rc, f"dgrad_gn(mode {mode})")
+
+
+def gn_bwd_coeff_raw(table_ptr: int, table_ns: int, gamma: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, k2: torch.Tensor,
+                     k3: torch.Tensor, dgamma_ptr: int, dbeta_ptr: int, n: int, c: int, groups: int, hw: int, device) -> None:
+    rc = _lib().dlb_gn_bwd_coeff(table_ptr, table_ns, gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), k2.data_ptr(),
+                                 k3.data_ptr(), k2.shape[1], dgamma_ptr, dbeta_ptr, n, c, groups, hw, nat.stream_ptr(device))
+    nat.check(rc, "gn_bwd_coeff")
 
 
 CONV3_MAX_HW = int(os.environ.get("DLB_TC_CONV3_MAX_HW", "64"))

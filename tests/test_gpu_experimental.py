@@ -1,0 +1,145 @@
+"""Round-2 groundwork kernels that are compiled into the library but OFF by default (DLB_FUSED_DGRAD=1 turns the
+fused dgrad+GroupNorm-backward path on).  These tests only run with DLB_TEST_EXPERIMENTAL=1 so that an unvalidated
+kernel can never turn the default GPU suite red; run them first thing on a GPU box:
+
+    DLB_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -x -q
+"""
+import os
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("DLB_TEST_EXPERIMENTAL", "0") != "1", reason="experimental kernels: opt-in")]
+
+
+@pytest.fixture(scope="module")
+def g():
+    from dynamic_load_balance_distributeddnn_b200.ops import gemm_tc
+    assert gemm_tc.available() and gemm_tc.dgrad_gn_available()
+    return gemm_tc
+
+
+def _problem(ns, hw, cl, cm, ct, seed):
+    torch.manual_seed(seed)
+    m = ns * hw
+    dy = torch.randn(m, cm, device="cuda").bfloat16()
+    w = (torch.randn(cm, cl, device="cuda") / cm ** 0.5).bfloat16()
+    big = torch.randn(m, ct, device="cuda").bfloat16()
+    off = ct - cl
+    kp = (cl + 63) // 64 * 64
+    ca = torch.zeros(ns, kp, device="cuda"); cb = torch.zeros(ns, kp, device="cuda")
+    ca[:, :cl] = torch.rand(ns, cl, device="cuda") + 0.5
+    cb[:, :cl] = torch.randn(ns, cl, device="cuda") * 0.3
+    # keep the recomputed ReLU mask away from its decision boundary (fp32 fma vs fp64 reference)
+    x = big[:, off:]
+    for _ in range(3):
+        z = ca[:, None, :cl].double() * x.double().view(ns, hw, cl) + cb[:, None, :cl].double()
+        near = (z.abs() < 1e-3).view(m, cl)
+        if not near.any():
+            break
+        x[near] = (x[near].float() + 1.0).bfloat16()
+    return dy, w, big, off, ca, cb, kp
+
+
+def _reference(dy, w, x, ca, cb, ns, hw, cl):
+    da = dy.double() @ w.double()
+    xv = x.double().view(ns, hw, cl)
+    z = ca[:, None, :cl].double() * xv + cb[:, None, :cl].double()
+    dz = da.view(ns, hw, cl) * (z > 0)
+    return dz, torch.stack([dz.sum(1), (dz * xv).sum(1)], dim=-1)          # [ns, cl, 2]
+
+
+@pytest.mark.parametrize("ns,hw,cl,cm,ct", [(4, 64, 96, 128, 160), (2, 1024, 256, 128, 256), (3, 32, 64, 128, 64),
+                                            (5, 256, 200, 128, 328), (2, 64, 1000, 128, 1024), (16, 256, 416, 64, 512)])
+def test_dgrad_gn_stats_pass(g, ns, hw, cl, cm, ct):
+    dy, w, big, off, ca, cb, kp = _problem(ns, hw, cl, cm, ct, ns + hw + cl)
+    x = big[:, off:]
+    table = torch.zeros(ns, cl, 2, device="cuda")
+    g.dgrad_gn_raw(1, dy.data_ptr(), cm, w.data_ptr(), cl, x.data_ptr(), ct, 0, 0, ns * hw, cl, cm, hw, ca, cb, None, None,
+                   table.data_ptr(), 2 * cl, dy.device)
+    torch.cuda.synchronize()
+    _, ref = _reference(dy, w, x, ca, cb, ns, hw, cl)
+    scale = ref.abs().max().item()
+    assert (table.double() - ref).abs().max().item() < 2e-3 * scale, ((table.double() - ref).abs().max().item(), scale)
+
+
+@pytest.mark.parametrize("ns,hw,cl,cm,ct", [(4, 64, 96, 128, 160), (2, 1024, 256, 128, 256), (3, 32, 64, 128, 64),
+                                            (5, 256, 200, 128, 328), (2, 64, 1000, 128, 1024)])
+def test_dgrad_gn_apply_pass(g, ns, hw, cl, cm, ct):
+    dy, w, big, off, ca, cb, kp = _problem(ns, hw, cl, cm, ct, 7 + ns + hw + cl)
+    x = big[:, off:]
+    k2 = torch.zeros(ns, kp, device="cuda"); k3 = torch.zeros(ns, kp, device="cuda")
+    k2[:, :cl] = torch.randn(ns, cl, device="cuda") * 0.1
+    k3[:, :cl] = torch.randn(ns, cl, device="cuda") * 0.1
+    dbig = torch.randn(ns * hw, ct, device="cuda").bfloat16()
+    before = dbig.clone()
+    dx = dbig[:, off:]
+    g.dgrad_gn_raw(2, dy.data_ptr(), cm, w.data_ptr(), cl, x.data_ptr(), ct, dx.data_ptr(), ct, ns * hw, cl, cm, hw, ca, cb, k2, k3,
+                   0, 0, dy.device)
+    torch.cuda.synchronize()
+    dz, _ = _reference(dy, w, x, ca, cb, ns, hw, cl)
+    xv = x.double().view(ns, hw, cl)
+    ref = before[:, off:].double().view(ns, hw, cl) + ca[:, None, :cl].double() * dz + k2[:, None, :cl].double() * xv + k3[:, None, :cl].double()
+    err = (dx.double().view(ns, hw, cl) - ref).abs().max().item()
+    assert err < 2e-2 * max(1.0, ref.abs().max().item()), err
+    if off:
+        assert torch.equal(dbig[:, :off], before[:, :off])                   # the other channels of the buffer are untouched
+
+
+def test_gn_bwd_coeff_matches_apply_kernel_math(g):
+    """k2/k3 + dgamma/dbeta from the (sum dz, sum dz*x) table == the formulas inside gn_bwd_apply / nc_reduce2."""
+    torch.manual_seed(3)
+    ns, c, groups, hw = 6, 96, 32, 64
+    table = torch.randn(ns, c, 2, device="cuda")
+    gamma = torch.rand(c, device="cuda") + 0.5
+    mean = torch.randn(ns * groups, device="cuda") * 0.2
+    rstd = torch.rand(ns * groups, device="cuda") + 0.5
+    kp = 128
+    k2 = torch.empty(ns, kp, device="cuda"); k3 = torch.empty(ns, kp, device="cuda")
+    dg = torch.zeros(c, device="cuda"); db = torch.zeros(c, device="cuda")
+    g.gn_bwd_coeff_raw(table.data_ptr(), 2 * c, gamma, mean, rstd, k2, k3, dg.data_ptr(), db.data_ptr(), ns, c, groups, hw, table.device)
+    torch.cuda.synchronize()
+    cpg = c // groups
+    A, B = table[..., 0].double(), table[..., 1].double()
+    mu = mean.double().view(ns, groups).repeat_interleave(cpg, 1); r = rstd.double().view(ns, groups).repeat_interleave(cpg, 1)
+    xh = r * (B - mu * A)
+    s1 = (gamma.double() * A).view(ns, groups, cpg).sum(-1).repeat_interleave(cpg, 1)
+    s2 = (gamma.double() * xh).view(ns, groups, cpg).sum(-1).repeat_interleave(cpg, 1)
+    inv_m = 1.0 / (cpg * hw)
+    q = r * r * s2 * inv_m
+    assert torch.allclose(k2[:, :c].double(), -q, atol=1e-4, rtol=1e-4)
+    assert torch.allclose(k3[:, :c].double(), -r * s1 * inv_m + q * mu, atol=1e-4, rtol=1e-4)
+    assert k2[:, c:].abs().sum().item() == 0 and k3[:, c:].abs().sum().item() == 0
+    assert torch.allclose(db.double(), A.sum(0), atol=1e-3, rtol=1e-4)
+    assert torch.allclose(dg.double(), xh.sum(0), atol=1e-3, rtol=1e-4)
+
+
+def test_dense_block_backward_with_fused_dgrad(g):
+    """Whole dense stage: gradients with the fused dgrad+GN-backward path == the validated three-kernel chain."""
+    from dynamic_load_balance_distributeddnn_b200.models import densenet
+    torch.manual_seed(0)
+    stage = densenet.DenseNet([4], growth_rate=32, num_classes=10).dense1.cuda()
+    for m in stage.modules():
+        if isinstance(m, torch.nn.Conv2d):
+            m.weight.data = m.weight.data.bfloat16()
+    x0 = torch.randn(8, 64, 16, 16, device="cuda").contiguous(memory_format=torch.channels_last).bfloat16()
+    outs = []
+    try:
+        for fused in (False, True):
+            g.FUSED_DGRAD = fused
+            for p in stage.parameters():
+                p.grad = None
+            x = x0.clone().requires_grad_(True)
+            y = stage(x)
+            gy = torch.randn(y.shape, device="cuda", generator=torch.Generator("cuda").manual_seed(5)).bfloat16()
+            y.backward(gy)
+            torch.cuda.synchronize()
+            outs.append((x.grad.float(), [p.grad.float().clone() for p in stage.parameters()]))
+    finally:
+        g.FUSED_DGRAD = False
+    (dx0, g0), (dx1, g1) = outs
+    assert float((dx0 - dx1).abs().max()) < 4e-2 * max(1.0, float(dx0.abs().max()))
+    for i, (a, b) in enumerate(zip(g0, g1)):
+        err, ref = float((a - b).abs().max()), float(a.abs().max())
+        assert err < 4e-2 * max(1.0, ref), (i, tuple(a.shape), err, ref)
