@@ -13,14 +13,10 @@
 // kernel runs it TWICE and never writes dA:
 //     MODE 1 (statistics): D tile in TMEM -> epilogue reads the x tile (TMA), accumulates sum(dz), sum(dz*x) per (n,c)
 //     MODE 2 (apply)     : D tile again   -> epilogue reads x and dX tiles (TMA), writes dX tile (TMA store, in place)
-// = 4 x |x| bytes.  Structure and protocols are those of gemm_tc.cu (B given as [K][N], MN-major descriptor); new here:
+// = 4 x |x| bytes.  Structure, protocols and primitives (tc_common.cuh) are those of gemm_tc.cu (B given as [K][N], MN-major descriptor); new here:
 // the per-tile auxiliary TMA loads feeding the epilogue, double buffered with their own full/empty mbarriers, and
 // 8 epilogue warps (two per TMEM lane quadrant, 64 columns each).
-#include "common.cuh"
-#include <cuda.h>
-#include <cudaTypedefs.h>
-#include <stdio.h>
-#include <stdlib.h>
+#include "tc_common.cuh"
 
 namespace {
 
@@ -32,99 +28,12 @@ constexpr int kBBytes = BN * BK * 2;            // 16 KB (two [64 k][64 n] boxes
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kHalfBytes = BM * 64 * 2;         // one [128 rows][64 cols] box = 16 KB
 constexpr int kTensorBytes = 2 * kHalfBytes;    // x (or dX) tile: 32 KB
-constexpr uint32_t kSpinLimitDG = 1u << 20;
 
 template <int MODE> struct DCfg {
   static constexpr int kStages = MODE == 2 ? 3 : 4;
   static constexpr int kAuxSlotBytes = (MODE == 2 ? 2 : 1) * kTensorBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kAuxSlotBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins > kSpinLimitDG) __trap();       // watchdog: never hang the GPU on a protocol bug
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-// K-major SWIZZLE_128B operand (rows 128 B apart, 8-row groups 1024 B apart)
-__device__ __forceinline__ uint64_t make_desc_k(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// MN-major SWIZZLE_128B operand: 64-wide MN groups one box (8192 B) apart, 8-row K groups 1024 B apart
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)(8192 >> 4) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 struct DgParams {
   int M, N, K;                 // pixels, input channels of the conv (width of x / dX), mid channels (width of dY)
@@ -246,7 +155,7 @@ dgrad_gn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-          const uint64_t adesc = make_desc_k(sa), bdesc = make_desc_mn(sa + kABytes);
+          const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc_mn(sa + kABytes);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
             umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(128 * k), idesc, (kb | k) != 0 ? 1u : 0u);
@@ -438,34 +347,6 @@ gn_bwd_coeff_kernel(const float* __restrict__ table, long long table_ns, const f
   }
 }
 
-PFN_cuTensorMapEncodeTiled_v12000 dg_encoder() {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-  if (!fn) {
-    cudaDriverEntryPointQueryResult qres;
-    void* ptr = nullptr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
-  }
-  return fn;
-}
-
-// 2-D bf16 map, inner box 64 elements (= the 128-byte swizzle span), `box_rows` rows
-int dg_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
-  auto enc = dg_encoder();
-  if (!enc) return -10;
-  static thread_local bool ctx_bound = false;   // the driver-API encoder needs a current context on this (autograd) thread
-  if (!ctx_bound) { cudaFree(0); ctx_bound = true; }
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : -11;
-}
-
 template <int MODE>
 int launch_dg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tx, const CUtensorMap& tgl, const CUtensorMap& tgs,
               const DgParams& p, int sms, cudaStream_t st) {
@@ -509,16 +390,16 @@ DLB_API int dlb_dgrad_gn(int mode, const void* dy, long long lddy, const void* w
   int sms = sm_count;
   if (sm_limit > 0 && sm_limit < sms) sms = sm_limit;
   CUtensorMap ta, tb, tx, tgl, tgs;
-  int rc = dg_map(&ta, dy, M, K, lddy, BM);
+  int rc = make_map(&ta, dy, M, K, lddy, BM);
   if (rc) return rc - 10;
-  rc = dg_map(&tb, w, K, N, ldw, 64);
+  rc = make_map(&tb, w, K, N, ldw, 64);
   if (rc) return rc - 20;
-  rc = dg_map(&tx, x, M, N, ldx, BM);
+  rc = make_map(&tx, x, M, N, ldx, BM);
   if (rc) return rc - 30;
   if (mode == 2) {
-    rc = dg_map(&tgl, dx, M, N, lddx, BM);
+    rc = make_map(&tgl, dx, M, N, lddx, BM);
     if (rc) return rc - 40;
-    rc = dg_map(&tgs, dx, M, N, lddx, 32);
+    rc = make_map(&tgs, dx, M, N, lddx, 32);
     if (rc) return rc - 50;
   } else {
     tgl = tx; tgs = tx;                         // unused in mode 1
