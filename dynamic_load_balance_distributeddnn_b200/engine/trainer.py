@@ -37,7 +37,7 @@ from ..data import (BatchStager, DataPartitioner, batchify, load_corpus, load_im
 from ..fault import StragglerInjector
 from ..models import build_model
 from ..parallel import FlatState, make_comm
-from ..utils import StatsRecorder, load_checkpoint, save_checkpoint
+from ..utils import StatsRecorder, Tracer, load_checkpoint, save_checkpoint
 from .lr_policy import lr_at_epoch
 
 _DT = {"fp32": torch.float32, "bf16": torch.bfloat16}
@@ -58,6 +58,9 @@ class Trainer:
         self._host_sleep_s = 0.0
         self._graphs: Dict[int, "GraphedStep"] = {}
         self._eager_steps_at: Dict[int, int] = {}
+        # --profile: NVTX ranges + a torch.profiler capture of a few steps + host phase table (utils/tracing.py)
+        self.tracer = Tracer(cfg.profile, os.path.join(cfg.log_dir, cfg.experiment_id(rank)) if cfg.profile else None,
+                             self.cuda, logger=logger)
         self._build()
 
     # ------------------------------------------------------------------------------------------------
@@ -128,12 +131,14 @@ class Trainer:
             nat.check(nat.get().dlb_stamp_acc(self.ts.data_ptr(), self.ts.data_ptr() + 8, nat.stream_ptr(self.device)), "stamp_acc")
 
     def _forward_backward(self, x, y) -> torch.Tensor:
-        if self.is_lm:
-            loss = self.model.forward_loss(x, y)
-        else:
-            out = self.model(x)
-            loss = ops.cross_entropy(out, y)
-        loss.backward()
+        with self.tracer.range("forward"):
+            if self.is_lm:
+                loss = self.model.forward_loss(x, y)
+            else:
+                out = self.model(x)
+                loss = ops.cross_entropy(out, y)
+        with self.tracer.range("backward"):
+            loss.backward()
         return loss.detach()
 
     def _prepare_images(self, imgs_u8: torch.Tensor) -> torch.Tensor:
@@ -146,18 +151,21 @@ class Trainer:
         self.tracker.start_compute()
         if steady:
             self._stamp_start()
-        x = xb if self.is_lm else self._prepare_images(xb)
+        with self.tracer.range("augment"):
+            x = xb if self.is_lm else self._prepare_images(xb)
         loss = self._forward_backward(x, yb)
-        slept = self.injector.host_delay()             # between backward and allreduce (reference dbs.py:236)
-        self.injector.device_delay()
+        with self.tracer.range("straggler"):
+            slept = self.injector.host_delay()         # between backward and allreduce (reference dbs.py:236)
+            self.injector.device_delay()
         if steady:
             self._stamp_compute_end()
         self.tracker.stop_compute(steady)
         if slept and self.cuda and steady:
             self.tracker.add_compute(slept)
             self._host_sleep_s += slept
-        waited = self.flat.reduce_and_step(self.rank)
-        self.flat.zero_grad()
+        with self.tracer.range("reduce_and_step"):
+            waited = self.flat.reduce_and_step(self.rank)
+            self.flat.zero_grad()
         self.tracker.add_sync(waited)
         self.loss_acc += loss.float()
         if self.cuda:
@@ -168,7 +176,9 @@ class Trainer:
         """Dispatch: CUDA-graph replay when enabled and warmed up for this batch size, else eager."""
         b = int(yb.shape[0]) if not self.is_lm else int(xb.shape[1])
         # gloo collectives (several ranks sharing a GPU, reference `-gpu 0,0,0,1`) cannot be stream-captured
-        use_graph = self.cuda and self.cfg.cuda_graphs and ops._native.available() and self.comm.name != "gloo"
+        # profiling runs stay eager: a replayed graph is one opaque launch, the NVTX ranges would be empty
+        use_graph = (self.cuda and self.cfg.cuda_graphs and ops._native.available() and self.comm.name != "gloo"
+                     and not self.cfg.profile)
         if use_graph:
             g = self._graphs.get(b)
             if g is None:
@@ -196,6 +206,7 @@ class Trainer:
         else:
             self._eager_step(xb, yb)
         self.global_step += 1
+        self.tracer.step()
 
     # ------------------------------------------------------------------------------------------------
     def _train_epoch_vision(self, epoch: int, shard, steps: int) -> Tuple[float, float, float]:
@@ -207,8 +218,9 @@ class Trainer:
         self.loss_acc.zero_()
         running_mark = 0.0
         for step in range(steps):
-            idx = shard.batch_indices(step, order)
-            xb, yb = self.stager.stage(idx)
+            with self.tracer.range("stage_h2d"):
+                idx = shard.batch_indices(step, order)
+                xb, yb = self.stager.stage(idx)
             self.train_step(xb, yb)
             self.stager.release()
             if step % self.log_every == 0 and step > 0:
@@ -230,9 +242,10 @@ class Trainer:
             i = step * cfg.bptt
             src = data[i:i + cfg.bptt]
             tgt = data[i + 1:i + 1 + cfg.bptt].reshape(-1)
-            if self.cuda:
-                src = src.to(self.device, non_blocking=True)
-                tgt = tgt.to(self.device, non_blocking=True)
+            with self.tracer.range("stage_h2d"):
+                if self.cuda:
+                    src = src.to(self.device, non_blocking=True)
+                    tgt = tgt.to(self.device, non_blocking=True)
             self.train_step(src, tgt)
             if step % self.log_every == 0 and step > 0:
                 acc = float(self.loss_acc.item())
@@ -327,7 +340,8 @@ class Trainer:
             lr = lr_at_epoch(cfg.learning_rate, epoch, cfg.epoch_size, cfg.lr_policy, cfg.one_cycle_policy,
                              cfg.disable_enhancements)
             self.flat.set_lr(lr)
-            fractions, local_batches = self.realloc.step()
+            with self.tracer.range("rebalance"):
+                fractions, local_batches = self.realloc.step()
             if cfg.dynamic_batch_size:
                 self.logger.info(f"Rank {self.rank}, adjusted partition size to {fractions}")
             self.flat.set_weights(self.realloc.weights(uniform=cfg.disable_enhancements))
@@ -353,7 +367,8 @@ class Trainer:
             else:
                 compute_s, sync_s, loss, wall_s = self._train_epoch_vision(epoch, shard, steps)
             self.total_train_time += time.perf_counter() - t0
-            val_loss, metric = self.validate(epoch) if cfg.validate else (float("nan"), float("nan"))
+            with self.tracer.range("validate"):
+                val_loss, metric = self.validate(epoch) if cfg.validate else (float("nan"), float("nan"))
             # ---- DBS feedback: exchange pure compute time (reference dbs.py:423-426) ----
             nodes_time = self.comm.gather_times(compute_s)
             if cfg.dynamic_batch_size:
@@ -368,11 +383,13 @@ class Trainer:
                 save_checkpoint(cfg, epoch, self.flat, self.realloc)
         if self.rank == 0:
             self.recorder.save()
+        self.tracer.close()
         self.logger.info(f"Rank {self.rank} Terminated")
         self.logger.info(f"Rank {self.rank} Total Time:")
         self.logger.info(self.total_train_time)
         return self.recorder
 
     def close(self) -> None:
+        self.tracer.close()
         self._graphs.clear()
         self.comm.close()

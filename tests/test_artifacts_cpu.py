@@ -75,3 +75,26 @@ def test_print_layer_and_prepare_data(tmp_path, capsys):
     from dynamic_load_balance_distributeddnn_b200.utils import print_layer
     m = build_model("mnistnet")
     assert print_layer(m, "fc2.bias") is m.fc2.bias and print_layer(m, "nope") is None
+
+
+def test_profile_flag_writes_trace_kernel_table_and_phase_log(tmp_path):
+    """--profile: NVTX/record_function ranges per phase, a Chrome trace + per-op table of a few steps,
+    and the host-side phase table in the rank log."""
+    import json
+    from dynamic_load_balance_distributeddnn_b200.config import DBSConfig
+    from dynamic_load_balance_distributeddnn_b200.engine import Trainer
+    from dynamic_load_balance_distributeddnn_b200.utils import init_logger
+    cfg = DBSConfig(debug=True, world_size=1, batch_size=16, model="mnistnet", dataset="mnist", synthetic=True,
+                    train_samples=16 * 12, test_samples=32, epoch_size=1, validate=True, profile=True,
+                    log_dir=str(tmp_path / "logs"), stats_dir=str(tmp_path / "statis"))
+    t = Trainer(cfg, 0, 1, "cpu", init_logger(cfg, 0, stream=False))
+    t.run()
+    t.close()
+    stem = os.path.join(cfg.log_dir, cfg.experiment_id(0))
+    trace = json.load(open(stem + ".trace.json"))
+    names = {e.get("name") for e in trace["traceEvents"]}
+    assert {"forward", "backward", "reduce_and_step"} <= names
+    assert os.path.getsize(stem + ".kernels.txt") > 0
+    log = open(stem + ".log").read()
+    assert "host-side phase table" in log and "stage_h2d" in log and "validate" in log
+    assert t.tracer.phase_n["forward"] == 12 and t.tracer.phase_n["rebalance"] == 1
