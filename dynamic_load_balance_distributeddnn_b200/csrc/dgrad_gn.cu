@@ -377,7 +377,7 @@ DLB_API int dlb_dgrad_gn(int mode, const void* dy, long long lddy, const void* w
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (mode != 1 && mode != 2) return -2;
   if ((K % 8) || (N % 8) || (lddy % 8) || (ldw % 8) || (ldx % 8) || ((uintptr_t)dy & 15) || ((uintptr_t)w & 15) || ((uintptr_t)x & 15)) return -3;
-  if (rows_per_sample <= 0 || (rows_per_sample % 32) || (M % rows_per_sample)) return -4;
+  if (rows_per_sample <= 0 || (rows_per_sample % 32) || (M % rows_per_sample) || M < BM) return -4;
   if (!ca || !cb || (cld % 64) || cld < (N + 63) / 64 * 64 || ((uintptr_t)ca & 15) || ((uintptr_t)cb & 15)) return -5;
   if (mode == 1 && !table) return -6;
   if (mode == 2 && (!dx || !k2 || !k3 || (lddx % 8) || ((uintptr_t)dx & 15) || ((uintptr_t)k2 & 15) || ((uintptr_t)k3 & 15))) return -6;

@@ -271,7 +271,7 @@ class _DenseBlockFn(torch.autograd.Function):
                 # (the wgrad re-applies GN+ReLU to the raw buffer slice in its operand prologue) and the GN1
                 # backward recomputes the ReLU mask from the saved affine coefficients.
                 w1_2d = gemm_tc._w2d(w1)                                            # [cm, cl], consumed MN-major: no transpose
-                fuse_dg = gemm_tc.FUSED_DGRAD and hw % 32 == 0 and gemm_tc.dgrad_gn_available()
+                fuse_dg = gemm_tc.FUSED_DGRAD and hw % 32 == 0 and n * hw >= 128 and gemm_tc.dgrad_gn_available()
                 if not fuse_dg:
                     dxhat = torch.empty((n, cl, h, w), dtype=buf.dtype, device=buf.device, memory_format=torch.channels_last)
                     gemm_tc.gemm_bmn_raw(dy.data_ptr(), cm, w1_2d.data_ptr(), w1_2d.stride(0), dxhat.data_ptr(), cl, n * hw, cl, cm,
