@@ -145,3 +145,25 @@ def test_affine_reallocator_handles_fixed_cost_stragglers():
     a = simulate(AffineReallocator(4, B), 6, zero, slope)
     p = simulate(Reallocator(4, B), 6, zero, slope)
     assert np.abs(a - p).max() <= 4, (a, p)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(2, 8).flatmap(lambda n: st.tuples(
+    st.lists(st.floats(0.0, 20.0), min_size=n, max_size=n),              # fixed cost alpha_r (ms)
+    st.lists(st.floats(0.0, 0.2), min_size=n, max_size=n),               # slope beta_r (ms / sample), 0 = flat
+    st.integers(64, 2048))))
+def test_affine_reallocator_invariants(arg):
+    """Whatever the (alpha, beta) landscape — including flat and mixed ranks — every split is a partition of B into
+    positive integers, and the predicted makespan never ends up worse than the uniform split by more than rounding."""
+    from dynamic_load_balance_distributeddnn_b200.balance import AffineReallocator
+    alpha, beta, B = np.array(arg[0]) + 0.5, np.array(arg[1]), arg[2]
+    n = len(alpha)
+    r = AffineReallocator(n, B)
+    for _ in range(6):
+        _, lb = r.step()
+        assert lb.sum() == B and (lb >= 1).all() and len(lb) == n
+        r.observe(alpha + beta * lb)
+    _, lb = r.step()
+    t_final = float((alpha + beta * lb).max())
+    t_uniform = float((alpha + beta * (B / n)).max())
+    assert t_final <= t_uniform * 1.02 + float(beta.max()) * n + 1e-9, (lb, t_final, t_uniform)

@@ -47,3 +47,10 @@ def test_experiment_id_matches_reference_format():
     g = c.replace(debug=False, gpu=[0, 0, 0, 1])
     assert [g.device_for_rank(r) for r in range(4)] == ["cuda:0", "cuda:0", "cuda:0", "cuda:1"]
     assert c.replace(debug=False, gpu=2).device_for_rank(3) == "cuda:2"
+
+
+def test_dbs_model_and_profile_extension_flags():
+    from dynamic_load_balance_distributeddnn_b200.cli import config_from_args
+    cfg = config_from_args(["-ws", "2", "--dbs_model", "affine", "--profile", "true"])
+    assert cfg.dbs_model == "affine" and cfg.profile is True
+    assert config_from_args([]).dbs_model == "proportional"
