@@ -9,7 +9,7 @@ re-parse the command line and tests can build configs directly.
 from __future__ import annotations
 
 import dataclasses
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import List, Optional, Union
 
 MODELS = ("mnistnet", "resnet", "resnet18", "resnet34", "resnet50", "resnet101", "resnet152",

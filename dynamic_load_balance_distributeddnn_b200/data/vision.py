@@ -15,7 +15,6 @@ class-conditional colour blobs + noise, so a model can actually learn it.
 """
 from __future__ import annotations
 
-import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 

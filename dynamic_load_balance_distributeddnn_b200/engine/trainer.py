@@ -23,7 +23,7 @@ from __future__ import annotations
 import math
 import os
 import time
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, Tuple
 
 import numpy as np
 import torch

@@ -10,10 +10,7 @@ from __future__ import annotations
 
 import datetime
 import os
-import sys
-import time
 import traceback
-from typing import Optional
 
 import torch
 import torch.distributed as dist

@@ -8,7 +8,6 @@ the intended conv→GN→ReLU.
 """
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .layers import Conv2d, GroupNormAct, Linear
 

@@ -10,7 +10,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_uint, c_ulonglong, c_void_p, POINTER
+from ctypes import c_double, c_float, c_int, c_longlong, c_uint, c_ulonglong, c_void_p
 from typing import Optional
 
 import torch

@@ -7,7 +7,6 @@ from __future__ import annotations
 
 import os
 
-import torch
 
 from . import _native as nat
 

@@ -19,13 +19,13 @@ from __future__ import annotations
 
 import ctypes
 import math
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import torch
 import torch.nn as nn
 
 from ..ops import _native as nat
-from .comm import Comm, SymmComm
+from .comm import Comm
 
 _ALIGN = 32          # elements; keeps every parameter 64-byte aligned in bf16 and 128-byte in fp32
 

@@ -20,7 +20,6 @@ import ctypes
 import time
 from typing import List, Optional, Sequence
 
-import numpy as np
 import torch
 import torch.distributed as dist
 
