@@ -40,6 +40,20 @@ def test_mnistnet_ws2_gloo_dbs(tmp_path):
     assert r2.returncode == 0 and "skipping" in r2.stdout
 
 
+def test_mnistnet_ws2_gloo_affine_dbs(tmp_path):
+    """Same plumbing with the latency-aware balancer (--dbs_model affine): runs end to end, every split sums to B, and the
+    rank carrying a fixed per-step delay does not gain share."""
+    from dynamic_load_balance_distributeddnn_b200.utils import load_stats
+    args = "-d true -ws 2 -b 64 -m mnistnet -ds mnist -e 4 --synthetic true --train_samples 1536 --test_samples 128 " \
+           "--throttle_rank 1 --throttle_ms 40 --dbs_model affine --master_port 29613".split()
+    r = _run_cli(tmp_path, args)
+    assert r.returncode == 0, r.stderr[-3000:]
+    stats = load_stats(str(tmp_path / "statis" / "mnistnet-mnist-debug1-n2-bs64-lr0.0100-ep4-dbs1-ft0-ftc0.100000-node0-ocp0.npy"))
+    lb = stats["local_batches"]
+    assert len(lb) == 4 and all(sum(x) == 64 and min(x) >= 1 for x in lb)
+    assert lb[0] == [32, 32] and lb[-1][1] <= 32
+
+
 def test_failure_propagates_exit_code(tmp_path):
     r = _run_cli(tmp_path, "-d true -ws 2 -b 64 -m mnistnet -ds cifar10 -e 1 --synthetic true --train_samples 256 "
                            "--test_samples 64 --master_port 29612".split(), timeout=300)
