@@ -9,6 +9,8 @@ graph never has to be re-captured except when the rebalancer changes this rank's
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from .. import ops
@@ -22,6 +24,12 @@ class GraphedStep:
         self.x.copy_(xb)
         self.y.copy_(yb)
         self.graph = torch.cuda.CUDAGraph()
+        # DLB_GRAPH_DUMP=<prefix>: write the captured graph as <prefix>.b<batch>.rank<r>.dot (cudaGraphDebugDotPrint);
+        # `python tools/graph_nodes.py <file>` reports node counts per kind / kernel and the critical-path length --
+        # the quantity that bounds the step at small per-rank batches
+        dump = os.environ.get("DLB_GRAPH_DUMP")
+        if dump:
+            self.graph.enable_debug_mode()
         t = trainer
         t.model.train()
         t.flat.zero_grad()
@@ -38,6 +46,9 @@ class GraphedStep:
             t.loss_acc += loss.float()
             t.step_t += 1
         self.native_launches = ops._native.launch_count() - launches0
+        if dump:
+            b = int(yb.shape[0]) if not t.is_lm else int(xb.shape[1])
+            self.graph.debug_dump(f"{dump}.b{b}.rank{t.rank}.dot")
         t.flat._keep = None
 
     def replay(self, xb: torch.Tensor, yb: torch.Tensor) -> None:
