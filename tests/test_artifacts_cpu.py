@@ -98,3 +98,33 @@ def test_profile_flag_writes_trace_kernel_table_and_phase_log(tmp_path):
     log = open(stem + ".log").read()
     assert "host-side phase table" in log and "stage_h2d" in log and "validate" in log
     assert t.tracer.phase_n["forward"] == 12 and t.tracer.phase_n["rebalance"] == 1
+
+
+def test_graph_nodes_tool_counts_and_critical_path(tmp_path):
+    """tools/graph_nodes.py on a cudaGraphDebugDotPrint-style dump: node kinds, kernel histogram, longest chain."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("graph_nodes", os.path.join(ROOT, "tools", "graph_nodes.py"))
+    gn = importlib.util.module_from_spec(spec); spec.loader.exec_module(gn)
+    dot = tmp_path / "g.dot"
+    dot.write_text(r'''digraph dot {
+subgraph cluster_1 {
+label="graph_1" graph[style="dashed"];
+"n0"[style="solid" shape="rectangle" label="0\nMEMSET\nnode handle: 0x1"];
+"n1"[style="bold" shape="octagon" label="1\n_Z3fooPf\nnode handle: 0x2"];
+"n2"[style="bold" shape="octagon" label="2\n_Z3barPf\nnode handle: 0x3"];
+"n3"[style="solid" shape="rectangle" label="3\nEVENT_RECORD\nnode handle: 0x4"];
+"n4"[style="bold" shape="octagon" label="4\n_Z3fooPf\nnode handle: 0x5"];
+"n0" -> "n1";
+"n1" -> "n2";
+"n1" -> "n3";
+"n2" -> "n4";
+}
+}
+''')
+    nodes, edges = gn.parse(str(dot))
+    assert len(nodes) == 5 and len(edges) == 4
+    kinds = sorted(k for k, _ in nodes.values())
+    assert kinds == ["EVENT_RECORD", "KERNEL", "KERNEL", "KERNEL", "MEMSET"]
+    roots, leaves, (path_nodes, path_kernels), acyclic = gn.critical_path(nodes, edges)
+    assert (roots, leaves, path_nodes, path_kernels, acyclic) == (1, 2, 4, 3, True)
+    assert gn.main([str(dot)]) == 0
