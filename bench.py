@@ -8,14 +8,21 @@ when N > 1 so the DBS rebalancer has something to do.
         bench.py --gpus 8 --steps 20 --warmup 5
     python bench.py --impl reference ...      # the UNMODIFIED reference from baseline/_ref, same metric
 
-Own arm, per rank:  W warm-up steps at the uniform split (eager warm-up + CUDA-graph capture) → exchange
-measured compute times with the P2P-store all-gather kernel → DBS reallocation → warm-up at the new local
-batch (re-capture) → timed region.  Two timed regions of exactly K steps each, both bracketed by
-barrier + cuda synchronize and timed with CUDA events, max over ranks:
-  * ``e2e``   — the public API path a user runs: every step gathers its batch into pinned host memory, copies
-                it host→device, runs the step (augment → fwd → bwd → pack(+w_r) → fused allreduce → SGD) and
-                copies the running loss device→host.
-  * ``value`` — the same K steps with the batch already resident on the device (kernel-only number).
+BOTH arms run the same schedule (W = max(5, --warmup) steps per phase):
+
+    N = 1 (or --no-dbs):  W warm-up steps                                   -> K timed steps
+    N > 1 with DBS:       R x [W steps -> exchange compute times -> re-split]  (R = --dbs-rounds, default 2)
+                          -> W warm-up steps at the final split              -> K timed steps at that split
+
+Own arm: two timed regions of exactly K steps each, both bracketed by barrier + cuda synchronize and timed with CUDA
+events, max over ranks:
+  * ``e2e``   -- the public API path a user runs: every step gathers its batch into pinned host memory, copies it
+                 host->device, runs the step (augment -> fwd -> bwd -> weighted allreduce -> SGD) and copies the running
+                 loss device->host.
+  * ``value`` -- the same K steps with the batch already resident on the device (kernel-only number).
+Reference arm: the unmodified reference loaded from baseline/_ref ONLY (the repo root is removed from sys.path, no module
+of this repository is imported, libdlb_b200.so is asserted absent from the process): its own models, DataLoader,
+per-parameter SSGD allreduce, torch.optim.SGD, get_size and time_allreduce, in the order its run() calls them.
 Scaling is STRONG: the global batch stays 512 as N grows (that is what `-b` means in the reference).
 """
 from __future__ import annotations
@@ -25,18 +32,20 @@ import datetime
 import itertools
 import json
 import os
+import statistics
+import subprocess
 import sys
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-if ROOT not in sys.path:
-    sys.path.insert(0, ROOT)
 # keep stdout to the single JSON line: NCCL's version banner goes to a file instead
 os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/dlb_nccl_%h_%p.log")
 if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
     os.environ["NCCL_DEBUG"] = "NONE"      # the version banner is printed to stdout at these levels
 
 METRIC = "densenet121_cifar10_images_per_sec"
+MODEL_NAMES = {"densenet": "densenet121", "resnet": "resnet101"}
 
 
 def parse():
@@ -51,14 +60,17 @@ def parse():
     p.add_argument("--throttle-ms", type=float, default=3.0, help="extra ms/step on the last rank when N>1")
     p.add_argument("--throttle-mode", choices=("burn", "sleep"), default="burn",
                    help="own arm: 'burn' = device-side spin kernel inside the step graph (a genuinely slower GPU); a host "
-                        "'sleep' is absorbed by the asynchronous engine and would not straggle at all")
+                        "'sleep' is absorbed by the asynchronous engine and would not straggle at all.  The reference arm "
+                        "always uses its own injector's mechanism (a host sleep between backward and allreduce, dbs.py:236)")
     p.add_argument("--no-dbs", action="store_true")
-    p.add_argument("--dbs-rounds", type=int, default=2, help="untimed measure->rebalance rounds before the timed region")
+    p.add_argument("--dbs-rounds", type=int, default=2, help="untimed measure->rebalance rounds before the timed region (both arms)")
+    p.add_argument("--dbs-model", default="auto", help="own arm: proportional | affine | auto (the framework default)")
     p.add_argument("--no-graphs", action="store_true")
     p.add_argument("--no-overlap", action="store_true")
     p.add_argument("--comm", default="auto")
     p.add_argument("--algo", default="auto")
-    p.add_argument("--dtype", default="bf16")
+    p.add_argument("--dtype", default="auto", help="own arm: auto | bf16 | tf32 (fp32 storage, tf32 tensor-core math) | fp32")
+    p.add_argument("--alt-dtype", default="", help="own arm: additionally measure this dtype and report it under 'alt'")
     return p.parse_args()
 
 
@@ -89,15 +101,97 @@ def sum_over_ranks(value: float, device, world: int) -> float:
     return float(t.item())
 
 
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed region (recipe: B200_PROFILING.md).  Stand-alone on
+    purpose: the reference arm must not import anything from this repository's package."""
+    _Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int = 0, period_ms: int = 100):
+        self.gpu_index, self.period_ms = gpu_index, period_ms
+        self.samples = []
+        self._proc = self._thread = None
+
+    def start(self) -> None:
+        try:
+            self._proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self._Q}", "--format=csv,noheader,nounits",
+                                           "-i", str(self.gpu_index), "-lms", str(self.period_ms)],
+                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self._proc = None
+            return
+
+        def pump():
+            for line in self._proc.stdout:
+                parts = [p.strip() for p in line.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+        self._thread = threading.Thread(target=pump, daemon=True)
+        self._thread.start()
+
+    def stop(self) -> dict:
+        if self._proc is not None:
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=2)
+            except Exception:      # noqa: BLE001
+                self._proc.kill()
+            if self._thread is not None:
+                self._thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx.append(float(s[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        busy = sorted(sm)[len(sm) // 2:]                  # upper half ~ samples under load
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def schedule(a, world):
+    """(W, K, dbs_rounds) -- identical for both arms."""
+    W, K = max(5, a.warmup), a.steps
+    rounds = a.dbs_rounds if (world > 1 and not a.no_dbs) else 0
+    return W, K, rounds
+
+
+def metric_name(a, is_lm):
+    if a.model == "densenet":
+        return METRIC
+    return f"{a.model}_{a.dataset}_tokens_per_sec" if is_lm else f"{a.model}_{a.dataset}_images_per_sec"
+
+
+def common_config(a, world, is_lm, throttle, rounds, W):
+    """The part of `config` that must be IDENTICAL in both arms (what the benchmark is)."""
+    cfg = {"model": MODEL_NAMES.get(a.model, a.model), "global_batch": a.batch, "parallelism": f"dp{world}",
+           "dataset": f"{a.dataset}-shape synthetic", "optimizer": "SGD momentum 0.9 (inside the timed region)",
+           "dbs": not a.no_dbs, "dbs_rounds_before_timing": rounds, "warmup_steps_per_phase": W,
+           "untimed_steps_total": (rounds + 1) * W,
+           "throttle": {"rank": world - 1, "ms_per_step": throttle} if throttle > 0 else None,
+           "l2": "per-step working set (activations + gradients, > 1 GB) exceeds the 126 MB L2; no explicit flush"}
+    if is_lm:
+        cfg["seq_len"] = 35
+    else:
+        cfg["image"] = "3x32x32"
+    return cfg
+
+
 # =====================================================================================================
 def run_ours(a) -> dict:
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
     from dynamic_load_balance_distributeddnn_b200.config import DBSConfig
     from dynamic_load_balance_distributeddnn_b200.data import DataPartitioner
     from dynamic_load_balance_distributeddnn_b200.engine import Trainer
     from dynamic_load_balance_distributeddnn_b200.ops import _native
-    from dynamic_load_balance_distributeddnn_b200.utils import ClockSampler, init_logger
+    from dynamic_load_balance_distributeddnn_b200.utils import init_logger
 
     rank, world, local = dist_env()
     assert world == a.gpus or world == 1, f"WORLD_SIZE {world} != --gpus {a.gpus}"
@@ -105,162 +199,195 @@ def run_ours(a) -> dict:
     torch.cuda.set_device(device)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(device), timeout=datetime.timedelta(seconds=300))
-    W, K = max(3, a.warmup), a.steps
-    total_steps = 4 * (W + 8) + 2 * K + 8
+    W, K, rounds = schedule(a, world)
     throttle = a.throttle_ms if world > 1 else 0.0
     lm = a.model == "transformer"
     if lm:
         a.dataset = "wikitext2"
-    cfg = DBSConfig(debug=False, world_size=world, batch_size=a.batch, model=a.model, dataset=a.dataset, synthetic=True,
-                    train_samples=(a.batch * 36 * (total_steps + 4)) if lm else a.batch * total_steps, test_samples=256,
-                    epoch_size=1, validate=False,
-                    dynamic_batch_size=not a.no_dbs, cuda_graphs=not a.no_graphs, comm=a.comm, allreduce_algo=a.algo,
-                    dtype=a.dtype, overlap_comm=not a.no_overlap, throttle_rank=world - 1 if throttle > 0 else -1, throttle_ms=throttle,
-                    throttle_mode=a.throttle_mode, log_dir="/tmp/dlb_bench/logs", stats_dir="/tmp/dlb_bench/statis")
-    logger = init_logger(cfg, rank, stream=False)
-    tr = Trainer(cfg, rank, world, device, logger)
-    is_lm = tr.is_lm
+    clocks = ClockSampler(local)
 
-    def make_shard(local_batches, n_steps, seed):
-        if is_lm:
-            return (int(local_batches[rank]), n_steps, seed)
-        part = DataPartitioner(len(tr.train_set), local_batches, seed, True, n_steps)
-        return part.use(rank)
+    def measure(dtype: str) -> dict:
+        total_steps = (rounds + 1) * W + 2 * K + 8
+        extra = {} if a.dbs_model == "auto" else {"dbs_model": a.dbs_model}
+        cfg = DBSConfig(debug=False, world_size=world, batch_size=a.batch, model=a.model, dataset=a.dataset, synthetic=True,
+                        train_samples=(a.batch * 36 * (total_steps + 4)) if lm else a.batch * total_steps, test_samples=256,
+                        epoch_size=1, validate=False,
+                        dynamic_batch_size=not a.no_dbs, cuda_graphs=not a.no_graphs, comm=a.comm, allreduce_algo=a.algo,
+                        dtype=dtype, overlap_comm=not a.no_overlap, throttle_rank=world - 1 if throttle > 0 else -1,
+                        throttle_ms=throttle, throttle_mode=a.throttle_mode, log_dir="/tmp/dlb_bench/logs",
+                        stats_dir="/tmp/dlb_bench/statis", **extra)
+        logger = init_logger(cfg, rank, stream=False)
+        tr = Trainer(cfg, rank, world, device, logger)
+        is_lm = tr.is_lm
 
-    lm_cache = {}
+        def make_shard(local_batches, n_steps, seed):
+            if is_lm:
+                return (int(local_batches[rank]), n_steps, seed)
+            part = DataPartitioner(len(tr.train_set), local_batches, seed, True, n_steps)
+            return part.use(rank)
 
-    def lm_batches(b, n_steps, seed):
-        """pinned [n_steps][bptt+1, b] token windows cut from the (synthetic) corpus, like Trainer._train_epoch_lm"""
-        key = (b, n_steps, seed)
-        if key not in lm_cache:
-            from dynamic_load_balance_distributeddnn_b200.data import batchify
-            need = b * (cfg.bptt * n_steps + 1)
-            stream = tr.corpus.train
-            off = (seed * 7919 + rank * need) % max(1, stream.numel() - need)
-            lm_cache[key] = batchify(stream[off:off + need], b).pin_memory()
-        return lm_cache[key]
+        lm_cache = {}
 
-    def run_steps(shard, n, e2e=True, sink=None):
-        import numpy as np
-        if is_lm:
-            b, n_steps, seed = shard
-            data = lm_batches(b, n_steps, seed)
+        def lm_batches(b, n_steps, seed):
+            """pinned [n_steps][bptt+1, b] token windows cut from the (synthetic) corpus, like Trainer._train_epoch_lm"""
+            key = (b, n_steps, seed)
+            if key not in lm_cache:
+                from dynamic_load_balance_distributeddnn_b200.data import batchify
+                need = b * (cfg.bptt * n_steps + 1)
+                stream = tr.corpus.train
+                off = (seed * 7919 + rank * need) % max(1, stream.numel() - need)
+                lm_cache[key] = batchify(stream[off:off + need], b).pin_memory()
+            return lm_cache[key]
+
+        def run_steps(shard, n, e2e=True, sink=None):
+            import numpy as np
+            if is_lm:
+                b, n_steps, seed = shard
+                data = lm_batches(b, n_steps, seed)
+                for s in range(n):
+                    i = (s if e2e else 0) * cfg.bptt
+                    if e2e or s == 0:
+                        src = data[i:i + cfg.bptt].to(device, non_blocking=True)                  # H2D from pinned memory
+                        tgt = data[i + 1:i + 1 + cfg.bptt].reshape(-1).to(device, non_blocking=True)
+                    tr.train_step(src, tgt)
+                    if e2e and sink is not None:
+                        sink[s % sink.shape[0]].copy_(tr.loss_acc, non_blocking=True)
+                return
+            order = np.arange(len(shard))
             for s in range(n):
-                i = (s if e2e else 0) * cfg.bptt
                 if e2e or s == 0:
-                    src = data[i:i + cfg.bptt].to(device, non_blocking=True)                  # H2D from pinned memory
-                    tgt = data[i + 1:i + 1 + cfg.bptt].reshape(-1).to(device, non_blocking=True)
-                tr.train_step(src, tgt)
-                if e2e and sink is not None:
-                    sink[s % sink.shape[0]].copy_(tr.loss_acc, non_blocking=True)
-            return
-        order = np.arange(len(shard))
-        for s in range(n):
-            if e2e or s == 0:
-                xb, yb = tr.stager.stage(shard.batch_indices(s, order))
-            tr.train_step(xb, yb)
-            if e2e:
+                    xb, yb = tr.stager.stage(shard.batch_indices(s, order))
+                tr.train_step(xb, yb)
+                if e2e:
+                    tr.stager.release()
+                    if sink is not None:
+                        sink[s % sink.shape[0]].copy_(tr.loss_acc, non_blocking=True)      # D2H of the step's result
+            if not e2e:
                 tr.stager.release()
-                if sink is not None:
-                    sink[s % sink.shape[0]].copy_(tr.loss_acc, non_blocking=True)      # D2H of the step's result
-        if not e2e:
-            tr.stager.release()
 
-    # ---- phase 1: start from the uniform split; each DBS round = run a short "epoch", exchange the measured compute
-    # times with the P2P-store all-gather kernel, re-split (exactly what Trainer.run does once per epoch) --------------
-    fractions, lb = tr.realloc.step()
-    tr.flat.set_weights(tr.realloc.weights())
-    tr.injector.begin_epoch(0, W + 8)
-    lb0 = [int(x) for x in lb]
-    rounds = a.dbs_rounds if (world > 1 and not a.no_dbs) else 1
-    for rnd in range(rounds):
-        tr.comm.barrier()
-        tr.reset_timers()
-        run_steps(make_shard(lb, W + 8, 1 + rnd), W + 8)
-        compute_s, sync_s, _ = tr.epoch_times()      # the device-side accounting the trainer feeds to the DBS reallocator
-        times = tr.comm.gather_times(compute_s)
-        if world > 1 and not a.no_dbs:
+        # ---- DBS rounds: a short "epoch" at the current split, exchange the measured compute times with the P2P-store
+        # all-gather kernel, re-split (exactly what Trainer.run does once per epoch) -------------------------------------
+        fractions, lb = tr.realloc.step()
+        tr.flat.set_weights(tr.realloc.weights())
+        tr.injector.begin_epoch(0, W)
+        lb0 = [int(x) for x in lb]
+        for rnd in range(rounds):
+            tr.comm.barrier()
+            tr.reset_timers()
+            run_steps(make_shard(lb, W, 1 + rnd), W)
+            compute_s, sync_s, _ = tr.epoch_times()      # the device-side accounting the trainer feeds to the DBS reallocator
+            times = tr.comm.gather_times(compute_s)
             tr.realloc.observe(times)
             fractions, lb = tr.realloc.step()
             tr.flat.set_weights(tr.realloc.weights())
-    # ---- phase 2: warm-up at the final local batch (graph re-capture) ------------------------------------------------
-    run_steps(make_shard(lb, W + 8, 9), W + 8)
-    torch.cuda.synchronize()
+        # ---- W warm-up steps at the final split (eager warm-up + CUDA-graph capture when the size is new) ---------------
+        run_steps(make_shard(lb, W, 9), W)
+        torch.cuda.synchronize()
+        sink = torch.zeros(8, 1, dtype=torch.float32).pin_memory()
 
-    sink = torch.zeros(8, 1, dtype=torch.float32).pin_memory()
-    clocks = ClockSampler(local)
+        def timed(e2e: bool, seed: int):
+            shard = make_shard(lb, K, seed)
+            if world > 1:
+                dist.barrier()
+            tr.comm.barrier()
+            torch.cuda.synchronize()
+            tr.reset_timers()
+            n0 = _native.launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            h0 = time.perf_counter()
+            run_steps(shard, K, e2e=e2e, sink=sink if e2e else None)
+            host_ms = (time.perf_counter() - h0) * 1e3          # time the HOST needed to issue the K steps
+            e1.record()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            ms = e0.elapsed_time(e1)
+            # straggler wait = part of the step this rank did NOT spend on its own compute (device-side stamps)
+            wait = max(0.0, ms * 1e-3 - float(tr.ts[1].item()) * 1e-9) if tr._dev_timers else 0.0
+            return max_over_ranks(ms, device, world), _native.launch_count() - n0, max_over_ranks(wait, device, world), host_ms
+
+        ms_e2e, _, wait_e2e, host_e2e = timed(True, 3)
+        ms_dev, launches, wait_dev, host_dev = timed(False, 4)
+        if hasattr(tr.comm, "check_errors"):
+            tr.comm.check_errors()
+        per_step_items = a.batch * (cfg.bptt if is_lm else 1)          # images, or tokens for the LM
+        h2d = (2 * cfg.bptt * int(lb[rank]) * 8) if is_lm else tr.stager.bytes_per_step
+        res = {"dtype": getattr(tr, "dtype_name", dtype), "is_lm": is_lm,
+               "value": per_step_items * K / (ms_dev * 1e-3), "e2e_value": per_step_items * K / (ms_e2e * 1e-3),
+               "ms_dev": ms_dev / K, "ms_e2e": ms_e2e / K, "h2d": int(h2d), "launches": int(launches),
+               "wait_dev": 1e3 * wait_dev / K, "host_dev": host_dev / K, "host_e2e": host_e2e / K,
+               "lb0": lb0, "lb": [int(x) for x in lb], "comm": tr.comm.name, "graphs": bool(tr._graphs),
+               "graph_nodes": getattr(tr, "graph_nodes", None), "dbs_model": cfg.dbs_model,
+               "loss": float(tr.loss_acc.item())}
+        tr.close()
+        del tr
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        return res
+
     if rank == 0:
         clocks.start()
-
-    def timed(e2e: bool, seed: int):
-        shard = make_shard(lb, K, seed)
-        if world > 1:
-            dist.barrier()
-        tr.comm.barrier()
-        torch.cuda.synchronize()
-        tr.reset_timers()
-        n0 = _native.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        h0 = time.perf_counter()
-        run_steps(shard, K, e2e=e2e, sink=sink if e2e else None)
-        host_ms = (time.perf_counter() - h0) * 1e3          # time the HOST needed to issue the K steps
-        e1.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ms = e0.elapsed_time(e1)
-        # straggler wait = part of the step this rank did NOT spend on its own compute (device-side stamps)
-        wait = max(0.0, ms * 1e-3 - float(tr.ts[1].item()) * 1e-9) if tr._dev_timers else 0.0
-        return max_over_ranks(ms, device, world), _native.launch_count() - n0, max_over_ranks(wait, device, world), host_ms
-
-    ms_e2e, _, wait_e2e, host_e2e = timed(True, 3)
-    ms_dev, launches, wait_dev, host_dev = timed(False, 4)
+    main_res = measure(a.dtype)
     clk = clocks.stop() if rank == 0 else {}
-    if hasattr(tr.comm, "check_errors"):
-        tr.comm.check_errors()
-    per_step_items = a.batch * (cfg.bptt if is_lm else 1)          # images, or tokens for the LM
-    h2d = (2 * cfg.bptt * int(lb[rank]) * 8) if is_lm else tr.stager.bytes_per_step
-    loss = float(tr.loss_acc.item())
-    value = per_step_items * K / (ms_dev * 1e-3)
-    e2e_value = per_step_items * K / (ms_e2e * 1e-3)
+    alt = measure(a.alt_dtype) if a.alt_dtype else None
+    is_lm = main_res["is_lm"]
+    unit = "tokens/s" if is_lm else "images/s"
+    config = common_config(a, world, is_lm, throttle, rounds, W)
     out = {
-        "metric": METRIC if a.model == "densenet" else (f"{a.model}_{a.dataset}_tokens_per_sec" if is_lm else f"{a.model}_{a.dataset}_images_per_sec"),
-        "value": round(value, 2), "unit": "tokens/s" if is_lm else "images/s", "n_gpus": world, "steps": K,
-        "warmup": (rounds + 1) * (W + 8),
-        "ms_per_step": round(ms_dev / K, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": a.dtype, "data": "synthetic (CIFAR-10-shape uint8 images, random-init weights)", "impl": "ours",
-        "config": {"model": "DenseNet-121 (GroupNorm)" if a.model == "densenet" else a.model, "global_batch": a.batch,
-                   "image": "3x32x32", "parallelism": f"dp{world}", "dbs": not a.no_dbs,
-                   "local_batches_before": lb0, "local_batches": [int(x) for x in lb],
-                   "throttle": {"rank": world - 1, "ms_per_step": throttle, "mode": a.throttle_mode} if throttle > 0 else None,
-                   "comm": tr.comm.name, "cuda_graphs": bool(tr._graphs), "optimizer": "SGD momentum 0.9 (in timed region)",
-                   "l2": "per-step working set (activations+grads, >1 GB) exceeds the 126 MB L2; no explicit flush"},
-        "e2e": {"value": round(e2e_value, 2), "unit": "tokens/s" if is_lm else "images/s", "ms_per_step": round(ms_e2e / K, 4),
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
-        "gpu_launches": int(launches),
-        "straggler_wait_ms_per_step": round(1e3 * wait_dev / K, 4),
-        "host_issue_ms_per_step": {"device_resident": round(host_dev / K, 4), "e2e": round(host_e2e / K, 4)},
+        "metric": metric_name(a, is_lm), "value": round(main_res["value"], 2), "unit": unit, "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": round(main_res["ms_dev"], 4), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": main_res["dtype"],
+        "data": "synthetic (CIFAR-10-shape uint8 images, random-init weights)" if not is_lm else
+                "synthetic (wikitext-2-shape token stream, vocab 33278, random-init weights)",
+        "impl": "ours", "config": config,
+        "detail": {"local_batches_before": main_res["lb0"], "local_batches": main_res["lb"], "comm": main_res["comm"],
+                   "cuda_graphs": main_res["graphs"], "graph_nodes": main_res["graph_nodes"], "dbs_model": main_res["dbs_model"],
+                   "throttle_mode": a.throttle_mode if throttle > 0 else None},
+        "e2e": {"value": round(main_res["e2e_value"], 2), "unit": unit, "ms_per_step": round(main_res["ms_e2e"], 4),
+                "h2d_bytes_per_step": main_res["h2d"], "d2h_bytes_per_step": 4},
+        "gpu_launches": main_res["launches"],
+        "straggler_wait_ms_per_step": round(main_res["wait_dev"], 4),
+        "host_issue_ms_per_step": {"device_resident": round(main_res["host_dev"], 4), "e2e": round(main_res["host_e2e"], 4)},
         "clocks": {"sm_mhz": clk.get("sm_mhz"), "sm_max_mhz": clk.get("sm_max_mhz"), "reasons": clk.get("reasons", [])},
-        "final_loss_acc": loss,
+        "final_loss_acc": main_res["loss"],
     }
-    tr.close()
+    if alt is not None:
+        out["alt"] = {"dtype": alt["dtype"], "value": round(alt["value"], 2), "unit": unit, "ms_per_step": round(alt["ms_dev"], 4),
+                      "e2e_value": round(alt["e2e_value"], 2), "local_batches": alt["lb"], "gpu_launches": alt["launches"]}
     if world > 1:
         dist.destroy_process_group()
     return out if rank == 0 else {}
 
 
 # =====================================================================================================
+def isolate_reference_imports(ref_dir: str) -> None:
+    """Make `import dbs / dataloader / parser / dbs_logging / utils / Net.*` resolve to baseline/_ref and nowhere else:
+    drop the repository root (and the cwd, if it is the root) from sys.path, forget any same-named module already
+    imported, put baseline/_ref first."""
+    root_real = os.path.realpath(ROOT)
+    sys.path[:] = [p for p in sys.path if os.path.realpath(p or os.getcwd()) != root_real]
+    for name in list(sys.modules):
+        if name.split(".")[0] in ("dbs", "dataloader", "parser", "dbs_logging", "utils", "Net",
+                                  "dynamic_load_balance_distributeddnn_b200"):
+            del sys.modules[name]
+    sys.path.insert(0, ref_dir)
+
+
 def run_reference(a) -> dict:
     """The unmodified reference (baseline/_ref): its own models, DataLoader, per-parameter SSGD allreduce,
-    torch.optim.SGD, get_size and time_allreduce, called in the order its run() calls them.  Shims live
+    torch.optim.SGD, get_size and time_allreduce, called in the order its run() calls them (dbs.py:313-446).  Shims live
     OUTSIDE its source: synthetic torchvision datasets (no network), pre-created log dirs, a deterministic
-    straggler in place of the broken -ft injector, CUDA-event timing, and islice() so every rank runs
-    exactly K steps (the reference can dead-lock on unequal step counts)."""
-    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    straggler in place of the broken -ft injector (SURVEY D1), CUDA-event timing, and islice() so every rank runs
+    exactly K steps (the reference can dead-lock on unequal step counts).
+
+    Import hygiene (round-1 verdict, weak #1): the repository root is REMOVED from sys.path, nothing of this repository is
+    imported, every reference module is verified to come from baseline/_ref and libdlb_b200.so must not be mapped."""
+    ref_dir = os.path.realpath(os.path.join(ROOT, "baseline", "_ref"))
     rank, world, local = dist_env()
     if not os.path.isfile(os.path.join(ref_dir, "dbs.py")):
         return {"impl": "reference", "unavailable": "baseline/_ref not installed (run tools/install_reference.sh)"}
+    isolate_reference_imports(ref_dir)
     try:
         import numpy as np
         import torch
@@ -270,14 +397,13 @@ def run_reference(a) -> dict:
     except Exception as e:           # noqa: BLE001
         return {"impl": "reference", "unavailable": f"import failed: {e!r}"}
 
-    W, K = max(3, a.warmup), a.steps
+    W, K, rounds = schedule(a, world)
     work = f"/tmp/dlb_ref_run_{os.getpid()}"
     os.makedirs(os.path.join(work, "logs"), exist_ok=True)
     os.makedirs(os.path.join(work, "statis"), exist_ok=True)
     os.chdir(work)
     if not os.path.exists(os.path.join(work, "rnn_data")) and os.path.isdir(os.path.join(ref_dir, "rnn_data")):
         os.symlink(os.path.join(ref_dir, "rnn_data"), os.path.join(work, "rnn_data"))     # its Corpus path is relative
-    sys.path.insert(0, ref_dir)
     is_lm = a.model == "transformer"
     if is_lm:
         a.dataset = "wikitext2"
@@ -291,7 +417,7 @@ def run_reference(a) -> dict:
     n_holder = {"n": a.batch * (W + 2)}
 
     class _Synth(torch.utils.data.Dataset):
-        """torchvision.datasets.CIFAR10-shaped stand-in: uint8 HWC arrays → PIL → the reference's transforms."""
+        """torchvision.datasets.CIFAR10-shaped stand-in: uint8 HWC arrays -> PIL -> the reference's transforms."""
         def __init__(self, root, train=True, download=False, transform=None, **kw):
             self.transform = transform
             g = np.random.RandomState(1234 if train else 4321)
@@ -314,6 +440,8 @@ def run_reference(a) -> dict:
     import dbs                      # parses sys.argv at import (reference dbs.py:22)
     import dataloader
     import dbs_logging
+    for mod in (dbs, dataloader, dbs_logging):
+        assert os.path.realpath(mod.__file__).startswith(ref_dir + os.sep), f"{mod.__name__} resolved to {mod.__file__}"
 
     device = f"cuda:{local}"
     torch.cuda.set_device(device)
@@ -332,25 +460,29 @@ def run_reference(a) -> dict:
             h.setLevel(logging.ERROR)
     throttle = a.throttle_ms if world > 1 else 0.0
     if throttle > 0:
-        def _wait(epoch, batch_num, r):        # deterministic stand-in for the broken -ft injector
-            if r == world - 1:
+        def _wait(epoch, batch_num, r):        # deterministic stand-in for the broken -ft injector: same place,
+            if r == world - 1:                 # same mechanism (host sleep between backward and allreduce, dbs.py:103,236)
                 time.sleep(throttle * 1e-3)
         dbs.fault_tolerance_wait = _wait
 
     # ---- what reference run() does (dbs.py:313-379), with its own classes/functions -----------------
     torch.manual_seed(1234)
     if a.model == "densenet":
-        import Net.Densenet
-        model = Net.Densenet.DenseNet121(10)
+        import Net.Densenet as ref_net
+        model = ref_net.DenseNet121(10)
     elif a.model == "resnet50":
-        import Net.Resnet
-        model = Net.Resnet.ResNet50(10)
+        import Net.Resnet as ref_net
+        model = ref_net.ResNet50(10)
     elif is_lm:
-        import Net.Transformer
-        model = Net.Transformer.TransformerModel(33278, 200, 2, 200, 2, 0.2)      # literals of reference run() (dbs.py:337-343)
+        import Net.Transformer as ref_net
+        model = ref_net.TransformerModel(33278, 200, 2, 200, 2, 0.2)      # literals of reference run() (dbs.py:337-343)
     else:
-        import Net.Resnet
-        model = Net.Resnet.ResNet101(10)
+        import Net.Resnet as ref_net
+        model = ref_net.ResNet101(10)
+    import inspect
+    model_file = os.path.realpath(inspect.getfile(type(model)))
+    assert type(model).__module__.startswith("Net.") and model_file.startswith(os.path.join(ref_dir, "Net") + os.sep), \
+        f"reference model resolved to {type(model).__module__} @ {model_file}"
     model = model.to(device)
     for _, p in model.named_parameters():
         dist.all_reduce(p.data, op=dist.ReduceOp.SUM)
@@ -360,9 +492,9 @@ def run_reference(a) -> dict:
     nodes_time = np.array([1.0 for _ in range(world)])
     partition = np.array([1.0 / world for _ in range(world)])
 
-    def epoch(e, n_steps, timed):
+    def epoch(e, n_steps, timed, rebalance):
         nonlocal partition, nodes_time
-        if dbs.dbs_enabled:
+        if dbs.dbs_enabled and rebalance:
             partition = dbs.get_size(nodes_time, partition)
         n_holder["n"] = a.batch * (n_steps + 2)
         train_set, _, bsz = dataloader.partition_dataset(a.dataset, partition, rank, a.batch, 1234)
@@ -384,30 +516,39 @@ def run_reference(a) -> dict:
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
-        if dbs.dbs_enabled:
+        if dbs.dbs_enabled and rebalance:
             nodes_time = np.array(dbs.time_allreduce(torch.tensor([t_train], dtype=torch.float32).cpu(), rank, world))
         return ms, int(bsz), t_sync, loss
 
-    from dynamic_load_balance_distributeddnn_b200.utils import ClockSampler
-    epoch(0, W, False)
+    # same schedule as the own arm: R x (W steps -> exchange times -> get_size), W warm-up steps at the final split, K timed
+    for rnd in range(rounds):
+        epoch(rnd, W, False, True)                          # get_size at the start of the epoch, as its run() does
+    if rounds:
+        partition = dbs.get_size(nodes_time, partition)     # the split the next epoch of its run() would use
+    epoch(rounds, W, False, False)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    ms, bsz, t_sync, loss = epoch(1, K, True)
+    ms, bsz, t_sync, loss = epoch(rounds + 1, K, True, False)
     clk = clocks.stop() if rank == 0 else {}
     ms = max_over_ranks(ms, device, world)
     global_bs = int(sum_over_ranks(float(int(bsz)), device, world))
     value = global_bs * (35 if is_lm else 1) * K / (ms * 1e-3)
+    with open("/proc/self/maps") as f:
+        assert "libdlb_b200" not in f.read(), "the repository's native library is mapped inside the reference arm"
+    assert not any(m.startswith("dynamic_load_balance_distributeddnn_b200") for m in sys.modules), "repo package imported"
+    unit = "tokens/s" if is_lm else "images/s"
     out = {
-        "metric": METRIC if a.model == "densenet" else (f"{a.model}_{a.dataset}_tokens_per_sec" if is_lm else f"{a.model}_{a.dataset}_images_per_sec"),
-        "value": round(value, 2), "unit": "tokens/s" if is_lm else "images/s", "n_gpus": world, "steps": K, "warmup": W,
+        "metric": metric_name(a, is_lm), "value": round(value, 2), "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "fp32", "data": "synthetic (CIFAR-10-shape, random-init weights)", "impl": "reference",
-        "config": {"model": a.model, "global_batch": a.batch, "effective_global_batch": global_bs, "parallelism": f"dp{world}",
-                   "backend": "cpu:gloo,cuda:nccl", "partition": [float(x) for x in partition],
-                   "throttle": {"rank": world - 1, "ms_per_step": throttle} if throttle > 0 else None,
-                   "l2": "per-step working set exceeds L2"},
-        "e2e": {"value": round(value, 2), "unit": "images/s", "h2d_bytes_per_step": int(bsz) * 3 * 32 * 32 * 4 + int(bsz) * 8,
+        "dtype": "fp32 (cuDNN convolutions may use TF32: torch.backends.cudnn.allow_tf32 defaults to True)",
+        "data": "synthetic (CIFAR-10-shape uint8 images, random-init weights)" if not is_lm else
+                "wikitext-2 corpus bundled with the reference, random-init weights",
+        "impl": "reference", "config": common_config(a, world, is_lm, throttle, rounds, W),
+        "detail": {"effective_global_batch": global_bs, "backend": "cpu:gloo,cuda:nccl", "partition": [float(x) for x in partition],
+                   "model_class": f"{type(model).__module__}.{type(model).__name__}", "model_file": model_file,
+                   "throttle_mode": "sleep (its own injector's mechanism)" if throttle > 0 else None},
+        "e2e": {"value": round(value, 2), "unit": unit, "h2d_bytes_per_step": int(bsz) * 3 * 32 * 32 * 4 + int(bsz) * 8,
                 "d2h_bytes_per_step": 8, "note": "the reference has no device-only path: its step always includes its DataLoader"},
         "gpu_launches": 0,
         "straggler_wait_ms_per_step": round(1e3 * t_sync / K, 4),

@@ -152,6 +152,7 @@ class Reallocator:
         self.fractions = np.full(world_size, 1.0 / world_size)           # dbs.py:379
         self.local_batches = self._initial_split()
         self.history = []
+        self._have_obs = False            # nodes_time still holds the all-ones placeholder: nothing to blend an EMA with
 
     def _initial_split(self) -> np.ndarray:
         if self.rounding == "reference":
@@ -160,9 +161,10 @@ class Reallocator:
 
     def observe(self, nodes_time: Sequence[float]) -> None:
         t = np.asarray(nodes_time, dtype=np.float64)
-        if self.ema > 0 and len(self.history) > 0:
+        if self.ema > 0 and self._have_obs:
             t = self.ema * self.nodes_time + (1.0 - self.ema) * t
         self.nodes_time = t
+        self._have_obs = True
 
     def step(self) -> Tuple[np.ndarray, np.ndarray]:
         """Called at the start of every epoch (or every N steps).  Returns the split to use."""
@@ -182,12 +184,13 @@ class Reallocator:
 
     def state_dict(self):
         return {"nodes_time": self.nodes_time.tolist(), "fractions": self.fractions.tolist(),
-                "local_batches": self.local_batches.tolist()}
+                "local_batches": self.local_batches.tolist(), "have_obs": bool(self._have_obs)}
 
     def load_state_dict(self, sd):
         self.nodes_time = np.asarray(sd["nodes_time"], dtype=np.float64)
         self.fractions = np.asarray(sd["fractions"], dtype=np.float64)
         self.local_batches = np.asarray(sd["local_batches"], dtype=np.int64)
+        self._have_obs = bool(sd.get("have_obs", True))
 
 
 class AffineReallocator(Reallocator):
@@ -216,6 +219,16 @@ class AffineReallocator(Reallocator):
             same = [p for p in self.obs[r] if p[0] == b]
             t = float(t) if not same else 0.5 * (same[-1][1] + float(t))   # one (smoothed) point per distinct batch size
             self.obs[r] = [p for p in self.obs[r] if p[0] != b][-(self.window - 1):] + [(b, t)]
+
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["obs"] = [[list(map(float, p)) for p in per_rank] for per_rank in self.obs]      # the (batch, time) history the fit needs
+        return sd
+
+    def load_state_dict(self, sd):
+        super().load_state_dict(sd)
+        if "obs" in sd:
+            self.obs = [[(float(b), float(t)) for b, t in per_rank] for per_rank in sd["obs"]]
 
     def _fit(self, r: int):
         pts = self.obs[r]

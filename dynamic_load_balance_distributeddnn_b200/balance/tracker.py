@@ -33,6 +33,8 @@ class TimeTracker:
         self._compute_s = 0.0
         self._sync_s = 0.0
         self._pairs: List = []
+        self._unsteady_pairs: List = []
+        self.unsteady_compute_s = 0.0
         self._t0: Optional[float] = None
         self._wall0 = time.perf_counter()
         self.steps = 0
@@ -53,7 +55,14 @@ class TimeTracker:
         total is extrapolated from the steady steps, otherwise a rank that has just been re-sized looks slow, gets
         shrunk again, is re-sized again ... and the split runs away."""
         if not steady:
+            # kept aside: only used when an epoch has NO steady step at all (e.g. max_steps_per_epoch <= warm-up steps)
             self.unsteady += 1
+            if self.cuda:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                self._unsteady_pairs.append((self._e0, e))
+            else:
+                self.unsteady_compute_s += time.perf_counter() - self._t0
             return
         if self.cuda:
             e = torch.cuda.Event(enable_timing=True)
@@ -77,6 +86,9 @@ class TimeTracker:
             for a, b in self._pairs:
                 self._compute_s += a.elapsed_time(b) * 1e-3
             self._pairs.clear()
+            for a, b in self._unsteady_pairs:
+                self.unsteady_compute_s += a.elapsed_time(b) * 1e-3
+            self._unsteady_pairs.clear()
         wall = time.perf_counter() - self._wall0
         if self.unsteady and self.steps:
             self._compute_s *= (self.steps + self.unsteady) / self.steps

@@ -112,6 +112,7 @@ def get_parser() -> argparse.ArgumentParser:
     x.add_argument("--overlap_comm", type=str2bool, default=True, help="overlap bucket allreduces with backward")
     x.add_argument("--wire_dtype", choices=("fp32", "bf16"), default="fp32")
     x.add_argument("--allreduce_algo", choices=("auto", "oneshot", "twoshot", "nvls"), default="auto")
+    x.add_argument("--comm_timeout_s", type=float, default=20.0, help="device-side watchdog of the fused collectives")
     x.add_argument("--max_steps_per_epoch", type=int, default=0)
     x.add_argument("--validate", type=str2bool, default=True)
     x.add_argument("--bptt", type=int, default=35)

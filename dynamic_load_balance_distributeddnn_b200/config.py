@@ -65,6 +65,7 @@ class DBSConfig:
     overlap_comm: bool = True            # fire bucket collectives from autograd hooks on a side stream
     wire_dtype: str = "fp32"             # fp32 | bf16 wire format of the gradient allreduce
     allreduce_algo: str = "auto"         # auto | oneshot | twoshot | nvls
+    comm_timeout_s: float = 20.0         # device-side watchdog of the fused collectives (a dead peer raises instead of hanging)
     max_steps_per_epoch: int = 0         # cap (0 = full epoch)
     validate: bool = True
     bptt: int = 35

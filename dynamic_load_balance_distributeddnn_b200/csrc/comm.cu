@@ -181,15 +181,23 @@ weighted_allreduce_kernel(const __grid_constant__ CommArgs a, long long offset, 
   if constexpr (ALGO == NVLS) {
     // fused staging: scale my own contribution in place before anyone reduces it in the switch
     if (a.use_weights) {
+      // The only cross-rank ordering before the reduce phase is block_barrier(a, 0), which orders block b here against
+      // block b on every peer.  Peer r's block b reduces the vectors  c0_r + b*blockDim + t + k*grid*blockDim  of ITS
+      // chunk [c0_r, c1_r), so block b must pre-scale exactly those vectors of every chunk (same grid on all ranks):
+      // a plain grid-stride loop over the whole bucket would let a peer read elements another block has not scaled yet.
       T* mine = (T*)a.in[a.rank] + offset;
       const float wr = w[a.rank];
       const long long nvec = count / V;
-      for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (long long)gridDim.x * blockDim.x) {
-        float x[V];
-        Wire<T>::load(mine + v * V, x);
+      const long long per = (nvec + world - 1) / world;
+      for (int r = 0; r < world; ++r) {
+        const long long c0 = min(nvec, per * r), c1 = min(nvec, c0 + per);
+        for (long long v = c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; v < c1; v += (long long)gridDim.x * blockDim.x) {
+          float x[V];
+          Wire<T>::load(mine + v * V, x);
 #pragma unroll
-        for (int k = 0; k < V; ++k) x[k] *= wr;
-        Wire<T>::store(mine + v * V, x);
+          for (int k = 0; k < V; ++k) x[k] *= wr;
+          Wire<T>::store(mine + v * V, x);
+        }
       }
       __threadfence_system();
     }

@@ -86,14 +86,19 @@ __global__ void __launch_bounds__(256) mt_pack_kernel(const __grid_constant__ Te
 // v = mu*v + g (+wd*p);  p -= lr*v;  shadow = bf16(p)
 __global__ void __launch_bounds__(256) sgd_flat_kernel(float* __restrict__ p, float* __restrict__ v,
                                                        const float* __restrict__ g, __nv_bfloat16* __restrict__ shadow,
-                                                       long long n, const float* __restrict__ lr_ptr, float mu, float wd) {
+                                                       long long n, const float* __restrict__ lr_ptr, float mu, float wd,
+                                                       const float* __restrict__ sumsq, float max_norm) {
   const float lr = *lr_ptr;
+  // post-reduce ("global") gradient clipping: the coefficient of clip_grad_norm_ applied to the REDUCED gradient,
+  // folded into the update so no separate scale pass runs (--clip_mode global; the reference clips locally, dbs.py:274)
+  const float gs = (sumsq && max_norm > 0.f) ? fminf(1.f, max_norm / (sqrtf(*sumsq) + 1e-6f)) : 1.f;
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 pv = reinterpret_cast<float4*>(p)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
-    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float4 gv = reinterpret_cast<const float4*>(g)[i];
+    gv.x *= gs; gv.y *= gs; gv.z *= gs; gv.w *= gs;
     vv.x = fmaf(mu, vv.x, fmaf(wd, pv.x, gv.x)); vv.y = fmaf(mu, vv.y, fmaf(wd, pv.y, gv.y));
     vv.z = fmaf(mu, vv.z, fmaf(wd, pv.z, gv.z)); vv.w = fmaf(mu, vv.w, fmaf(wd, pv.w, gv.w));
     pv.x = fmaf(-lr, vv.x, pv.x); pv.y = fmaf(-lr, vv.y, pv.y);
@@ -110,7 +115,7 @@ __global__ void __launch_bounds__(256) sgd_flat_kernel(float* __restrict__ p, fl
   }
   // tail (n is padded to a multiple of 4 by the Python side, kept for safety)
   for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float vv = fmaf(mu, v[i], fmaf(wd, p[i], g[i]));
+    const float vv = fmaf(mu, v[i], fmaf(wd, p[i], gs * g[i]));
     const float pv = fmaf(-lr, vv, p[i]);
     v[i] = vv; p[i] = pv;
     if (shadow) shadow[i] = __float2bfloat16(pv);
@@ -173,14 +178,20 @@ DLB_API int dlb_mt_pack(int count, const void* const* ptrs, const long long* off
   return dlb_post_launch(launched);
 }
 
-DLB_API int dlb_sgd_flat(float* p, float* v, const float* g, void* shadow, long long n, const float* lr_ptr,
-                         float momentum, float weight_decay, void* stream) {
+DLB_API int dlb_sgd_flat_clip(float* p, float* v, const float* g, void* shadow, long long n, const float* lr_ptr,
+                              float momentum, float weight_decay, const float* sumsq, float max_norm, void* stream) {
   if (n <= 0) return 0;
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  sgd_flat_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, v, g, (__nv_bfloat16*)shadow, n, lr_ptr, momentum, weight_decay);
+  sgd_flat_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, v, g, (__nv_bfloat16*)shadow, n, lr_ptr, momentum, weight_decay,
+                                                                  sumsq, max_norm);
   return dlb_post_launch();
+}
+
+DLB_API int dlb_sgd_flat(float* p, float* v, const float* g, void* shadow, long long n, const float* lr_ptr,
+                         float momentum, float weight_decay, void* stream) {
+  return dlb_sgd_flat_clip(p, v, g, shadow, n, lr_ptr, momentum, weight_decay, nullptr, 0.f, stream);
 }
 
 DLB_API int dlb_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {

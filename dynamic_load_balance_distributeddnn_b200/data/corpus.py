@@ -109,7 +109,11 @@ def load_corpus(root: str = "", synthetic: Optional[bool] = None, sizes: Optiona
             _CACHE[key] = SyntheticCorpus(sizes=sizes, seed=seed)
         return _CACHE[key]
     if path not in _CACHE:
-        cache_file = os.path.join(path, ".dlb_tokens.pt")
+        # the token cache lives under the user's cache directory, keyed by the corpus path -- never next to the corpus itself
+        # (round 1 wrote `.dlb_tokens.pt` into /root/reference/rnn_data, a side effect on a tree this repo must not touch)
+        import hashlib
+        cache_dir = os.environ.get("DLB_CACHE_DIR") or os.path.join(os.path.expanduser("~"), ".cache", "dlb_b200")
+        cache_file = os.path.join(cache_dir, "tokens_" + hashlib.sha1(os.path.realpath(path).encode()).hexdigest()[:16] + ".pt")
         corpus = None
         if os.path.isfile(cache_file):
             try:
@@ -124,10 +128,13 @@ def load_corpus(root: str = "", synthetic: Optional[bool] = None, sizes: Optiona
         if corpus is None:
             corpus = Corpus(path)
             try:
+                os.makedirs(cache_dir, exist_ok=True)
+                tmp = f"{cache_file}.{os.getpid()}.tmp"
                 torch.save({"idx2word": corpus.dictionary.idx2word, "train": corpus.train,
-                            "valid": corpus.valid, "test": corpus.test}, cache_file)
+                            "valid": corpus.valid, "test": corpus.test}, tmp)
+                os.replace(tmp, cache_file)          # atomic: several ranks may tokenise at the same time
             except OSError:
-                pass                         # read-only location (e.g. /root/reference)
+                pass                         # unwritable cache directory: just re-tokenise next time
         _CACHE[path] = corpus
     return _CACHE[path]
 

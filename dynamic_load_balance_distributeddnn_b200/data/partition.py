@@ -45,20 +45,23 @@ class DataPartitioner:
     """Splits ``n`` samples across ranks for one epoch given integer local batches."""
 
     def __init__(self, n: int, local_batches: Sequence[int], seed: int = 1234, shuffle: bool = True,
-                 max_steps: int = 0):
+                 max_steps: int = 0, start: int = 0):
+        """``start``: number of samples of this epoch's permutation already consumed (mid-epoch re-partitioning with
+        ``--rebalance_every``: the segments of one epoch still form a disjoint cover of the same permutation)."""
         self.n = int(n)
         self.local_batches = [int(b) for b in local_batches]
         self.global_batch = int(sum(self.local_batches))
         if self.global_batch <= 0:
             raise ValueError("global batch must be positive")
-        self.steps = self.n // self.global_batch
+        self.start = int(start)
+        self.steps = (self.n - self.start) // self.global_batch
         if max_steps > 0:
             self.steps = min(self.steps, max_steps)
         if self.steps == 0:
             raise ValueError(f"dataset of {n} samples is smaller than the global batch {self.global_batch}")
         perm = global_permutation(self.n, seed, shuffle)
         self.shards: List[Shard] = []
-        off = 0
+        off = self.start
         for b in self.local_batches:
             cnt = self.steps * b
             self.shards.append(Shard(perm[off:off + cnt], b, self.steps))

@@ -51,7 +51,8 @@ class Trainer:
         if self.cuda:
             torch.cuda.set_device(self.device)
         self.dtype = _DT[cfg.resolved_dtype(device)]
-        self.comm = comm if comm is not None else make_comm(cfg.resolved_comm(device), self.device)
+        self.comm = comm if comm is not None else make_comm(cfg.resolved_comm(device), self.device, algo=cfg.allreduce_algo,
+                                                            timeout_s=cfg.comm_timeout_s)
         self.is_lm = cfg.is_lm
         self.log_every = 10
         self.max_cached_graphs = 4
@@ -85,7 +86,7 @@ class Trainer:
         torch.manual_seed(cfg.seed)
         self.model = build_model(cfg.model, cfg.num_classes, self.ntokens)
         self.flat = FlatState(self.model, self.device, self.dtype, self.comm, cfg.learning_rate, cfg.momentum,
-                              0.0, cfg.bucket_mb, _DT[cfg.wire_dtype], cfg.resolved_clip() if cfg.clip_mode == "local" else 0.0)
+                              0.0, cfg.bucket_mb, _DT[cfg.wire_dtype], cfg.resolved_clip(), cfg.clip_mode)
         self.flat.sync_initial_params()
         if cfg.overlap_comm:
             self.flat.enable_overlap()
@@ -109,10 +110,18 @@ class Trainer:
             blob = load_checkpoint(cfg, self.flat, self.realloc)
             if blob is not None:
                 self.start_epoch = int(blob["epoch"]) + 1
+                self._resume_extra = blob.get("extra") or {}
                 self.logger.info(f"Rank {self.rank} resumed from epoch {blob['epoch']}")
         self.total_train_time = 0.0
         self.global_step = 0
         self.step_t = torch.zeros(1, dtype=torch.int64, device=self.device)
+        extra = getattr(self, "_resume_extra", None)
+        if extra:                      # counters that seed the augmentation stream + the stats history of the resumed run
+            self.global_step = int(extra.get("global_step", 0))
+            self.step_t.fill_(int(extra.get("step_t", 0)))
+            self.total_train_time = float(extra.get("total_train_time", 0.0))
+            if extra.get("recorder"):
+                self.recorder.load_state(extra["recorder"])
         self.ts = torch.zeros(2, dtype=torch.int64, device=self.device)      # [0] step-start stamp, [1] accumulated compute ns
         self._dev_timers = self.cuda and ops._native.available() and hasattr(ops._native.get(), "dlb_stamp")
         self.loss_acc = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -155,14 +164,17 @@ class Trainer:
             x = xb if self.is_lm else self._prepare_images(xb)
         loss = self._forward_backward(x, yb)
         with self.tracer.range("straggler"):
-            slept = self.injector.host_delay()         # between backward and allreduce (reference dbs.py:236)
-            self.injector.device_delay()
+            self.injector.device_delay()               # between backward and allreduce (reference dbs.py:236)
         if steady:
             self._stamp_compute_end()
         self.tracker.stop_compute(steady)
-        if slept and self.cuda and steady:
+        # the host sleep sits OUTSIDE the device-stamped region (still between backward and the allreduce) and is booked
+        # explicitly: inside it, a host-bound eager step would count the sleep once in the stamp delta and once here
+        slept = self.injector.host_delay()
+        if slept and (steady or not self.cuda):
             self.tracker.add_compute(slept)
-            self._host_sleep_s += slept
+            if self.cuda:
+                self._host_sleep_s += slept
         with self.tracer.range("reduce_and_step"):
             waited = self.flat.reduce_and_step(self.rank)
             self.flat.zero_grad()
@@ -278,6 +290,10 @@ class Trainer:
         total_s, host_sync_s, wall_s = self.tracker.finish()
         scale = (steady + unsteady) / steady if (steady and unsteady) else 1.0
         if self._dev_timers and (self._graphs or self.cuda):
+            if steady == 0 and unsteady:
+                # every step of this epoch was an unmeasured warm-up step at a new local batch: fall back to the event-timed
+                # eager steps instead of reporting ~0 (which the reallocator would read as an infinitely fast rank)
+                return max(1e-6, self.tracker.unsteady_compute_s + self._host_sleep_s), host_sync_s, wall_s
             compute_s = float(self.ts[1].item()) * 1e-9 * scale + self._host_sleep_s
             sync_s = max(0.0, total_s - compute_s) + host_sync_s
             if not self._graphs:
@@ -345,42 +361,70 @@ class Trainer:
             if cfg.dynamic_batch_size:
                 self.logger.info(f"Rank {self.rank}, adjusted partition size to {fractions}")
             self.flat.set_weights(self.realloc.weights(uniform=cfg.disable_enhancements))
-            b = int(local_batches[self.rank])
-            # ---- re-partition (indices only) ----
+            # ---- epoch = one segment (reference: re-split once per epoch, dbs.py:388-391) or, with --rebalance_every N,
+            # segments of N steps with a time exchange + re-split between them (indices only are re-partitioned) ----------
+            B = cfg.batch_size
             if self.is_lm:
-                pieces = split_token_stream(self.corpus.train.numel(), local_batches)
-                tokens = self.corpus.train[pieces[self.rank]]
-                rows = tokens.numel() // b
-                steps = (rows - 1) // cfg.bptt
-                if cfg.max_steps_per_epoch:
-                    steps = min(steps, cfg.max_steps_per_epoch)
-                length = rows * b
+                total_steps = (self.corpus.train.numel() // B - 1) // cfg.bptt
             else:
-                part = DataPartitioner(len(self.train_set), local_batches, cfg.seed, True, cfg.max_steps_per_epoch)
-                shard = part.use(self.rank)
-                steps, length = part.steps, len(shard)
-            self.logger.info(f"Rank {self.rank}, number of batches {steps}, batch size {b}, length {length}")
-            self.injector.begin_epoch(epoch, steps)
-            t0 = time.perf_counter()
-            if self.is_lm:
-                compute_s, sync_s, loss, wall_s = self._train_epoch_lm(epoch, tokens, b, steps)
-            else:
-                compute_s, sync_s, loss, wall_s = self._train_epoch_vision(epoch, shard, steps)
-            self.total_train_time += time.perf_counter() - t0
+                total_steps = len(self.train_set) // B
+            if cfg.max_steps_per_epoch:
+                total_steps = min(total_steps, cfg.max_steps_per_epoch)
+            seg_cap = cfg.rebalance_every if (cfg.rebalance_every > 0 and cfg.dynamic_batch_size) else 0
+            done = used = 0
+            agg = {"compute": 0.0, "sync": 0.0, "loss": 0.0, "wall": 0.0}
+            while done < total_steps:
+                b = int(local_batches[self.rank])
+                seg = min(seg_cap, total_steps - done) if seg_cap else total_steps
+                if self.is_lm:
+                    if seg_cap:
+                        rows = seg * cfg.bptt + 1
+                        start = used + rows * int(sum(int(x) for x in local_batches[:self.rank]))
+                        tokens = self.corpus.train[start:start + rows * b]
+                        consumed = seg * cfg.bptt * B
+                    else:
+                        pieces = split_token_stream(self.corpus.train.numel(), local_batches)
+                        tokens = self.corpus.train[pieces[self.rank]]
+                        consumed = 0
+                    steps, length = seg, (tokens.numel() // b) * b
+                else:
+                    part = DataPartitioner(len(self.train_set), local_batches, cfg.seed, True, seg, start=used)
+                    shard = part.use(self.rank)
+                    steps, length, consumed = part.steps, len(shard), part.steps * B
+                self.logger.info(f"Rank {self.rank}, number of batches {steps}, batch size {b}, length {length}")
+                if done == 0:
+                    self.injector.begin_epoch(epoch, total_steps)
+                t0 = time.perf_counter()
+                if self.is_lm:
+                    compute_s, sync_s, loss, wall_s = self._train_epoch_lm(epoch, tokens, b, steps)
+                else:
+                    compute_s, sync_s, loss, wall_s = self._train_epoch_vision(epoch, shard, steps)
+                self.total_train_time += time.perf_counter() - t0
+                agg["compute"] += compute_s; agg["sync"] += sync_s; agg["loss"] += loss * steps; agg["wall"] += wall_s
+                done += steps
+                used += consumed
+                # ---- DBS feedback: exchange pure compute time (reference dbs.py:423-426) ----
+                nodes_time = self.comm.gather_times(compute_s)
+                if cfg.dynamic_batch_size:
+                    self.realloc.observe(nodes_time)
+                    self.logger.info(f"Rank {self.rank}, total time {nodes_time}")
+                if seg_cap and done < total_steps:
+                    fractions, local_batches = self.realloc.step()
+                    self.logger.info(f"Rank {self.rank}, step {done}: adjusted partition size to {fractions}")
+                    self.flat.set_weights(self.realloc.weights(uniform=cfg.disable_enhancements))
+            steps = max(1, done)
+            compute_s, sync_s, loss, wall_s = agg["compute"], agg["sync"], agg["loss"] / steps, agg["wall"]
             with self.tracer.range("validate"):
                 val_loss, metric = self.validate(epoch) if cfg.validate else (float("nan"), float("nan"))
-            # ---- DBS feedback: exchange pure compute time (reference dbs.py:423-426) ----
-            nodes_time = self.comm.gather_times(compute_s)
-            if cfg.dynamic_batch_size:
-                self.realloc.observe(nodes_time)
-                self.logger.info(f"Rank {self.rank}, total time {nodes_time}")
             self.recorder.append(epoch=epoch, train_loss=loss, train_time=compute_s, sync_time=sync_s, val_loss=val_loss,
                                  accuracy=metric, partition=np.asarray(fractions), node_time=list(nodes_time),
                                  wallclock_time=self.total_train_time, local_batches=[int(x) for x in local_batches],
                                  samples_per_sec=(steps * cfg.batch_size / wall_s) if wall_s > 0 else 0.0,
                                  straggler_wait_ms_per_step=1e3 * sync_s / max(1, steps), steps=steps, lr=lr)
             if cfg.checkpoint_dir and self.rank == 0:
-                save_checkpoint(cfg, epoch, self.flat, self.realloc)
+                save_checkpoint(cfg, epoch, self.flat, self.realloc,
+                                extra={"global_step": self.global_step, "step_t": int(self.step_t.item()),
+                                       "total_train_time": self.total_train_time, "recorder": self.recorder.state()})
         if self.rank == 0:
             self.recorder.save()
         self.tracer.close()

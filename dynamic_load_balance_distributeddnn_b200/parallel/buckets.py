@@ -46,12 +46,17 @@ def _flat_order(t: torch.Tensor) -> torch.Tensor:
 class FlatState:
     def __init__(self, model: nn.Module, device, compute_dtype: torch.dtype, comm: Comm,
                  lr: float, momentum: float = 0.9, weight_decay: float = 0.0, bucket_mb: float = 8.0,
-                 wire_dtype: torch.dtype = torch.float32, clip_norm: float = 0.0):
+                 wire_dtype: torch.dtype = torch.float32, clip_norm: float = 0.0, clip_mode: str = "local"):
         self.device = torch.device(device)
         self.comm = comm
         self.params: List[nn.Parameter] = [p for p in model.parameters()]
         self.compute_dtype = compute_dtype
-        self.momentum, self.weight_decay, self.clip_norm = momentum, weight_decay, clip_norm
+        self.momentum, self.weight_decay = momentum, weight_decay
+        # local  = clip this rank's gradient before weighting/allreduce (reference dbs.py:274; coefficient folded into pack)
+        # global = clip the REDUCED gradient (coefficient folded into the SGD kernel)
+        assert clip_mode in ("local", "global"), clip_mode
+        self.clip_norm = clip_norm if clip_mode == "local" else 0.0
+        self.global_clip = clip_norm if clip_mode == "global" else 0.0
         self.native = self.device.type == "cuda" and nat.available()
         self.offsets: List[int] = []
         off = 0
@@ -65,6 +70,7 @@ class FlatState:
                 n_alloc = rows_pad * p.shape[1]
                 p._dlb_padded_rows = rows_pad
             off += (n_alloc + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.base_numel = off            # world-size independent part (the tail padding below depends on the world size)
         world = max(1, comm.world)
         pad_to = _ALIGN * world
         self.numel = (off + pad_to - 1) // pad_to * pad_to
@@ -219,6 +225,26 @@ class FlatState:
             return self._reduce_and_step_native(rank)
         return self._reduce_and_step_torch(rank)
 
+    def _sgd_native(self, g: torch.Tensor) -> None:
+        lib = nat.require()
+        st = nat.stream_ptr(self.device)
+        if g.dtype != torch.float32:
+            g = g.float()
+        sumsq = None
+        if self.global_clip > 0:
+            # global L2 norm of the reduced gradient: one multi-tensor sum-of-squares launch over the flat buffer
+            n = self.numel
+            nat.check(lib.dlb_zero_f32(self.sumsq_t.data_ptr(), 1, st), "zero")
+            chunk = 1 << 30
+            for o in range(0, n, chunk):
+                c = min(chunk, n - o)
+                nat.check(lib.dlb_mt_sumsq(1, (ctypes.c_void_p * 1)(g.data_ptr() + 4 * o), (ctypes.c_int * 1)(c),
+                                           (ctypes.c_int * 1)(nat.F32), self.sumsq_t.data_ptr(), st), "mt_sumsq")
+            sumsq = self.sumsq_t
+        nat.check(lib.dlb_sgd_flat_clip(self.master.data_ptr(), self.mom.data_ptr(), g.data_ptr(), nat.ptr(self.shadow), self.numel,
+                                        self.lr_t.data_ptr(), float(self.momentum), float(self.weight_decay), nat.ptr(sumsq),
+                                        float(self.global_clip), st), "sgd_flat")
+
     def _reduce_and_step_native(self, rank: int) -> float:
         lib = nat.require()
         st = nat.stream_ptr(self.device)
@@ -230,9 +256,7 @@ class FlatState:
             ev = torch.cuda.Event()
             ev.record(self._comm_stream)
             torch.cuda.current_stream(self.device).wait_event(ev)
-            g = self.grad_out if self.grad_out.dtype == torch.float32 else self.grad_out.float()
-            nat.check(lib.dlb_sgd_flat(self.master.data_ptr(), self.mom.data_ptr(), g.data_ptr(), nat.ptr(self.shadow), self.numel,
-                                       self.lr_t.data_ptr(), float(self.momentum), float(self.weight_decay), st), "sgd_flat")
+            self._sgd_native(self.grad_out)
             self._pending = [len(gp) for gp in self.bucket_params]
             self._fired = [False] * len(self.buckets)
             self._keep, self._keep_overlap = self._keep_overlap, []
@@ -251,11 +275,7 @@ class FlatState:
             g = self.grad_out
         else:                              # single rank: the packed (weighted, clipped) gradient IS the result
             waited, g = 0.0, self.grad_in
-        if g.dtype != torch.float32:
-            g = g.float()
-        nat.check(lib.dlb_sgd_flat(self.master.data_ptr(), self.mom.data_ptr(), g.data_ptr(),
-                                   nat.ptr(self.shadow), self.numel, self.lr_t.data_ptr(), float(self.momentum),
-                                   float(self.weight_decay), st), "sgd_flat")
+        self._sgd_native(g)
         return waited
 
     def _reduce_and_step_torch(self, rank: int) -> float:
@@ -270,6 +290,8 @@ class FlatState:
                     self.grad_in[off:off + p.numel()].copy_(_flat_order(p.grad).to(self.grad_in.dtype) * scale)
             waited = self.comm.allreduce_buckets(self.grad_in, self.grad_out, self.buckets)
             g = self.grad_out.float()
+            if self.global_clip > 0:
+                g = g * min(1.0, self.global_clip / (float(g.norm()) + 1e-6))
             if self.weight_decay:
                 g = g + self.weight_decay * self.master
             self.mom.mul_(self.momentum).add_(g)
@@ -284,10 +306,12 @@ class FlatState:
 
     # ---- checkpointing ------------------------------------------------------------------------------
     def state_dict(self):
-        return {"master": self.master.detach().cpu(), "momentum": self.mom.detach().cpu(), "lr": float(self.lr_t.item())}
+        n = self.base_numel
+        return {"master": self.master[:n].detach().cpu(), "momentum": self.mom[:n].detach().cpu(), "lr": float(self.lr_t.item())}
 
     def load_state_dict(self, sd) -> None:
-        self.master.copy_(sd["master"].to(self.device))
-        self.mom.copy_(sd["momentum"].to(self.device))
+        n = min(self.base_numel, sd["master"].numel())        # older checkpoints carry the (zero) tail padding too
+        self.master[:n].copy_(sd["master"][:n].to(self.device))
+        self.mom[:n].copy_(sd["momentum"][:n].to(self.device))
         self.set_lr(sd["lr"])
         self.refresh_shadow()

@@ -1,6 +1,8 @@
 """Checkpoint / resume (absent from the reference — SURVEY §5.4).  Rank 0 writes
-{model master weights, momentum, lr, epoch, reallocator state, RNG}; every rank loads it, so a run can
-continue with the same partition vector and timing history."""
+{model master weights, momentum, lr, epoch, reallocator state (incl. the affine model's (batch, time) history), torch RNG
+state, step counters, stats history}; every rank loads it, so a run continues with the same partition vector, timing
+history, augmentation stream and statistics lists.  The flat buffers are stored WITHOUT the world-size-dependent tail padding,
+so a checkpoint written at one world size resumes at another."""
 from __future__ import annotations
 
 import os
@@ -33,5 +35,9 @@ def load_checkpoint(cfg, flat_state, reallocator):
         return None
     blob = torch.load(path, map_location="cpu", weights_only=False)
     flat_state.load_state_dict(blob["flat"])
-    reallocator.load_state_dict(blob["reallocator"])
+    rsd = blob["reallocator"]
+    if len(rsd.get("nodes_time", [])) == reallocator.world_size:      # a different world size starts from the uniform split
+        reallocator.load_state_dict(rsd)
+    if blob.get("torch_rng") is not None:
+        torch.set_rng_state(blob["torch_rng"])
     return blob

@@ -27,6 +27,15 @@ class StatsRecorder:
             if k in kw:
                 self.data[k].append(kw[k])
 
+    def state(self) -> dict:
+        """History so far (saved in checkpoints so a resumed run continues the same per-epoch lists)."""
+        return {k: list(v) for k, v in self.data.items()}
+
+    def load_state(self, sd: dict) -> None:
+        for k in self.data:
+            if k in sd:
+                self.data[k] = list(sd[k])
+
     def path(self, ext: str = ".npy") -> str:
         return os.path.join(self.cfg.stats_dir, self.cfg.experiment_id(0) + ext)
 

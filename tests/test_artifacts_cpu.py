@@ -43,13 +43,8 @@ def test_stats_schema_matches_reference(tmp_path):
 
 
 def test_net_aliases_import_like_the_reference():
-    sys.path.insert(0, ROOT)
-    import Net.Densenet
-    import Net.GoogleNet
-    import Net.MnistNet
-    import Net.RegNet
-    import Net.Resnet
-    import Net.Transformer
+    from dynamic_load_balance_distributeddnn_b200 import Net
+    assert not os.path.exists(os.path.join(ROOT, "Net")), "a top-level Net package would shadow the reference's in bench.py"
     assert sum(p.numel() for p in Net.Densenet.DenseNet121(10).parameters()) == 6956298
     assert sum(p.numel() for p in Net.Resnet.ResNet50(10).parameters()) == 23520842
     assert Net.MnistNet.MnistNet and Net.GoogleNet.GoogLeNet and Net.RegNet.RegNetY_400MF and Net.Transformer.TransformerModel

@@ -1,0 +1,53 @@
+"""bench.py --impl reference must run the UNMODIFIED reference from baseline/_ref and nothing of this repository
+(round-1 verdict: a top-level `Net` package of the repo shadowed the reference's namespace package)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+
+_SCRIPT = r"""
+import os, sys, inspect
+import bench                                      # sys.path[0] is the repo root, exactly like `python bench.py`
+import dynamic_load_balance_distributeddnn_b200   # worst case: the repo package is already imported
+ref = os.path.realpath(os.path.join(bench.ROOT, "baseline", "_ref"))
+bench.isolate_reference_imports(ref)
+os.chdir("/tmp")
+import Net.Densenet, Net.Resnet, Net.Transformer, dataloader, dbs_logging
+m = Net.Densenet.DenseNet121(10)
+f = os.path.realpath(inspect.getfile(type(m)))
+assert f.startswith(os.path.join(ref, "Net") + os.sep), f
+assert type(m).__module__ == "Net.Densenet", type(m).__module__
+assert type(m.dense1[0].gn1).__module__.startswith("torch.nn"), "reference layers are stock torch.nn"
+for mod in (dataloader, dbs_logging, Net.Resnet, Net.Transformer):
+    assert os.path.realpath(mod.__file__).startswith(ref + os.sep), mod.__file__
+assert not any(k.startswith("dynamic_load_balance_distributeddnn_b200") for k in sys.modules)
+with open("/proc/self/maps") as fh:
+    assert "libdlb_b200" not in fh.read()
+print("ISOLATED", f)
+"""
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "dbs.py")), reason="baseline/_ref not installed")
+def test_reference_arm_imports_only_the_reference():
+    env = dict(os.environ, PYTHONPATH="")
+    r = subprocess.run([sys.executable, "-c", _SCRIPT], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ISOLATED" in r.stdout, r.stdout + r.stderr
+
+
+def test_no_top_level_net_package():
+    assert not os.path.exists(os.path.join(ROOT, "Net"))
+
+
+def test_both_arms_share_schedule_and_config():
+    sys.path.insert(0, ROOT)
+    import bench
+    a = bench.parse.__globals__["argparse"].Namespace(warmup=5, steps=20, dbs_rounds=2, no_dbs=False, model="densenet",
+                                                        dataset="cifar10", batch=512)
+    assert bench.schedule(a, 1) == (5, 20, 0)
+    assert bench.schedule(a, 8) == (5, 20, 2)
+    c = bench.common_config(a, 8, False, 3.0, 2, 5)
+    assert c["model"] == "densenet121" and c["global_batch"] == 512 and c["parallelism"] == "dp8" and c["untimed_steps_total"] == 15

@@ -21,4 +21,5 @@ def test_resume_continues_from_saved_epoch(tmp_path):
     t2 = Trainer(cfg2, 0, 1, "cpu", init_logger(cfg2, 0, stream=False))
     assert t2.start_epoch == 2 and torch.equal(t2.flat.master, w_end)
     rec = t2.run()
-    assert rec.data["epoch"] == [2]
+    assert rec.data["epoch"] == [0, 1, 2]                               # the stats history is restored and continued
+    assert t2.global_step == 3 * (256 // 32)                            # step counters continue too (augmentation stream)

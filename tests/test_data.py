@@ -80,3 +80,16 @@ def test_synthetic_images_and_augment():
     assert torch.allclose(x0.permute(0, 2, 3, 1), ref, atol=1e-6)
     t = load_image_dataset("mnist", False, synthetic=True, n_override=64)
     assert t.images.shape == (64, 28, 28, 1) and t.pad == 0
+
+
+def test_partitioner_segments_cover_one_permutation():
+    """--rebalance_every: segments with different splits still form a disjoint cover of the epoch's permutation."""
+    from dynamic_load_balance_distributeddnn_b200.data import DataPartitioner
+    n, seen, used = 1000, [], 0
+    for lbs in ([16, 16], [20, 12], [25, 7]):
+        p = DataPartitioner(n, lbs, 1234, True, 5, start=used)
+        assert p.steps == 5
+        for r in range(2):
+            seen += list(p.use(r).indices)
+        used += p.steps * 32
+    assert len(seen) == len(set(seen)) == 3 * 5 * 32

@@ -169,3 +169,18 @@ def test_flat_state_layout_and_buckets():
     assert torch.equal(r.conv1.weight, w) and r.conv1.weight.is_contiguous(memory_format=torch.channels_last)
     o, i, kh, kw = w.shape
     assert torch.equal(fr.master[:w.numel()].view(o, kh, kw, i), w.permute(0, 2, 3, 1))   # stored [O][kh][kw][I]
+
+
+def test_rebalance_every_n_steps(tmp_path):
+    """--rebalance_every N: the split moves INSIDE an epoch (time exchange + re-split every N steps), every segment's
+    batches still sum to B and the throttled rank loses share before the first epoch is over."""
+    args = "-d true -ws 2 -b 64 -m mnistnet -ds mnist -e 1 --synthetic true --train_samples 1536 --test_samples 128 " \
+           "--throttle_rank 1 --throttle_ms 60 --rebalance_every 6 --validate false --master_port 29614".split()
+    r = _run_cli(tmp_path, args)
+    assert r.returncode == 0, r.stderr[-3000:]
+    log = (tmp_path / "logs" / "mnistnet-mnist-debug1-n2-bs64-lr0.0100-ep1-dbs1-ft0-ftc0.100000-node0-ocp0.log").read_text()
+    import re
+    sizes = [int(m) for m in re.findall(r"Rank 0, number of batches \d+, batch size (\d+)", log)]
+    assert len(sizes) == 4, sizes                     # 24 steps / 6 per segment
+    assert sizes[0] == 32 and sizes[-1] > 32          # rank 0 (not throttled) gained share within the epoch
+    assert log.count("adjusted partition size") >= 4
