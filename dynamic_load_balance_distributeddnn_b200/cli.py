@@ -83,7 +83,9 @@ def get_parser() -> argparse.ArgumentParser:
     x.add_argument("--comm", choices=("auto", "gloo", "nccl", "symm"), default="auto",
                    help="gradient transport: symm = fused sm_100a P2P/NVLS kernels (default on GPU), "
                         "nccl = A/B baseline, gloo = CPU debug")
-    x.add_argument("--dtype", choices=("auto", "fp32", "bf16"), default="auto")
+    x.add_argument("--dtype", choices=("auto", "fp32", "tf32", "bf16"), default="auto",
+                   help="bf16 (default on GPU): bf16 compute, fp32 master weights/accumulation; tf32 / fp32: fp32 storage, TF32 "
+                        "tensor-core math (the reference's precision class)")
     x.add_argument("--synthetic", type=str2bool, default=None,
                    help="force synthetic data of the dataset's shape (auto when files are absent)")
     x.add_argument("--train_samples", type=int, default=0)

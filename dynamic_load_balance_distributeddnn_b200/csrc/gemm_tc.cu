@@ -1,4 +1,5 @@
-// Persistent warp-specialised bf16 GEMM on the 5th-gen tensor cores (sm_100a):
+// Persistent warp-specialised GEMM on the 5th-gen tensor cores (sm_100a), bf16 (kind::f16) or fp32 storage with TF32
+// math (kind::tf32) -- template parameter E; in bytes both flavours use the same shared-memory layouts (tc_common.cuh):
 //
 //     D[M, N] (+)= epilogue( prologue(A)[M, K] * B[N, K]^T )          fp32 accumulation in TMEM
 //
@@ -27,14 +28,13 @@
 namespace {
 
 constexpr int BM = 128;            // UMMA_M (cta_group::1)
-constexpr int BK = 64;             // 64 bf16 = 128 bytes = one SWIZZLE_128B atom row
-constexpr int UMMA_K = 16;
+// BK = Elt<E>::kAtom elements = 128 bytes = one SWIZZLE_128B atom row; UMMA_K = Elt<E>::kUmmaK (32 bytes of K)
 constexpr int kNumEpiWarps = 4;
 constexpr int kProWarps = 8;       // prologue-transform warps (PRO_GN only): 16 KB per stage must clear in < ~380 cycles
 
 struct GemmParams {
   int M, N, K;
-  void* d;            // output, bf16, row-major with row stride ldd (elements)
+  void* d;            // output (element type E), row-major with row stride ldd (elements)
   long long ldd;
   int accumulate_out; // (reserved)
   // PRO_GN: per-(sample, k) affine coefficients a,b fp32 [num_samples][K] (row n = pixel_row / rows_per_sample)
@@ -52,17 +52,21 @@ struct GemmParams {
   int conv_sign;                // +1 forward (x[h+dy, w+dx]), -1 dgrad (dy[h-dy, w-dx])
 };
 
-template <int BN> struct Cfg {
-  static constexpr int kStages = BN >= 256 ? 3 : (BN >= 128 ? 5 : 6);
-  static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+template <typename E, int BN> struct Cfg {
+  static constexpr int kEB = Elt<E>::kBytes;
+  static constexpr int kABytes = BM * 128;                         // 128 rows x one 128-byte swizzle row of K
+  static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  // epilogue staging: per epilogue warp, (BN/64) boxes of [32 rows][64 cols] bf16 = 4 KB each, 128B-swizzled,
+  // epilogue staging: per epilogue warp, kBoxes boxes of [32 rows][128 bytes] = 4 KB each, 128B-swizzled,
   // drained with cp.async.bulk.tensor stores (fully coalesced, tails clipped by the tensor map)
-  static constexpr int kHalves = (BN + 63) / 64;
-  static constexpr int kEpiBytes = kNumEpiWarps * kHalves * 4096;
+  static constexpr int kBoxes = (BN * kEB + 127) / 128;
+  static constexpr int kEpiBytes = kNumEpiWarps * kBoxes * 4096;
+  static constexpr int kStagesWanted = BN >= 256 ? 3 : (BN >= 128 ? 5 : 6);
+  static constexpr int kStagesFit = (227 * 1024 - kEpiBytes - 1024 - 256) / kStageBytes;
+  static constexpr int kStages = kStagesWanted < kStagesFit ? kStagesWanted : kStagesFit;
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(kStages >= 2, "tile does not fit");
 };
 
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator (+ idle), 3 = idle (keeps epilogue warps at
@@ -72,11 +76,16 @@ template <int BN> struct Cfg {
 // through an MN-major shared-memory descriptor, so no transposed copy of the weights is ever made.
 // CONV3: implicit-GEMM 3x3 convolution (see GemmParams); with B_MN it is the data-gradient (flipped taps, weights
 // consumed untransposed through a 3-D tensor map {Cin, 9, Cout}).
-template <int BN, bool PRO_GN, bool EPI_STATS, bool B_MN = false, bool CONV3 = false>
+template <typename E, int BN, bool PRO_GN, bool EPI_STATS, bool B_MN = false, bool CONV3 = false>
 __global__ void __launch_bounds__(PRO_GN ? 512 : 256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<E, BN>;
+  using EL = Elt<E>;
+  constexpr int BK = EL::kAtom;
+  constexpr int UMMA_K = EL::kUmmaK;
+  constexpr int kMnBox = BK * 128;                 // bytes of one MN-major B box: [BK k-rows][128 bytes of n]
+  constexpr int kMnBoxes = (BN * EL::kBytes) / 128;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* epi_base = smem + C::kStages * C::kStageBytes;                  // 1024-byte aligned (stage sizes are)
@@ -141,7 +150,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tma_load_4d(sa, &tmap_a, fb, kc * BK, dx, h0 + dy, img);
             if constexpr (B_MN) {
 #pragma unroll
-              for (int gi = 0; gi < BN / 64; ++gi) tma_load_3d(sb + gi * 8192, &tmap_b, fb, n0 + gi * 64, tap, kc * BK);
+              for (int gi = 0; gi < kMnBoxes; ++gi) tma_load_3d(sb + gi * kMnBox, &tmap_b, fb, n0 + gi * BK, tap, kc * BK);
             } else {
               tma_load_2d(sb, &tmap_b, fb, tap * p.conv_C + kc * BK, n0);
             }
@@ -149,7 +158,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tma_load_2d(sa, &tmap_a, fb, kb * BK, m0);
             if constexpr (B_MN) {
 #pragma unroll
-              for (int gi = 0; gi < BN / 64; ++gi) tma_load_2d(sb + gi * 8192, &tmap_b, fb, n0 + gi * 64, kb * BK);
+              for (int gi = 0; gi < kMnBoxes; ++gi) tma_load_2d(sb + gi * kMnBox, &tmap_b, fb, n0 + gi * BK, kb * BK);
             } else {
               tma_load_2d(sb, &tmap_b, fb, kb * BK, n0);
             }
@@ -161,8 +170,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (B_MN ? (1u << 16) : 0u) |
+      // instruction descriptor: D=f32, A/B format (bf16 = 1, tf32 = 2) at bits 7 / 10, B major at bit 16, N=BN, M=128
+      const uint32_t idesc = (1u << 4) | (EL::kFmt << 7) | (EL::kFmt << 10) | (B_MN ? (1u << 16) : 0u) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -175,12 +184,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
           const uint32_t sb = sa + C::kABytes;
-          const uint64_t adesc = make_smem_desc(sa), bdesc = B_MN ? make_smem_desc_mn(sb) : make_smem_desc(sb);
+          const uint64_t adesc = make_smem_desc(sa), bdesc = B_MN ? make_smem_desc_mn(sb, kMnBox) : make_smem_desc(sb);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            // K-major: advance 32 bytes (16 bf16) inside the 128-byte swizzle atom: +2 in 16-byte units;
-            // MN-major: advance 16 k-rows of 128 bytes: +128
-            umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)((B_MN ? 128 : 2) * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            // K-major: advance 32 bytes (one UMMA_K) inside the 128-byte swizzle atom: +2 in 16-byte units;
+            // MN-major: advance UMMA_K k-rows of 128 bytes: +8*UMMA_K
+            EL::mma(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)((B_MN ? 8 * UMMA_K : 2) * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(smem_u32(&empty_bar[stage]));            // frees the smem stage when these MMAs retire
           if (kb == num_kb - 1) umma_commit(smem_u32(&tmem_full[acc]));
@@ -193,7 +202,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===================================== epilogue =========================================
     const int q = warp & 3;                                     // TMEM lane quadrant owned by this warp
     int acc = 0; uint32_t acc_phase = 0;
-    uint8_t* stage_buf = epi_base + q * (C::kHalves * 4096);
+    uint8_t* stage_buf = epi_base + q * (C::kBoxes * 4096);
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m0 = (t / num_n) * BM, n0 = (t % num_n) * BN;
       mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
@@ -207,27 +216,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-        uint32_t packed[16];
+        // 32 accumulator columns -> 32*kBytes bytes of the output row = kCh 16-byte chunks of staging box `bx`
+        constexpr int kCh = 32 * EL::kBytes / 16;                   // 4 (bf16) or 8 (fp32)
+        uint32_t packed[kCh * 4];
+        if constexpr (EL::kBytes == 2) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-          packed[j] = *reinterpret_cast<uint32_t*>(&h);
+          for (int j = 0; j < 16; ++j) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            packed[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) packed[j] = v[j];
         }
         const int col = n0 + c0;
         {
-          // box `c0/64`: [32 rows][128 B], 16-byte chunk j of row r at r*128 + ((j ^ (r & 7)) << 4)
-          const uint32_t box = smem_u32(stage_buf + (c0 >> 6) * 4096 + lane * 128);
-          const int jb = (c0 & 32) ? 4 : 0;
+          // box `bx`: [32 rows][128 B], 16-byte chunk j of row r at r*128 + ((j ^ (r & 7)) << 4)
+          const int byte0 = c0 * EL::kBytes;
+          const int bx = byte0 >> 7;
+          const uint32_t box = smem_u32(stage_buf + bx * 4096 + lane * 128);
+          const int jb = (byte0 & 127) >> 4;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
+          for (int j = 0; j < kCh; ++j)
             sts128(box + (((jb + j) ^ (lane & 7)) << 4), make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]));
-          if ((c0 & 32) || c0 + 32 >= BN) {
-            // a 64-column box (or the final partial one) is complete: hand it to the TMA store engine
+          if ((((c0 + 32) * EL::kBytes) & 127) == 0 || c0 + 32 >= BN) {
+            // a 128-byte-wide box (or the final partial one) is complete: hand it to the TMA store engine
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0 && n0 + (c0 & ~63) < p.N && m0 + q * 32 < p.M) {
+            const int ncol = n0 + bx * BK;
+            if (lane == 0 && ncol < p.N && m0 + q * 32 < p.M) {
               asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                           ::"l"(&tmap_d), "r"(smem_u32(stage_buf + (c0 >> 6) * 4096)), "r"(n0 + (c0 & ~63)), "r"(m0 + q * 32)
+                           ::"l"(&tmap_d), "r"(smem_u32(stage_buf + bx * 4096)), "r"(ncol), "r"(m0 + q * 32)
                            : "memory");
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
@@ -238,12 +257,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           // (host guarantees rows_per_sample % 32 == 0).  Transpose-reduce: after 5 exchange steps lane j
           // holds the total of column c0 + j over the warp's 32 rows.
           float s[32], ss[32];
+          if constexpr (EL::kBytes == 2) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&packed[j]));
-            if (!row_ok) { f.x = 0.f; f.y = 0.f; }
-            s[2 * j] = f.x; s[2 * j + 1] = f.y;
-            ss[2 * j] = f.x * f.x; ss[2 * j + 1] = f.y * f.y;
+            for (int j = 0; j < 16; ++j) {
+              float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&packed[j]));
+              if (!row_ok) { f.x = 0.f; f.y = 0.f; }
+              s[2 * j] = f.x; s[2 * j + 1] = f.y;
+              ss[2 * j] = f.x * f.x; ss[2 * j + 1] = f.y * f.y;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float f = row_ok ? __uint_as_float(v[j]) : 0.f;
+              s[j] = f; ss[j] = f * f;
+            }
           }
 #pragma unroll
           for (int step = 0; step < 5; ++step) {
@@ -305,12 +332,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           raw[i] = lds128(sa + r * 128 + ((cc ^ (r & 7)) << 4));
         }
         int cur = -1;
-        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
-        if (uniform) {
-          const float4* ca = reinterpret_cast<const float4*>(p.pro_a + (long long)s_first * p.pro_ld + kb * BK + cc * 8);
-          const float4* cb = reinterpret_cast<const float4*>(p.pro_b + (long long)s_first * p.pro_ld + kb * BK + cc * 8);
-          a0 = __ldg(ca); a1 = __ldg(ca + 1); b0 = __ldg(cb); b1 = __ldg(cb + 1);
-        }
+        float ca[8], cb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { ca[i] = 0.f; cb[i] = 0.f; }
+        const long long coff = (long long)kb * BK + cc * EL::kPer16;
+        if (uniform) load_coef<E>(p.pro_a + (long long)s_first * p.pro_ld + coff, p.pro_b + (long long)s_first * p.pro_ld + coff, ca, cb);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = r_base + 32 * i;
@@ -318,22 +344,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const bool live = uniform || grow < p.M;
           const int sample = uniform ? s_first : min(grow, p.M - 1) / p.rows_per_sample;
           if (!uniform && sample != cur) {
-            // coefficient rows are padded to a multiple of BK and zero-filled by the host (a = b = 0 beyond K)
-            const float4* ca = reinterpret_cast<const float4*>(p.pro_a + (long long)sample * p.pro_ld + kb * BK + cc * 8);
-            const float4* cb = reinterpret_cast<const float4*>(p.pro_b + (long long)sample * p.pro_ld + kb * BK + cc * 8);
-            a0 = __ldg(ca); a1 = __ldg(ca + 1); b0 = __ldg(cb); b1 = __ldg(cb + 1);
+            // coefficient rows are padded to a multiple of 64 and zero-filled by the host (a = b = 0 beyond K)
+            load_coef<E>(p.pro_a + (long long)sample * p.pro_ld + coff, p.pro_b + (long long)sample * p.pro_ld + coff, ca, cb);
             cur = sample;
           }
-          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw[i]);
-          float2 f;
-          f = __bfloat1622float2(h[0]);
-          h[0] = __floats2bfloat162_rn(fmaxf(fmaf(a0.x, f.x, b0.x), 0.f), fmaxf(fmaf(a0.y, f.y, b0.y), 0.f));
-          f = __bfloat1622float2(h[1]);
-          h[1] = __floats2bfloat162_rn(fmaxf(fmaf(a0.z, f.x, b0.z), 0.f), fmaxf(fmaf(a0.w, f.y, b0.w), 0.f));
-          f = __bfloat1622float2(h[2]);
-          h[2] = __floats2bfloat162_rn(fmaxf(fmaf(a1.x, f.x, b1.x), 0.f), fmaxf(fmaf(a1.y, f.y, b1.y), 0.f));
-          f = __bfloat1622float2(h[3]);
-          h[3] = __floats2bfloat162_rn(fmaxf(fmaf(a1.z, f.x, b1.z), 0.f), fmaxf(fmaf(a1.w, f.y, b1.w), 0.f));
+          affine_relu_chunk<E>(raw[i], ca, cb);
           if (!live) raw[i] = make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
@@ -378,24 +393,33 @@ struct WgradParams {
   int rows_per_sample;
 };
 
-template <int BN> struct WCfg {
-  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 5 : 6);
-  static constexpr int kBoxBytes = 64 * 64 * 2;                  // 64 channels x 64 pixel rows
-  static constexpr int kABytes = 2 * kBoxBytes;                  // 128 output channels
-  static constexpr int kBBytes = (BN / 64) * kBoxBytes;
+template <typename E, int BN> struct WCfg {
+  static constexpr int kEB = Elt<E>::kBytes;
+  static constexpr int kBoxBytes = 64 * 128;                       // 64 pixel rows x 128 bytes of channels (64 bf16 / 32 fp32)
+  static constexpr int kABoxes = 128 * kEB / 128;                  // 128 output channels
+  static constexpr int kBBoxes = BN * kEB / 128;
+  static constexpr int kABytes = kABoxes * kBoxBytes;
+  static constexpr int kBBytes = kBBoxes * kBoxBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagesWanted = BN >= 256 ? 4 : (BN >= 128 ? 5 : 6);
+  static constexpr int kStagesFit = (227 * 1024 - 1024 - 256) / kStageBytes;
+  static constexpr int kStages = kStagesWanted < kStagesFit ? kStagesWanted : kStagesFit;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static_assert(kStages >= 2, "tile does not fit");
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BN, bool PRO_GN>
+template <typename E, int BN, bool PRO_GN>
 __global__ void __launch_bounds__(PRO_GN ? 512 : 256, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x, const WgradParams p) {
-  using C = WCfg<BN>;
+  using C = WCfg<E, BN>;
+  using EL = Elt<E>;
+  constexpr int UMMA_K = EL::kUmmaK;
+  constexpr int kAtom = EL::kAtom;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* bar_base = smem + C::kStages * C::kStageBytes;
@@ -457,18 +481,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
           const uint32_t sb = sa + C::kABytes;
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_expect_tx(fb, C::kStageBytes);
-          tma_load_2d(sa, &tmap_dy, fb, co0, r);
-          tma_load_2d(sa + C::kBoxBytes, &tmap_dy, fb, co0 + 64, r);
 #pragma unroll
-          for (int gi = 0; gi < BN / 64; ++gi) tma_load_2d(sb + gi * C::kBoxBytes, &tmap_x, fb, ci0 + gi * 64, r);
+          for (int gi = 0; gi < C::kABoxes; ++gi) tma_load_2d(sa + gi * C::kBoxBytes, &tmap_dy, fb, co0 + gi * kAtom, r);
+#pragma unroll
+          for (int gi = 0; gi < C::kBBoxes; ++gi) tma_load_2d(sb + gi * C::kBoxBytes, &tmap_x, fb, ci0 + gi * kAtom, r);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // D=f32, A=B=bf16, BOTH MN-major (bits 15, 16), N=BN, M=128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+      // D=f32, A/B format, BOTH MN-major (bits 15, 16), N=BN, M=128
+      const uint32_t idesc = (1u << 4) | (EL::kFmt << 7) | (EL::kFmt << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -484,11 +508,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
           const uint32_t sb = sa + C::kABytes;
-          const uint64_t adesc = make_smem_desc_mn(sa), bdesc = make_smem_desc_mn(sb);
+          const uint64_t adesc = make_smem_desc_mn(sa, C::kBoxBytes), bdesc = make_smem_desc_mn(sb, C::kBoxBytes);
 #pragma unroll
           for (int k = 0; k < 64 / UMMA_K; ++k) {
-            // advance 16 pixel rows = 2048 bytes along K: +128 in 16-byte units
-            umma_f16(tmem_d, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (first && k == 0) ? 0u : 1u);
+            // advance UMMA_K pixel rows of 128 bytes along K: +8*UMMA_K in 16-byte units
+            EL::mma(tmem_d, adesc + (uint64_t)(8 * UMMA_K * k), bdesc + (uint64_t)(8 * UMMA_K * k), idesc, (first && k == 0) ? 0u : 1u);
           }
           first = false;
           umma_commit(smem_u32(&empty_bar[stage]));
@@ -528,33 +552,32 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (PRO_GN && warp >= 8) {
-    // X tile: (BN/64) boxes of [64 pixel rows][64 channels].  thread -> one chunk column (8 channels) of one
+    // X tile: kBBoxes boxes of [64 pixel rows][128 bytes of channels].  thread -> one chunk column (16 bytes) of one
     // box and every (256/cols)-th pixel row; coefficients stay in registers down the rows.
     const int tp = threadIdx.x - 256;          // 0..255
-    constexpr int kBoxes = BN / 64;
-    constexpr int kCols = kBoxes * 8;          // chunk columns in the tile: 8, 16 or 32
-    constexpr int kRowStep = 256 / kCols;      // 32, 16, 8
+    constexpr int kBoxes = C::kBBoxes;
+    constexpr int kCols = kBoxes * 8;          // chunk columns in the tile: 8, 16, 32 (or 64 for fp32 BN = 256)
+    constexpr int kRowStep = 256 / kCols > 0 ? 256 / kCols : 1;
+    static_assert(kCols <= 256, "tile too wide for the transform warps");
     const int ccg = tp % kCols, r_base = tp / kCols;
     const int box = ccg >> 3, cc = ccg & 7;
     int stage = 0; uint32_t phase = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
       int sp, co0, ci0; decode(u, sp, co0, ci0);
       const int r0 = sp * p.rows_per_split, r1 = min(p.M, r0 + p.rows_per_split);
-      const int cbase = ci0 + box * 64 + cc * 8;
+      const int cbase = ci0 + box * kAtom + cc * EL::kPer16;
       const bool in_range = cbase < p.pro_ld;            // coefficient rows are padded to a multiple of 64
       for (int rr = r0; rr < r1; rr += 64) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         const uint32_t sb = smem_u32(smem + stage * C::kStageBytes + C::kABytes + box * C::kBoxBytes);
         int cur = -1;
-        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+        float ca[8], cb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { ca[i] = 0.f; cb[i] = 0.f; }
         const int s_first = rr / p.rows_per_sample;
         const bool uniform = in_range && (rr + 64 <= p.M) && ((rr + 63) / p.rows_per_sample == s_first);
-        if (uniform) {
-          const float4* ca = reinterpret_cast<const float4*>(p.pro_a + (long long)s_first * p.pro_ld + cbase);
-          const float4* cb = reinterpret_cast<const float4*>(p.pro_b + (long long)s_first * p.pro_ld + cbase);
-          a0 = __ldg(ca); a1 = __ldg(ca + 1); b0 = __ldg(cb); b1 = __ldg(cb + 1);
-        }
-        constexpr int kIters = 64 / kRowStep;          // 2, 4 or 8 chunks per thread per stage
+        if (uniform) load_coef<E>(p.pro_a + (long long)s_first * p.pro_ld + cbase, p.pro_b + (long long)s_first * p.pro_ld + cbase, ca, cb);
+        constexpr int kIters = 64 / kRowStep;          // chunks per thread per stage
         constexpr int kBatch = kIters < 4 ? kIters : 4;
 #pragma unroll
         for (int i0 = 0; i0 < kIters; i0 += kBatch) {
@@ -571,25 +594,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
             const bool live = uniform || (grow < p.M && in_range);
             const int sample = uniform ? s_first : min(grow, p.M - 1) / p.rows_per_sample;
             if (!uniform && sample != cur && in_range) {
-              const float4* ca = reinterpret_cast<const float4*>(p.pro_a + (long long)sample * p.pro_ld + cbase);
-              const float4* cb = reinterpret_cast<const float4*>(p.pro_b + (long long)sample * p.pro_ld + cbase);
-              a0 = __ldg(ca); a1 = __ldg(ca + 1); b0 = __ldg(cb); b1 = __ldg(cb + 1);
+              load_coef<E>(p.pro_a + (long long)sample * p.pro_ld + cbase, p.pro_b + (long long)sample * p.pro_ld + cbase, ca, cb);
               cur = sample;
             }
-            if (live) {
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw[j]);
-              float2 f;
-              f = __bfloat1622float2(h[0]);
-              h[0] = __floats2bfloat162_rn(fmaxf(fmaf(a0.x, f.x, b0.x), 0.f), fmaxf(fmaf(a0.y, f.y, b0.y), 0.f));
-              f = __bfloat1622float2(h[1]);
-              h[1] = __floats2bfloat162_rn(fmaxf(fmaf(a0.z, f.x, b0.z), 0.f), fmaxf(fmaf(a0.w, f.y, b0.w), 0.f));
-              f = __bfloat1622float2(h[2]);
-              h[2] = __floats2bfloat162_rn(fmaxf(fmaf(a1.x, f.x, b1.x), 0.f), fmaxf(fmaf(a1.y, f.y, b1.y), 0.f));
-              f = __bfloat1622float2(h[3]);
-              h[3] = __floats2bfloat162_rn(fmaxf(fmaf(a1.z, f.x, b1.z), 0.f), fmaxf(fmaf(a1.w, f.y, b1.w), 0.f));
-            } else {
-              raw[j] = make_uint4(0u, 0u, 0u, 0u);
-            }
+            if (live) affine_relu_chunk<E>(raw[j], ca, cb);
+            else raw[j] = make_uint4(0u, 0u, 0u, 0u);
           }
 #pragma unroll
           for (int j = 0; j < kBatch; ++j) {
@@ -612,10 +621,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
   }
 }
 
-template <int BN, bool PRO, bool STATS, bool BMN = false, bool CONV3 = false>
+template <typename E, int BN, bool PRO, bool STATS, bool BMN = false, bool CONV3 = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p, int sms, cudaStream_t st) {
-  using C = Cfg<BN>;
-  auto kern = gemm_tc_kernel<BN, PRO, STATS, BMN, CONV3>;
+  using C = Cfg<E, BN>;
+  auto kern = gemm_tc_kernel<E, BN, PRO, STATS, BMN, CONV3>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
@@ -628,156 +637,18 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
   return dlb_post_launch();
 }
 
-template <int BN>
+template <typename E, int BN>
 int dispatch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p, bool pro, bool stats, int sms, cudaStream_t st,
              bool b_mn = false) {
-  if constexpr (BN >= 64) {
-    if (b_mn) return launch<BN, false, false, true>(ta, tb, td, p, sms, st);
+  if constexpr (BN * Elt<E>::kBytes >= 128) {
+    if (b_mn) return launch<E, BN, false, false, true>(ta, tb, td, p, sms, st);
   }
-  if (pro && stats) return launch<BN, true, true>(ta, tb, td, p, sms, st);
-  if (pro) return launch<BN, true, false>(ta, tb, td, p, sms, st);
-  if (stats) return launch<BN, false, true>(ta, tb, td, p, sms, st);
-  return launch<BN, false, false>(ta, tb, td, p, sms, st);
+  if (pro && stats) return launch<E, BN, true, true>(ta, tb, td, p, sms, st);
+  if (pro) return launch<E, BN, true, false>(ta, tb, td, p, sms, st);
+  if (stats) return launch<E, BN, false, true>(ta, tb, td, p, sms, st);
+  return launch<E, BN, false, false>(ta, tb, td, p, sms, st);
 }
 
-}  // namespace
-
-// D[M,N] = A[M,K] * B[K,N]   with B given row-major [K][N] (row stride ldb): dgrad of a 1x1 conv / linear
-// (dX = dY * W with W = [Cout=K][Cin=N]) without a transposed weight copy.
-DLB_API int dlb_gemm_tc_bmn(const void* a, long long lda, const void* b, long long ldb, void* d, long long ldd, int M, int N, int K,
-                            int sm_limit, void* stream) {
-  if (M <= 0 || N <= 0 || K <= 0) return 0;
-  if ((K % 8) || (N % 8) || (lda % 8) || (ldb % 8) || (ldd % 8) || ((uintptr_t)a & 15) || ((uintptr_t)b & 15) || ((uintptr_t)d & 15)) return -3;
-  static int sm_count = 0;
-  if (!sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  }
-  int sms = sm_count;
-  if (sm_limit > 0 && sm_limit < sms) sms = sm_limit;
-  const int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
-  CUtensorMap ta, tb, td;
-  int rc = make_map(&ta, a, M, K, lda, BM);
-  if (rc) return rc - 10;
-  rc = make_map(&tb, b, K, N, ldb, 64);                 // boxes of [64 k-rows][64 n]
-  if (rc) return rc - 20;
-  rc = make_map(&td, d, M, N, ldd, 32);
-  if (rc) return rc - 30;
-  GemmParams p;
-  p.M = M; p.N = N; p.K = K; p.d = d; p.ldd = ldd; p.accumulate_out = 0;
-  p.pro_a = nullptr; p.pro_b = nullptr; p.pro_ld = 0; p.rows_per_sample = M; p.stats = nullptr; p.stats_ns = 0;
-  p.conv_H = p.conv_W = p.conv_C = 0; p.conv_kchunks = 1; p.conv_sign = 1;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (bn == 64) return dispatch<64>(ta, tb, td, p, false, false, sms, st, true);
-  if (bn == 128) return dispatch<128>(ta, tb, td, p, false, false, sms, st, true);
-  return dispatch<256>(ta, tb, td, p, false, false, sms, st, true);
-}
-
-// D[M,N] (bf16, row stride ldd) = pro(A[M,K] (bf16, row stride lda)) * B[N,K]^T (bf16, row stride ldb).
-//   pro_a/pro_b (optional): fp32 [M / rows_per_sample][K] affine coefficients -> A' = relu(a*A + b)
-//   stats (optional): fp32 table [M / rows_per_sample][stats_ns] accumulating (sum, sumsq) per output column;
-//                     must be zeroed by the caller.
-// Requirements: K % 8 == 0, lda % 8 == 0, ldb % 8 == 0, 16-byte aligned base pointers; with stats or prologue
-// rows_per_sample % 32 == 0 (stats) / any (prologue).
-DLB_API int dlb_gemm_tc(const void* a, long long lda, const void* b, long long ldb, void* d, long long ldd, int M, int N, int K,
-                        const float* pro_a, const float* pro_b, long long pro_ld, int rows_per_sample, float* stats, long long stats_ns,
-                        int sm_limit, void* stream) {
-  if (M <= 0 || N <= 0 || K <= 0) return 0;
-  if ((K % 8) || (lda % 8) || (ldb % 8) || ((uintptr_t)a & 15) || ((uintptr_t)b & 15)) return -3;
-  if ((ldd % 8) || ((uintptr_t)d & 15) || (N % 8)) return -6;
-  if (stats && (rows_per_sample % 32)) return -4;
-  if (pro_a && ((pro_ld % BK) || pro_ld < K || ((uintptr_t)pro_a & 15) || ((uintptr_t)pro_b & 15))) return -5;
-  static int sm_count = 0;
-  if (!sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  }
-  int sms = sm_count;
-  if (sm_limit > 0 && sm_limit < sms) sms = sm_limit;
-  const int bn = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
-  CUtensorMap ta, tb;
-  int rc = make_map(&ta, a, M, K, lda, BM);
-  if (rc) return rc;
-  rc = make_map(&tb, b, N, K, ldb, bn);
-  if (rc) return rc;
-  CUtensorMap td;
-  rc = make_map(&td, d, M, N, ldd, 32);                 // output boxes: 32 rows x 64 columns, 128B swizzle
-  if (rc) return rc;
-  GemmParams p;
-  p.M = M; p.N = N; p.K = K; p.d = d; p.ldd = ldd; p.accumulate_out = 0;
-  p.pro_a = pro_a; p.pro_b = pro_b; p.pro_ld = pro_ld; p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : M;
-  p.stats = stats; p.stats_ns = stats_ns;
-  p.conv_H = p.conv_W = p.conv_C = 0; p.conv_kchunks = 1; p.conv_sign = 1;
-  cudaStream_t st = (cudaStream_t)stream;
-  const bool pro = pro_a != nullptr, sts = stats != nullptr;
-  switch (bn) {
-    case 32: return dispatch<32>(ta, tb, td, p, pro, sts, sms, st);
-    case 64: return dispatch<64>(ta, tb, td, p, pro, sts, sms, st);
-    case 128: return dispatch<128>(ta, tb, td, p, pro, sts, sms, st);
-    default: return dispatch<256>(ta, tb, td, p, pro, sts, sms, st);
-  }
-}
-
-namespace {
-template <int BN, bool PRO>
-int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const WgradParams& p, int grid, cudaStream_t st) {
-  using C = WCfg<BN>;
-  auto kern = wgrad_tc_kernel<BN, PRO>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
-  dlb_launch(kern, dim3(grid), dim3(PRO ? 512 : 256), (size_t)C::kSmemBytes, st, tdy, tx, p);
-  return dlb_post_launch();
-}
-}  // namespace
-
-// dW[Co][ldw] (fp32, zero-initialised by the caller or accumulated into) += dY[M,Co]^T * pro(X[M,Ci]).
-// dY / X: bf16 row-major with row strides lddy / ldx (elements, multiples of 8).
-DLB_API int dlb_wgrad_tc(const void* dy, long long lddy, const void* x, long long ldx, float* dw, long long ldw, int M, int Co, int Ci,
-                         const float* pro_a, const float* pro_b, long long pro_ld, int rows_per_sample, int sm_limit, void* stream) {
-  if (M <= 0 || Co <= 0 || Ci <= 0) return 0;
-  if ((lddy % 8) || (ldx % 8) || ((uintptr_t)dy & 15) || ((uintptr_t)x & 15) || (Co % 8) || (Ci % 8)) return -3;
-  if (pro_a && ((pro_ld % 64) || pro_ld < Ci || ((uintptr_t)pro_a & 15) || ((uintptr_t)pro_b & 15))) return -5;
-  static int sm_count = 0;
-  if (!sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  }
-  int sms = sm_count;
-  if (sm_limit > 0 && sm_limit < sms) sms = sm_limit;
-  const int bn = Ci <= 64 ? 64 : (Ci <= 128 ? 128 : 256);
-  const int co_tiles = (Co + 127) / 128, ci_tiles = (Ci + bn - 1) / bn;
-  int splits = (2 * sms + co_tiles * ci_tiles - 1) / (co_tiles * ci_tiles);
-  int max_splits = (M + 255) / 256;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  int rows = (M + splits - 1) / splits;
-  rows = (rows + 63) / 64 * 64;
-  splits = (M + rows - 1) / rows;
-  CUtensorMap tdy, tx;
-  int rc = make_map(&tdy, dy, M, Co, lddy, 64);
-  if (rc) return rc;
-  rc = make_map(&tx, x, M, Ci, ldx, 64);
-  if (rc) return rc;
-  WgradParams p;
-  p.M = M; p.Co = Co; p.Ci = Ci; p.dw = dw; p.ldw = ldw; p.rows_per_split = rows; p.num_splits = splits;
-  p.pro_a = pro_a; p.pro_b = pro_b; p.pro_ld = pro_ld; p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : M;
-  const int units = co_tiles * ci_tiles * splits;
-  const int grid = units < sms ? units : sms;
-  cudaStream_t st = (cudaStream_t)stream;
-  const bool pro = pro_a != nullptr;
-  if (bn == 64) return pro ? launch_wgrad<64, true>(tdy, tx, p, grid, st) : launch_wgrad<64, false>(tdy, tx, p, grid, st);
-  if (bn == 128) return pro ? launch_wgrad<128, true>(tdy, tx, p, grid, st) : launch_wgrad<128, false>(tdy, tx, p, grid, st);
-  return pro ? launch_wgrad<256, true>(tdy, tx, p, grid, st) : launch_wgrad<256, false>(tdy, tx, p, grid, st);
-}
-
-namespace {
 int sm_count_cached() {
   static int sm_count = 0;
   if (!sm_count) {
@@ -787,6 +658,136 @@ int sm_count_cached() {
   }
   return sm_count;
 }
+inline int sms_for(int sm_limit) {
+  int sms = sm_count_cached();
+  if (sm_limit > 0 && sm_limit < sms) sms = sm_limit;
+  return sms;
+}
+inline GemmParams base_params(int M, int N, int K, void* d, long long ldd) {
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.d = d; p.ldd = ldd; p.accumulate_out = 0;
+  p.pro_a = nullptr; p.pro_b = nullptr; p.pro_ld = 0; p.rows_per_sample = M; p.stats = nullptr; p.stats_ns = 0;
+  p.conv_H = p.conv_W = p.conv_C = 0; p.conv_kchunks = 1; p.conv_sign = 1;
+  return p;
+}
+
+// ---- element-type generic implementations -------------------------------------------------------------------------
+template <typename E>
+int gemm_bmn_impl(const void* a, long long lda, const void* b, long long ldb, void* d, long long ldd, int M, int N, int K, int sm_limit,
+                  cudaStream_t st) {
+  constexpr int EB = Elt<E>::kBytes, AT = Elt<E>::kAtom, V = 16 / EB;
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((K % V) || (N % V) || (lda % V) || (ldb % V) || (ldd % V) || ((uintptr_t)a & 15) || ((uintptr_t)b & 15) || ((uintptr_t)d & 15)) return -3;
+  const int sms = sms_for(sm_limit);
+  CUtensorMap ta, tb, td;
+  int rc = make_map(&ta, a, M, K, lda, BM, EB);
+  if (rc) return rc - 10;
+  rc = make_map(&tb, b, K, N, ldb, AT, EB);                 // boxes of [BK k-rows][128 bytes of n]
+  if (rc) return rc - 20;
+  rc = make_map(&td, d, M, N, ldd, 32, EB);
+  if (rc) return rc - 30;
+  GemmParams p = base_params(M, N, K, d, ldd);
+  if constexpr (EB == 2) {
+    const int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    if (bn == 64) return dispatch<E, 64>(ta, tb, td, p, false, false, sms, st, true);
+    if (bn == 128) return dispatch<E, 128>(ta, tb, td, p, false, false, sms, st, true);
+    return dispatch<E, 256>(ta, tb, td, p, false, false, sms, st, true);
+  } else {
+    const int bn = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+    if (bn == 32) return dispatch<E, 32>(ta, tb, td, p, false, false, sms, st, true);
+    if (bn == 64) return dispatch<E, 64>(ta, tb, td, p, false, false, sms, st, true);
+    return dispatch<E, 128>(ta, tb, td, p, false, false, sms, st, true);
+  }
+}
+
+template <typename E>
+int gemm_impl(const void* a, long long lda, const void* b, long long ldb, void* d, long long ldd, int M, int N, int K,
+              const float* pro_a, const float* pro_b, long long pro_ld, int rows_per_sample, float* stats, long long stats_ns,
+              int sm_limit, cudaStream_t st) {
+  constexpr int EB = Elt<E>::kBytes, V = 16 / EB;
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((K % V) || (lda % V) || (ldb % V) || ((uintptr_t)a & 15) || ((uintptr_t)b & 15)) return -3;
+  if ((ldd % V) || ((uintptr_t)d & 15) || (N % V)) return -6;
+  if (stats && (rows_per_sample % 32)) return -4;
+  if (pro_a && ((pro_ld % 64) || pro_ld < K || ((uintptr_t)pro_a & 15) || ((uintptr_t)pro_b & 15))) return -5;
+  const int sms = sms_for(sm_limit);
+  int bn = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+  if (EB == 4 && bn > 128) bn = 128;                      // fp32 tiles: 128 columns = 512 output bytes per row
+  CUtensorMap ta, tb, td;
+  int rc = make_map(&ta, a, M, K, lda, BM, EB);
+  if (rc) return rc;
+  rc = make_map(&tb, b, N, K, ldb, bn, EB);
+  if (rc) return rc;
+  rc = make_map(&td, d, M, N, ldd, 32, EB);                 // output boxes: 32 rows x 128 bytes, 128B swizzle
+  if (rc) return rc;
+  GemmParams p = base_params(M, N, K, d, ldd);
+  p.pro_a = pro_a; p.pro_b = pro_b; p.pro_ld = pro_ld; p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : M;
+  p.stats = stats; p.stats_ns = stats_ns;
+  const bool pro = pro_a != nullptr, sts = stats != nullptr;
+  switch (bn) {
+    case 32: return dispatch<E, 32>(ta, tb, td, p, pro, sts, sms, st);
+    case 64: return dispatch<E, 64>(ta, tb, td, p, pro, sts, sms, st);
+    case 128: return dispatch<E, 128>(ta, tb, td, p, pro, sts, sms, st);
+    default:
+      if constexpr (EB == 2) return dispatch<E, 256>(ta, tb, td, p, pro, sts, sms, st);
+      return -9;
+  }
+}
+
+template <typename E, int BN, bool PRO>
+int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const WgradParams& p, int grid, cudaStream_t st) {
+  using C = WCfg<E, BN>;
+  auto kern = wgrad_tc_kernel<E, BN, PRO>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  dlb_launch(kern, dim3(grid), dim3(PRO ? 512 : 256), (size_t)C::kSmemBytes, st, tdy, tx, p);
+  return dlb_post_launch();
+}
+
+template <typename E>
+int wgrad_impl(const void* dy, long long lddy, const void* x, long long ldx, float* dw, long long ldw, int M, int Co, int Ci,
+               const float* pro_a, const float* pro_b, long long pro_ld, int rows_per_sample, int sm_limit, cudaStream_t st) {
+  constexpr int EB = Elt<E>::kBytes, V = 16 / EB;
+  if (M <= 0 || Co <= 0 || Ci <= 0) return 0;
+  if ((lddy % V) || (ldx % V) || ((uintptr_t)dy & 15) || ((uintptr_t)x & 15) || (Co % V) || (Ci % V)) return -3;
+  if (pro_a && ((pro_ld % 64) || pro_ld < Ci || ((uintptr_t)pro_a & 15) || ((uintptr_t)pro_b & 15))) return -5;
+  const int sms = sms_for(sm_limit);
+  int bn = Ci <= 64 ? 64 : (Ci <= 128 ? 128 : 256);
+  if (EB == 4) bn = Ci <= 32 ? 32 : (Ci <= 64 ? 64 : 128);
+  const int co_tiles = (Co + 127) / 128, ci_tiles = (Ci + bn - 1) / bn;
+  int splits = (2 * sms + co_tiles * ci_tiles - 1) / (co_tiles * ci_tiles);
+  int max_splits = (M + 255) / 256;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int rows = (M + splits - 1) / splits;
+  rows = (rows + 63) / 64 * 64;
+  splits = (M + rows - 1) / rows;
+  CUtensorMap tdy, tx;
+  int rc = make_map(&tdy, dy, M, Co, lddy, 64, EB);
+  if (rc) return rc;
+  rc = make_map(&tx, x, M, Ci, ldx, 64, EB);
+  if (rc) return rc;
+  WgradParams p;
+  p.M = M; p.Co = Co; p.Ci = Ci; p.dw = dw; p.ldw = ldw; p.rows_per_split = rows; p.num_splits = splits;
+  p.pro_a = pro_a; p.pro_b = pro_b; p.pro_ld = pro_ld; p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : M;
+  const int units = co_tiles * ci_tiles * splits;
+  const int grid = units < sms ? units : sms;
+  const bool pro = pro_a != nullptr;
+  if constexpr (EB == 2) {
+    if (bn == 64) return pro ? launch_wgrad<E, 64, true>(tdy, tx, p, grid, st) : launch_wgrad<E, 64, false>(tdy, tx, p, grid, st);
+    if (bn == 128) return pro ? launch_wgrad<E, 128, true>(tdy, tx, p, grid, st) : launch_wgrad<E, 128, false>(tdy, tx, p, grid, st);
+    return pro ? launch_wgrad<E, 256, true>(tdy, tx, p, grid, st) : launch_wgrad<E, 256, false>(tdy, tx, p, grid, st);
+  } else {
+    if (bn == 32) return pro ? launch_wgrad<E, 32, true>(tdy, tx, p, grid, st) : launch_wgrad<E, 32, false>(tdy, tx, p, grid, st);
+    if (bn == 64) return pro ? launch_wgrad<E, 64, true>(tdy, tx, p, grid, st) : launch_wgrad<E, 64, false>(tdy, tx, p, grid, st);
+    return pro ? launch_wgrad<E, 128, true>(tdy, tx, p, grid, st) : launch_wgrad<E, 128, false>(tdy, tx, p, grid, st);
+  }
+}
+
 // box geometry for 128-pixel tiles made of whole image rows
 bool conv_tile_geometry(int N, int H, int W, int& hb, int& nb) {
   if (W <= 0 || H <= 0 || 128 % W) return false;
@@ -795,63 +796,131 @@ bool conv_tile_geometry(int N, int H, int W, int& hb, int& nb) {
   else { if (rows % H) return false; hb = H; nb = rows / H; }
   return true;
 }
-}  // namespace
 
-// 3x3 / stride 1 / pad 1 convolution, NHWC bf16:  y[N,H,W,Co] (row stride ldy) = conv(x[N,H,W,Ci] (pixel stride ldx), w[Co][3][3][Ci]).
-// dgrad != 0 computes the data gradient instead: x := dY [N,H,W,Co], output := dX [N,H,W,Ci], same weight tensor.
-// stats (optional, forward only): per-(sample, out-channel) (sum, sumsq) table, needs (H*W) % 32 == 0; pre-zeroed.
-DLB_API int dlb_conv3x3_tc(int dgrad, const void* x, long long ldx, const void* w, void* y, long long ldy, int N, int H, int W, int Ci,
-                           int Co, float* stats, long long stats_ns, int sm_limit, void* stream) {
+template <typename E>
+int conv3x3_impl(int dgrad, const void* x, long long ldx, const void* w, void* y, long long ldy, int N, int H, int W, int Ci,
+                 int Co, float* stats, long long stats_ns, int sm_limit, cudaStream_t st) {
+  constexpr int EB = Elt<E>::kBytes, AT = Elt<E>::kAtom, V = 16 / EB;
   const int Cin = dgrad ? Co : Ci;            // channels of the tensor being convolved
   const int Cout = dgrad ? Ci : Co;           // channels produced
   int hb, nb;
   if (!conv_tile_geometry(N, H, W, hb, nb)) return -7;
-  if ((Cin % 8) || (Cout % 8) || (ldx % 8) || (ldy % 8) || ((uintptr_t)x & 15) || ((uintptr_t)w & 15) || ((uintptr_t)y & 15)) return -3;
+  if ((Cin % V) || (Cout % V) || (ldx % V) || (ldy % V) || ((uintptr_t)x & 15) || ((uintptr_t)w & 15) || ((uintptr_t)y & 15)) return -3;
   if (stats && ((H * W) % 32)) return -4;
   const int M = N * H * W;
-  int sms = sm_count_cached();
-  if (sm_limit > 0 && sm_limit < sms) sms = sm_limit;
+  const int sms = sms_for(sm_limit);
   CUtensorMap ta, tb, td;
   {
     long long dims[4] = {Cin, W, H, N};
     long long strides[4] = {1, ldx, (long long)W * ldx, (long long)H * W * ldx};
-    int box[4] = {64, W, hb, nb};
-    int rc = make_map_nd(&ta, x, 4, dims, strides, box);
+    int box[4] = {AT, W, hb, nb};
+    int rc = make_map_nd(&ta, x, 4, dims, strides, box, EB);
     if (rc) return rc - 10;
   }
   int bn;
   if (!dgrad) {
     bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256));
-    int rc = make_map(&tb, w, Cout, 9LL * Cin, 9LL * Cin, bn);          // [Co][9*Ci], K-major
+    if (EB == 4 && bn > 128) bn = 128;
+    int rc = make_map(&tb, w, Cout, 9LL * Cin, 9LL * Cin, bn, EB);          // [Co][9*Ci], K-major
     if (rc) return rc - 20;
   } else {
     bn = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
+    if (EB == 4) bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128);
     long long dims[3] = {Ci, 9, Co};                                     // w[co][tap][ci]: {ci (n, contiguous), tap, co (k rows)}
     long long strides[3] = {1, Ci, 9LL * Ci};
-    int box[3] = {64, 1, 64};
-    int rc = make_map_nd(&tb, w, 3, dims, strides, box);
+    int box[3] = {AT, 1, AT};
+    int rc = make_map_nd(&tb, w, 3, dims, strides, box, EB);
     if (rc) return rc - 20;
   }
-  int rc = make_map(&td, y, M, Cout, ldy, 32);
+  int rc = make_map(&td, y, M, Cout, ldy, 32, EB);
   if (rc) return rc - 30;
-  GemmParams p;
-  p.M = M; p.N = Cout; p.K = 9 * Cin; p.d = y; p.ldd = ldy; p.accumulate_out = 0;
-  p.pro_a = nullptr; p.pro_b = nullptr; p.pro_ld = 0; p.rows_per_sample = H * W; p.stats = stats; p.stats_ns = stats_ns;
-  p.conv_H = H; p.conv_W = W; p.conv_C = Cin; p.conv_kchunks = (Cin + 63) / 64; p.conv_sign = dgrad ? -1 : 1;
-  cudaStream_t st = (cudaStream_t)stream;
+  GemmParams p = base_params(M, Cout, 9 * Cin, y, ldy);
+  p.rows_per_sample = H * W; p.stats = stats; p.stats_ns = stats_ns;
+  p.conv_H = H; p.conv_W = W; p.conv_C = Cin; p.conv_kchunks = (Cin + AT - 1) / AT; p.conv_sign = dgrad ? -1 : 1;
   if (dgrad) {
-    if (bn == 64) return launch<64, false, false, true, true>(ta, tb, td, p, sms, st);
-    if (bn == 128) return launch<128, false, false, true, true>(ta, tb, td, p, sms, st);
-    return launch<256, false, false, true, true>(ta, tb, td, p, sms, st);
+    if constexpr (EB == 2) {
+      if (bn == 64) return launch<E, 64, false, false, true, true>(ta, tb, td, p, sms, st);
+      if (bn == 128) return launch<E, 128, false, false, true, true>(ta, tb, td, p, sms, st);
+      return launch<E, 256, false, false, true, true>(ta, tb, td, p, sms, st);
+    } else {
+      if (bn == 32) return launch<E, 32, false, false, true, true>(ta, tb, td, p, sms, st);
+      if (bn == 64) return launch<E, 64, false, false, true, true>(ta, tb, td, p, sms, st);
+      return launch<E, 128, false, false, true, true>(ta, tb, td, p, sms, st);
+    }
   }
   if (stats) {
-    if (bn == 32) return launch<32, false, true, false, true>(ta, tb, td, p, sms, st);
-    if (bn == 64) return launch<64, false, true, false, true>(ta, tb, td, p, sms, st);
-    if (bn == 128) return launch<128, false, true, false, true>(ta, tb, td, p, sms, st);
-    return launch<256, false, true, false, true>(ta, tb, td, p, sms, st);
+    if (bn == 32) return launch<E, 32, false, true, false, true>(ta, tb, td, p, sms, st);
+    if (bn == 64) return launch<E, 64, false, true, false, true>(ta, tb, td, p, sms, st);
+    if (bn == 128) return launch<E, 128, false, true, false, true>(ta, tb, td, p, sms, st);
+    if constexpr (EB == 2) return launch<E, 256, false, true, false, true>(ta, tb, td, p, sms, st);
+    return -9;
   }
-  if (bn == 32) return launch<32, false, false, false, true>(ta, tb, td, p, sms, st);
-  if (bn == 64) return launch<64, false, false, false, true>(ta, tb, td, p, sms, st);
-  if (bn == 128) return launch<128, false, false, false, true>(ta, tb, td, p, sms, st);
-  return launch<256, false, false, false, true>(ta, tb, td, p, sms, st);
+  if (bn == 32) return launch<E, 32, false, false, false, true>(ta, tb, td, p, sms, st);
+  if (bn == 64) return launch<E, 64, false, false, false, true>(ta, tb, td, p, sms, st);
+  if (bn == 128) return launch<E, 128, false, false, false, true>(ta, tb, td, p, sms, st);
+  if constexpr (EB == 2) return launch<E, 256, false, false, false, true>(ta, tb, td, p, sms, st);
+  return -9;
+}
+
+}  // namespace
+
+// ---- C ABI.  `dtype`: DLB_BF16 (bf16 operands/outputs, kind::f16) or DLB_F32 (fp32 storage, TF32 tensor-core math, kind::tf32).
+// The un-suffixed entry points are the bf16 flavour (kept for callers that predate the fp32/TF32 path). --------------------
+
+// D[M,N] = A[M,K] * B[K,N]   with B given row-major [K][N] (row stride ldb): dgrad of a 1x1 conv / linear
+// (dX = dY * W with W = [Cout=K][Cin=N]) without a transposed weight copy.
+DLB_API int dlb_gemm_tc_bmn_dt(int dtype, const void* a, long long lda, const void* b, long long ldb, void* d, long long ldd, int M, int N,
+                               int K, int sm_limit, void* stream) {
+  if (dtype == DLB_F32) return gemm_bmn_impl<float>(a, lda, b, ldb, d, ldd, M, N, K, sm_limit, (cudaStream_t)stream);
+  return gemm_bmn_impl<__nv_bfloat16>(a, lda, b, ldb, d, ldd, M, N, K, sm_limit, (cudaStream_t)stream);
+}
+DLB_API int dlb_gemm_tc_bmn(const void* a, long long lda, const void* b, long long ldb, void* d, long long ldd, int M, int N, int K,
+                            int sm_limit, void* stream) {
+  return dlb_gemm_tc_bmn_dt(DLB_BF16, a, lda, b, ldb, d, ldd, M, N, K, sm_limit, stream);
+}
+
+// D[M,N] (row stride ldd) = pro(A[M,K] (row stride lda)) * B[N,K]^T (row stride ldb).
+//   pro_a/pro_b (optional): fp32 [M / rows_per_sample][K] affine coefficients -> A' = relu(a*A + b)
+//   stats (optional): fp32 table [M / rows_per_sample][stats_ns] accumulating (sum, sumsq) per output column;
+//                     must be zeroed by the caller.
+// Requirements: K, N, lda, ldb, ldd multiples of the 16-byte vector (8 bf16 / 4 fp32), 16-byte aligned base pointers; with
+// stats rows_per_sample % 32 == 0.
+DLB_API int dlb_gemm_tc_dt(int dtype, const void* a, long long lda, const void* b, long long ldb, void* d, long long ldd, int M, int N, int K,
+                           const float* pro_a, const float* pro_b, long long pro_ld, int rows_per_sample, float* stats, long long stats_ns,
+                           int sm_limit, void* stream) {
+  if (dtype == DLB_F32)
+    return gemm_impl<float>(a, lda, b, ldb, d, ldd, M, N, K, pro_a, pro_b, pro_ld, rows_per_sample, stats, stats_ns, sm_limit, (cudaStream_t)stream);
+  return gemm_impl<__nv_bfloat16>(a, lda, b, ldb, d, ldd, M, N, K, pro_a, pro_b, pro_ld, rows_per_sample, stats, stats_ns, sm_limit, (cudaStream_t)stream);
+}
+DLB_API int dlb_gemm_tc(const void* a, long long lda, const void* b, long long ldb, void* d, long long ldd, int M, int N, int K,
+                        const float* pro_a, const float* pro_b, long long pro_ld, int rows_per_sample, float* stats, long long stats_ns,
+                        int sm_limit, void* stream) {
+  return dlb_gemm_tc_dt(DLB_BF16, a, lda, b, ldb, d, ldd, M, N, K, pro_a, pro_b, pro_ld, rows_per_sample, stats, stats_ns, sm_limit, stream);
+}
+
+// dW[Co][ldw] (fp32, zero-initialised by the caller or accumulated into) += dY[M,Co]^T * pro(X[M,Ci]).
+// dY / X: row-major with row strides lddy / ldx (elements, multiples of the 16-byte vector).
+DLB_API int dlb_wgrad_tc_dt(int dtype, const void* dy, long long lddy, const void* x, long long ldx, float* dw, long long ldw, int M, int Co,
+                            int Ci, const float* pro_a, const float* pro_b, long long pro_ld, int rows_per_sample, int sm_limit, void* stream) {
+  if (dtype == DLB_F32)
+    return wgrad_impl<float>(dy, lddy, x, ldx, dw, ldw, M, Co, Ci, pro_a, pro_b, pro_ld, rows_per_sample, sm_limit, (cudaStream_t)stream);
+  return wgrad_impl<__nv_bfloat16>(dy, lddy, x, ldx, dw, ldw, M, Co, Ci, pro_a, pro_b, pro_ld, rows_per_sample, sm_limit, (cudaStream_t)stream);
+}
+DLB_API int dlb_wgrad_tc(const void* dy, long long lddy, const void* x, long long ldx, float* dw, long long ldw, int M, int Co, int Ci,
+                         const float* pro_a, const float* pro_b, long long pro_ld, int rows_per_sample, int sm_limit, void* stream) {
+  return dlb_wgrad_tc_dt(DLB_BF16, dy, lddy, x, ldx, dw, ldw, M, Co, Ci, pro_a, pro_b, pro_ld, rows_per_sample, sm_limit, stream);
+}
+
+// 3x3 / stride 1 / pad 1 convolution, NHWC:  y[N,H,W,Co] (row stride ldy) = conv(x[N,H,W,Ci] (pixel stride ldx), w[Co][3][3][Ci]).
+// dgrad != 0 computes the data gradient instead: x := dY [N,H,W,Co], output := dX [N,H,W,Ci], same weight tensor.
+// stats (optional, forward only): per-(sample, out-channel) (sum, sumsq) table, needs (H*W) % 32 == 0; pre-zeroed.
+DLB_API int dlb_conv3x3_tc_dt(int dtype, int dgrad, const void* x, long long ldx, const void* w, void* y, long long ldy, int N, int H, int W,
+                              int Ci, int Co, float* stats, long long stats_ns, int sm_limit, void* stream) {
+  if (dtype == DLB_F32)
+    return conv3x3_impl<float>(dgrad, x, ldx, w, y, ldy, N, H, W, Ci, Co, stats, stats_ns, sm_limit, (cudaStream_t)stream);
+  return conv3x3_impl<__nv_bfloat16>(dgrad, x, ldx, w, y, ldy, N, H, W, Ci, Co, stats, stats_ns, sm_limit, (cudaStream_t)stream);
+}
+DLB_API int dlb_conv3x3_tc(int dgrad, const void* x, long long ldx, const void* w, void* y, long long ldy, int N, int H, int W, int Ci,
+                           int Co, float* stats, long long stats_ns, int sm_limit, void* stream) {
+  return dlb_conv3x3_tc_dt(DLB_BF16, dgrad, x, ldx, w, y, ldy, N, H, W, Ci, Co, stats, stats_ns, sm_limit, stream);
 }

@@ -91,6 +91,66 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// fp32 operands in shared memory consumed as TF32 (10-bit mantissa, the low 13 bits are ignored), fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Element traits of the tensor-core kernels.  In BYTES the two operand types are identical: one SWIZZLE_128B atom row
+// is 128 bytes of K (64 bf16 / 32 fp32), one UMMA consumes 32 bytes of K per row (UMMA_K = 16 bf16 / 8 tf32), so the
+// shared-memory layouts, descriptor strides and the K-major "+2 per MMA" descriptor advance do not depend on the type.
+template <typename E> struct Elt;
+template <> struct Elt<__nv_bfloat16> {
+  static constexpr int kBytes = 2;
+  static constexpr int kAtom = 64;          // elements per 128-byte swizzle row
+  static constexpr int kUmmaK = 16;
+  static constexpr int kPer16 = 8;          // elements per 16-byte chunk
+  static constexpr uint32_t kFmt = 1;       // UMMA instruction-descriptor operand format: BF16
+  static constexpr CUtensorMapDataType kTmap = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  __device__ static __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) { umma_f16(d, a, b, idesc, acc); }
+};
+template <> struct Elt<float> {
+  static constexpr int kBytes = 4;
+  static constexpr int kAtom = 32;
+  static constexpr int kUmmaK = 8;
+  static constexpr int kPer16 = 4;
+  static constexpr uint32_t kFmt = 2;       // TF32
+  static constexpr CUtensorMapDataType kTmap = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  __device__ static __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) { umma_tf32(d, a, b, idesc, acc); }
+};
+
+// relu(a*x + b) on one 16-byte chunk (8 bf16 or 4 fp32) with per-channel coefficients held in registers
+template <typename E>
+__device__ __forceinline__ void affine_relu_chunk(uint4& raw, const float (&ca)[8], const float (&cb)[8]) {
+  if constexpr (sizeof(E) == 2) {
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      h[i] = __floats2bfloat162_rn(fmaxf(fmaf(ca[2 * i], f.x, cb[2 * i]), 0.f), fmaxf(fmaf(ca[2 * i + 1], f.y, cb[2 * i + 1]), 0.f));
+    }
+  } else {
+    raw.x = __float_as_uint(fmaxf(fmaf(ca[0], __uint_as_float(raw.x), cb[0]), 0.f));
+    raw.y = __float_as_uint(fmaxf(fmaf(ca[1], __uint_as_float(raw.y), cb[1]), 0.f));
+    raw.z = __float_as_uint(fmaxf(fmaf(ca[2], __uint_as_float(raw.z), cb[2]), 0.f));
+    raw.w = __float_as_uint(fmaxf(fmaf(ca[3], __uint_as_float(raw.w), cb[3]), 0.f));
+  }
+}
+// load the kPer16 coefficients of one chunk (pointers 16-byte aligned)
+template <typename E>
+__device__ __forceinline__ void load_coef(const float* pa, const float* pb, float (&ca)[8], float (&cb)[8]) {
+  const float4 a0 = __ldg(reinterpret_cast<const float4*>(pa)), b0 = __ldg(reinterpret_cast<const float4*>(pb));
+  ca[0] = a0.x; ca[1] = a0.y; ca[2] = a0.z; ca[3] = a0.w; cb[0] = b0.x; cb[1] = b0.y; cb[2] = b0.z; cb[3] = b0.w;
+  if constexpr (sizeof(E) == 2) {
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(pa) + 1), b1 = __ldg(reinterpret_cast<const float4*>(pb) + 1);
+    ca[4] = a1.x; ca[5] = a1.y; ca[6] = a1.z; ca[7] = a1.w; cb[4] = b1.x; cb[5] = b1.y; cb[6] = b1.z; cb[7] = b1.w;
+  }
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -107,10 +167,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes = 8192) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)(8192 >> 4) << 16;       // LBO: next 64-wide MN group (one TMA box further)
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;  // LBO: next 128-byte-wide MN group (one TMA box further)
   d |= (uint64_t)(1024 >> 4) << 32;       // SBO: next 8-row K group
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
@@ -131,8 +191,9 @@ inline PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 // 2-D bf16 tensor map: inner dim `cols` (contiguous), outer dim `rows` with row stride `ld` elements.
-inline int make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
-  // inner box is always 64 elements = 128 bytes = the swizzle span
+inline int make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows,
+                    int esize = 2) {
+  // inner box is always 128 bytes = the swizzle span (64 bf16 or 32 fp32)
   auto enc = get_encode();
   if (!enc) return -10;
   // the driver-API encoder needs a current context on THIS thread (autograd runs backward on its own threads,
@@ -140,10 +201,10 @@ inline int make_map(CUtensorMap* map, const void* ptr, long long rows, long long
   static thread_local bool ctx_bound = false;
   if (!ctx_bound) { cudaFree(0); ctx_bound = true; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (cuuint64_t)esize};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(map, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS && getenv("DLB_DEBUG_TMAP"))
@@ -152,15 +213,16 @@ inline int make_map(CUtensorMap* map, const void* ptr, long long rows, long long
 }
 
 // general rank-n bf16 tensor map (dims/strides innermost first; strides in elements for dims 1..n-1)
-inline int make_map_nd(CUtensorMap* map, const void* ptr, int rank, const long long* dims, const long long* strides, const int* box) {
+inline int make_map_nd(CUtensorMap* map, const void* ptr, int rank, const long long* dims, const long long* strides, const int* box,
+                       int esize = 2) {
   auto enc = get_encode();
   if (!enc) return -10;
   static thread_local bool ctx_bound = false;
   if (!ctx_bound) { cudaFree(0); ctx_bound = true; }
   cuuint64_t d[5]; cuuint64_t sbytes[4]; cuuint32_t b[5]; cuuint32_t es[5];
   for (int i = 0; i < rank; ++i) { d[i] = (cuuint64_t)dims[i]; b[i] = (cuuint32_t)box[i]; es[i] = 1; }
-  for (int i = 1; i < rank; ++i) sbytes[i - 1] = (cuuint64_t)strides[i] * 2;
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), d, sbytes, b, es,
+  for (int i = 1; i < rank; ++i) sbytes[i - 1] = (cuuint64_t)strides[i] * (cuuint64_t)esize;
+  CUresult r = enc(map, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), d, sbytes, b, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS && getenv("DLB_DEBUG_TMAP"))

@@ -40,7 +40,10 @@ from ..parallel import FlatState, make_comm
 from ..utils import StatsRecorder, Tracer, load_checkpoint, save_checkpoint
 from .lr_policy import lr_at_epoch
 
-_DT = {"fp32": torch.float32, "bf16": torch.bfloat16}
+# tf32 = fp32 storage with TF32 tensor-core math in the conv / linear kernels (tcgen05.mma kind::tf32): the precision class of
+# the reference's default PyTorch path (fp32 model, dbs.py:363; cuDNN convolutions run TF32 by default).  "fp32" is the same
+# storage; on CUDA its convolutions take the same TF32 kernels unless DLB_TF32=0 (then the vendor library decides).
+_DT = {"fp32": torch.float32, "bf16": torch.bfloat16, "tf32": torch.float32}
 
 
 class Trainer:
@@ -51,6 +54,9 @@ class Trainer:
         if self.cuda:
             torch.cuda.set_device(self.device)
         self.dtype = _DT[cfg.resolved_dtype(device)]
+        self.dtype_name = cfg.resolved_dtype(device)
+        if self.dtype_name == "fp32" and self.cuda and os.environ.get("DLB_TF32", "1") == "1":
+            self.dtype_name = "tf32"
         self.comm = comm if comm is not None else make_comm(cfg.resolved_comm(device), self.device, algo=cfg.allreduce_algo,
                                                             timeout_s=cfg.comm_timeout_s)
         self.is_lm = cfg.is_lm

@@ -108,8 +108,9 @@ class _DenseBlockFn(torch.autograd.Function):
         lib.dlb_norm_skip_zero(1)
         copy_in_with_stats(x, ct - c0, c0)
         saved = []
-        fused = x.dtype == torch.bfloat16 and gemm_tc.available() and (n * hw) >= 128
-        conv3_ok = fused and gemm_tc.conv3x3_profitable(h, w) and _USE_CONV3 and hasattr(nat.get(), "dlb_conv3x3_tc")
+        # tensor-core path: bf16, or fp32 storage with TF32 math (the reference's precision class: fp32 tensors, TF32 convs)
+        fused = x.dtype in gemm_tc.TC_DTYPES and gemm_tc.available() and (n * hw) >= 128
+        conv3_ok = fused and gemm_tc.conv3x3_profitable(h, w) and _USE_CONV3
         for l in range(n_layers):
             g1w, g1b, w1, g2w, g2b, w2 = params[6 * l:6 * l + 6]
             cl = c0 + l * g
@@ -119,7 +120,7 @@ class _DenseBlockFn(torch.autograd.Function):
             rstd1 = torch.empty_like(mean1)
             mean2 = torch.empty(n * groups, dtype=torch.float32, device=x.device)
             rstd2 = torch.empty_like(mean2)
-            if fused and w1.dtype == torch.bfloat16:
+            if fused and w1.dtype == x.dtype:
                 # GN1-apply + ReLU runs as the A-operand prologue of the tcgen05 GEMM; the normalised
                 # activation is never written to HBM.  The epilogue emits the statistics GN2 needs.
                 kpad = (cl + 63) // 64 * 64
@@ -133,7 +134,7 @@ class _DenseBlockFn(torch.autograd.Function):
                 t2 = t2_all[l]
                 w1_2d = gemm_tc._w2d(w1)
                 gemm_tc.gemm_raw(slice_ptr(off), ct, w1_2d.data_ptr(), w1_2d.stride(0), yv.data_ptr(), cm, n * hw, cm, cl,
-                                 x.device, ca, cb, hw, t2 if epi else None, 0, 2 * cm)
+                                 x.device, ca, cb, hw, t2 if epi else None, 0, 2 * cm, dtype=dt)
                 if not epi:
                     nat.check(lib.dlb_nc_reduce2(0, dt, yv.data_ptr(), cm, 0, 0, 0, 0, t2.data_ptr(), 0, n, hw, cm, st), "dense.y_stats")
                 kpad2 = (cm + 63) // 64 * 64
@@ -160,14 +161,14 @@ class _DenseBlockFn(torch.autograd.Function):
                 nat.check(lib.dlb_gn_forward(dt, yv.data_ptr(), ldy, 0, 0, yhat.data_ptr(), cm, g2w.data_ptr(), g2b.data_ptr(),
                                              mean2.data_ptr(), rstd2.data_ptr(), t2.data_ptr(), n, hw, cm, groups, eps, 1, 0, st),
                           "dense.gn2")
-            if fused and conv3_ok and w2.dtype == torch.bfloat16:
+            if fused and conv3_ok and w2.dtype == x.dtype:
                 # 3x3 conv on the tcgen05 implicit-GEMM kernel: its TMA-store epilogue writes the g new channels
                 # straight into their slice of the block buffer and (when H*W % 32 == 0) accumulates their
                 # GroupNorm statistics -- no staging tensor, no copy, no separate statistics pass
                 w2k = gemm_tc._w_ohwi(w2)
                 epi2 = hw % 32 == 0
                 gemm_tc.conv3x3_raw(False, yhat.data_ptr(), cm, w2k.data_ptr(), slice_ptr(off - g), ct, n, h, w, cm, g, x.device,
-                                    (table.data_ptr() + (off - g) * 8) if epi2 else 0, tns)
+                                    (table.data_ptr() + (off - g) * 8) if epi2 else 0, tns, dtype=dt)
                 if not epi2:
                     nat.check(lib.dlb_nc_reduce2(0, dt, slice_ptr(off - g), ct, 0, 0, 0, 0, table.data_ptr() + (off - g) * 8, tns,
                                                  n, hw, g, st), "dense.new_stats")
@@ -213,9 +214,9 @@ class _DenseBlockFn(torch.autograd.Function):
         lib.dlb_norm_skip_zero(1)
         dw1_views = [None] * n_layers
         main = torch.cuda.current_stream(buf.device)
-        side = _side_stream(buf.device) if (_USE_SIDE and buf.dtype == torch.bfloat16) else None
-        conv3_ok = (buf.dtype == torch.bfloat16 and gemm_tc.available() and gemm_tc.conv3x3_profitable(h, w) and _USE_CONV3
-                    and hasattr(nat.get(), "dlb_conv3x3_tc") and n * h * w >= 128)
+        side = _side_stream(buf.device) if (_USE_SIDE and buf.dtype in gemm_tc.TC_DTYPES) else None
+        conv3_ok = (buf.dtype in gemm_tc.TC_DTYPES and gemm_tc.available() and gemm_tc.conv3x3_profitable(h, w) and _USE_CONV3
+                    and n * h * w >= 128)
         for l in reversed(range(n_layers)):
             g1w, g1b, w1, g2w, g2b, w2 = params[6 * l:6 * l + 6]
             xhat, y, yhat, mean1, rstd1, mean2, rstd2, ca, cb, ca2, cb2 = saved[11 * l:11 * l + 11]
@@ -232,11 +233,11 @@ class _DenseBlockFn(torch.autograd.Function):
                 side.wait_event(ev_in)
                 with torch.cuda.stream(side):
                     _, dw2, _ = _CONV_BWD(dnew, yhat, w2c, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [False, True, False])
-                if conv3_ok and w2.dtype == torch.bfloat16:
+                if conv3_ok and w2.dtype == buf.dtype:
                     # data gradient on the tcgen05 3x3 kernel, reading dY in place from the gradient-buffer slice
                     dyhat = torch.empty((n, cm, h, w), dtype=buf.dtype, device=buf.device, memory_format=torch.channels_last)
                     gemm_tc.conv3x3_raw(True, dbuf.data_ptr() + (off - g) * esz, ct, gemm_tc._w_ohwi(w2).data_ptr(), dyhat.data_ptr(),
-                                        cm, n, h, w, cm, g, buf.device)
+                                        cm, n, h, w, cm, g, buf.device, dtype=dt)
                 else:
                     dyhat, _, _ = _CONV_BWD(dnew, yhat, w2c, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [True, False, False])
             else:
@@ -271,20 +272,21 @@ class _DenseBlockFn(torch.autograd.Function):
                 # (the wgrad re-applies GN+ReLU to the raw buffer slice in its operand prologue) and the GN1
                 # backward recomputes the ReLU mask from the saved affine coefficients.
                 w1_2d = gemm_tc._w2d(w1)                                            # [cm, cl], consumed MN-major: no transpose
-                fuse_dg = gemm_tc.FUSED_DGRAD and hw % 32 == 0 and n * hw >= 128 and gemm_tc.dgrad_gn_available()
+                fuse_dg = (gemm_tc.FUSED_DGRAD and hw % 32 == 0 and n * hw >= 128 and gemm_tc.dgrad_gn_available()
+                           and buf.dtype == torch.bfloat16)
                 if not fuse_dg:
                     dxhat = torch.empty((n, cl, h, w), dtype=buf.dtype, device=buf.device, memory_format=torch.channels_last)
                     gemm_tc.gemm_bmn_raw(dy.data_ptr(), cm, w1_2d.data_ptr(), w1_2d.stride(0), dxhat.data_ptr(), cl, n * hw, cl, cm,
-                                         buf.device)
+                                         buf.device, dtype=dt)
                 if side is not None:
                     ev_dy = torch.cuda.Event(); ev_dy.record(main)
                     side.wait_event(ev_dy)
                     dw1f = dw1_arena[w_off[l]:w_off[l + 1]].view(cm, cl)
                     with torch.cuda.stream(side):
-                        gemm_tc.wgrad_raw(dy.data_ptr(), cm, xs, ct, dw1f, n * hw, cm, cl, buf.device, ca, cb, hw)
+                        gemm_tc.wgrad_raw(dy.data_ptr(), cm, xs, ct, dw1f, n * hw, cm, cl, buf.device, ca, cb, hw, dtype=dt)
                 else:
                     dw1f = dw1_arena[w_off[l]:w_off[l + 1]].view(cm, cl)
-                    gemm_tc.wgrad_raw(dy.data_ptr(), cm, xs, ct, dw1f, n * hw, cm, cl, buf.device, ca, cb, hw)
+                    gemm_tc.wgrad_raw(dy.data_ptr(), cm, xs, ct, dw1f, n * hw, cm, cl, buf.device, ca, cb, hw, dtype=dt)
                 dw1 = None                      # cast for all layers at once after the loop
                 kpad = ca.shape[1]
                 if fuse_dg:

@@ -20,10 +20,10 @@ def _lib():
     lib = nat.require()
     if not _DECLARED:
         vp, i64, i32 = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
-        nat.declare("dlb_gemm_tc", i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, i32, vp, i64, i32, vp])
-        nat.declare("dlb_gemm_tc_bmn", i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp])
-        nat.declare("dlb_conv3x3_tc", i32, [i32, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, vp, i64, i32, vp])
-        nat.declare("dlb_wgrad_tc", i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, i32, i32, vp])
+        nat.declare("dlb_gemm_tc_dt", i32, [i32, vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, i32, vp, i64, i32, vp])
+        nat.declare("dlb_gemm_tc_bmn_dt", i32, [i32, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp])
+        nat.declare("dlb_conv3x3_tc_dt", i32, [i32, i32, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, vp, i64, i32, vp])
+        nat.declare("dlb_wgrad_tc_dt", i32, [i32, vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, i32, i32, vp])
         nat.declare("dlb_dgrad_gn", i32, [i32, vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, i64, vp, i64,
                                           i32, vp])
         nat.declare("dlb_gn_bwd_coeff", i32, [vp, i64, vp, vp, vp, vp, vp, i64, vp, vp, i32, i32, i32, i32, vp])
@@ -32,64 +32,79 @@ def _lib():
 
 
 def available() -> bool:
-    return ENABLED and nat.available() and hasattr(nat.get(), "dlb_gemm_tc")
+    return ENABLED and nat.available() and hasattr(nat.get(), "dlb_gemm_tc_dt")
+
+
+#: element types the tensor-core kernels take: bf16 (kind::f16) and fp32 storage with TF32 math (kind::tf32) -- the
+#: precision class of the reference's default PyTorch path (fp32 tensors, cuDNN convolutions with allow_tf32=True)
+TC_DTYPES = (torch.bfloat16, torch.float32) if os.environ.get("DLB_TF32", "1") == "1" else (torch.bfloat16,)
+BF16, F32 = nat.BF16, nat.F32
+
+
+def vec(dtype_code: int) -> int:
+    """elements per 16-byte vector: every K / N / row stride must be a multiple of it"""
+    return 4 if dtype_code == F32 else 8
 
 
 def gemm_raw(a_ptr: int, lda: int, b_ptr: int, ldb: int, d_ptr: int, ldd: int, m: int, n: int, k: int, device,
              pro_a: Optional[torch.Tensor] = None, pro_b: Optional[torch.Tensor] = None, rows_per_sample: int = 0,
-             stats: Optional[torch.Tensor] = None, stats_ptr: int = 0, stats_ns: int = 0, sm_limit: int = 0) -> None:
+             stats: Optional[torch.Tensor] = None, stats_ptr: int = 0, stats_ns: int = 0, sm_limit: int = 0,
+             dtype: int = nat.BF16) -> None:
     pro_ld = pro_a.shape[1] if pro_a is not None else 0
     sp = stats_ptr if stats_ptr else nat.ptr(stats)
-    rc = _lib().dlb_gemm_tc(a_ptr, lda, b_ptr, ldb, d_ptr, ldd, m, n, k, nat.ptr(pro_a), nat.ptr(pro_b), pro_ld,
+    rc = _lib().dlb_gemm_tc_dt(dtype, a_ptr, lda, b_ptr, ldb, d_ptr, ldd, m, n, k, nat.ptr(pro_a), nat.ptr(pro_b), pro_ld,
                             rows_per_sample, sp, stats_ns, sm_limit, nat.stream_ptr(device))
     nat.check(rc, "gemm_tc")
 
 
 def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, pro_a=None, pro_b=None,
          rows_per_sample: int = 0, stats=None, stats_ns: int = 0) -> torch.Tensor:
-    """out[M,N] = pro(a[M,K]) @ b[N,K]^T.  a, b, out: bf16 2-D with unit inner stride (row strides free)."""
-    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1
+    """out[M,N] = pro(a[M,K]) @ b[N,K]^T.  a, b, out: bf16 or fp32 (TF32 math) 2-D with unit inner stride (row strides free)."""
+    assert a.dtype in TC_DTYPES and b.dtype == a.dtype and a.stride(1) == 1 and b.stride(1) == 1
     m, k = a.shape
     n = b.shape[0]
     if out is None:
-        out = torch.empty((m, n), dtype=torch.bfloat16, device=a.device)
+        out = torch.empty((m, n), dtype=a.dtype, device=a.device)
     assert out.stride(1) == 1
     gemm_raw(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), out.stride(0), m, n, k, a.device,
-             pro_a, pro_b, rows_per_sample, stats, 0, stats_ns)
+             pro_a, pro_b, rows_per_sample, stats, 0, stats_ns, dtype=nat.dtype_code(a.dtype))
     return out
 
 
 def gemm_bmn_raw(a_ptr: int, lda: int, b_ptr: int, ldb: int, d_ptr: int, ldd: int, m: int, n: int, k: int, device,
-                 sm_limit: int = 0) -> None:
+                 sm_limit: int = 0, dtype: int = nat.BF16) -> None:
     """d[m,n] = a[m,k] @ b[k,n] with b row-major [k][n] (no transposed copy; MN-major tensor-core operand)."""
-    nat.check(_lib().dlb_gemm_tc_bmn(a_ptr, lda, b_ptr, ldb, d_ptr, ldd, m, n, k, sm_limit, nat.stream_ptr(device)), "gemm_tc_bmn")
+    nat.check(_lib().dlb_gemm_tc_bmn_dt(dtype, a_ptr, lda, b_ptr, ldb, d_ptr, ldd, m, n, k, sm_limit, nat.stream_ptr(device)),
+              "gemm_tc_bmn")
 
 
 def gemm_bmn(a: torch.Tensor, b_kn: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     m, k = a.shape
     n = b_kn.shape[1]
     if out is None:
-        out = torch.empty((m, n), dtype=torch.bfloat16, device=a.device)
-    gemm_bmn_raw(a.data_ptr(), a.stride(0), b_kn.data_ptr(), b_kn.stride(0), out.data_ptr(), out.stride(0), m, n, k, a.device)
+        out = torch.empty((m, n), dtype=a.dtype, device=a.device)
+    gemm_bmn_raw(a.data_ptr(), a.stride(0), b_kn.data_ptr(), b_kn.stride(0), out.data_ptr(), out.stride(0), m, n, k, a.device,
+                 dtype=nat.dtype_code(a.dtype))
     return out
 
 
 def wgrad_raw(dy_ptr: int, lddy: int, x_ptr: int, ldx: int, dw: torch.Tensor, m: int, co: int, ci: int, device,
               pro_a: Optional[torch.Tensor] = None, pro_b: Optional[torch.Tensor] = None, rows_per_sample: int = 0,
-              sm_limit: int = 0) -> None:
+              sm_limit: int = 0, dtype: int = nat.BF16) -> None:
     """dw[co, ci] (fp32, pre-zeroed or accumulated into) += dy[m, co]^T @ pro(x[m, ci])."""
     pro_ld = pro_a.shape[1] if pro_a is not None else 0
-    rc = _lib().dlb_wgrad_tc(dy_ptr, lddy, x_ptr, ldx, dw.data_ptr(), dw.stride(0), m, co, ci, nat.ptr(pro_a), nat.ptr(pro_b),
+    rc = _lib().dlb_wgrad_tc_dt(dtype, dy_ptr, lddy, x_ptr, ldx, dw.data_ptr(), dw.stride(0), m, co, ci, nat.ptr(pro_a), nat.ptr(pro_b),
                              pro_ld, rows_per_sample, sm_limit, nat.stream_ptr(device))
     nat.check(rc, "wgrad_tc")
 
 
 def wgrad(dy: torch.Tensor, x: torch.Tensor, pro_a=None, pro_b=None, rows_per_sample: int = 0) -> torch.Tensor:
-    """-> fp32 [Co, Ci] = dy[M,Co]^T @ pro(x[M,Ci]); dy/x bf16 2-D with unit inner stride."""
+    """-> fp32 [Co, Ci] = dy[M,Co]^T @ pro(x[M,Ci]); dy/x bf16 or fp32 2-D with unit inner stride."""
     m, co = dy.shape
     ci = x.shape[1]
     dw = torch.zeros((co, ci), dtype=torch.float32, device=dy.device)
-    wgrad_raw(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dw, m, co, ci, dy.device, pro_a, pro_b, rows_per_sample)
+    wgrad_raw(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dw, m, co, ci, dy.device, pro_a, pro_b, rows_per_sample,
+              dtype=nat.dtype_code(dy.dtype))
     return dw
 
 
@@ -138,10 +153,10 @@ def conv3x3_profitable(h: int, w: int) -> bool:
 
 
 def conv3x3_raw(dgrad: bool, x_ptr: int, ldx: int, w_ptr: int, y_ptr: int, ldy: int, n: int, h: int, w: int, ci: int, co: int,
-                device, stats_ptr: int = 0, stats_ns: int = 0, sm_limit: int = 0) -> None:
+                device, stats_ptr: int = 0, stats_ns: int = 0, sm_limit: int = 0, dtype: int = nat.BF16) -> None:
     """3x3/s1/p1 NHWC conv on tcgen05: forward (x[N,H,W,ci] -> y[N,H,W,co]) or data gradient (x := dY[..,co] -> y := dX[..,ci]).
     Weight memory must be [co][3][3][ci] (channels-last OIHW).  ldx / ldy are pixel strides in elements."""
-    rc = _lib().dlb_conv3x3_tc(int(dgrad), x_ptr, ldx, w_ptr, y_ptr, ldy, n, h, w, ci, co, stats_ptr, stats_ns, sm_limit,
+    rc = _lib().dlb_conv3x3_tc_dt(dtype, int(dgrad), x_ptr, ldx, w_ptr, y_ptr, ldy, n, h, w, ci, co, stats_ptr, stats_ns, sm_limit,
                                nat.stream_ptr(device))
     nat.check(rc, "conv3x3_tc")
 
@@ -159,7 +174,7 @@ class _Conv3x3Fn(torch.autograd.Function):
         h, w = x.shape[2], x.shape[3]
         wk = _w_ohwi(weight)
         y = torch.empty((n, o, h, w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
-        conv3x3_raw(False, xv.data_ptr(), ld, wk.data_ptr(), y.data_ptr(), o, n, h, w, c, o, x.device)
+        conv3x3_raw(False, xv.data_ptr(), ld, wk.data_ptr(), y.data_ptr(), o, n, h, w, c, o, x.device, dtype=nat.dtype_code(x.dtype))
         ctx.save_for_backward(xv, weight)
         ctx.cfg = (n, h, w, c, ld, o)
         return y
@@ -173,7 +188,8 @@ class _Conv3x3Fn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             wk = _w_ohwi(weight)
             dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
-            conv3x3_raw(True, dyv.data_ptr(), lddy, wk.data_ptr(), dx.data_ptr(), c, n, h, w, c, o, dy.device)
+            conv3x3_raw(True, dyv.data_ptr(), lddy, wk.data_ptr(), dx.data_ptr(), c, n, h, w, c, o, dy.device,
+                        dtype=nat.dtype_code(dy.dtype))
         if ctx.needs_input_grad[1]:
             # weight gradient of the 3x3: vendor kernel (a 9-tap MN-major split-K tcgen05 variant is future work)
             x4 = torch.as_strided(xv, (n, c, h, w), (h * w * ld, 1, w * ld, ld))
@@ -200,7 +216,7 @@ class _Conv1x1Fn(torch.autograd.Function):
         h, w = x.shape[2], x.shape[3]
         y = torch.empty((n, o, h, w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
         w2 = _w2d(weight)
-        gemm_raw(xv.data_ptr(), ld, w2.data_ptr(), w2.stride(0), y.data_ptr(), o, n * hw, o, c, x.device)
+        gemm_raw(xv.data_ptr(), ld, w2.data_ptr(), w2.stride(0), y.data_ptr(), o, n * hw, o, c, x.device, dtype=nat.dtype_code(x.dtype))
         ctx.save_for_backward(xv, weight)
         ctx.cfg = (n, hw, c, ld, o, h, w)
         return y
@@ -215,24 +231,25 @@ class _Conv1x1Fn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
             # dX = dY * W with W = [Cout][Cin] consumed as an MN-major operand: no transposed weight copy
-            gemm_bmn_raw(dyv.data_ptr(), lddy, w2.data_ptr(), w2.stride(0), dx.data_ptr(), c, n * hw, c, o, dy.device)
+            gemm_bmn_raw(dyv.data_ptr(), lddy, w2.data_ptr(), w2.stride(0), dx.data_ptr(), c, n * hw, c, o, dy.device,
+                         dtype=nat.dtype_code(dy.dtype))
         if ctx.needs_input_grad[1]:
             dwf = torch.zeros((o, c), dtype=torch.float32, device=dy.device)
-            wgrad_raw(dyv.data_ptr(), lddy, xv.data_ptr(), ld, dwf, n * hw, o, c, dy.device)     # MN-major split-K tcgen05
+            wgrad_raw(dyv.data_ptr(), lddy, xv.data_ptr(), ld, dwf, n * hw, o, c, dy.device,     # MN-major split-K tcgen05
+                      dtype=nat.dtype_code(dy.dtype))
             dw = dwf.view(o, c, 1, 1).to(weight.dtype)
         return dx, dw
 
 
 def conv_supported(x, weight, stride, padding, groups) -> bool:
-    if not available():
+    if not available() or x.dtype not in TC_DTYPES or weight.dtype != x.dtype or x.dim() != 4 or groups != 1:
         return False
-    if (weight.dim() == 4 and weight.shape[2] == 3 and weight.shape[3] == 3 and stride == 1 and padding == 1 and groups == 1
-            and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and x.dim() == 4):
-        return (x.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0 and conv3x3_profitable(x.shape[2], x.shape[3])
-                and hasattr(nat.get(), "dlb_conv3x3_tc") and x.shape[0] * x.shape[2] * x.shape[3] >= 128)
-    return (x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and x.dim() == 4 and groups == 1
-            and stride == 1 and padding == 0 and weight.shape[2] == 1 and weight.shape[3] == 1
-            and x.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0 and x.shape[0] * x.shape[2] * x.shape[3] >= 128)
+    v = 8 if x.dtype == torch.bfloat16 else 4
+    if weight.dim() == 4 and weight.shape[2] == 3 and weight.shape[3] == 3 and stride == 1 and padding == 1:
+        return (x.shape[1] % v == 0 and weight.shape[0] % v == 0 and conv3x3_profitable(x.shape[2], x.shape[3])
+                and x.shape[0] * x.shape[2] * x.shape[3] >= 128)
+    return (stride == 1 and padding == 0 and weight.shape[2] == 1 and weight.shape[3] == 1
+            and x.shape[1] % v == 0 and weight.shape[0] % v == 0 and x.shape[0] * x.shape[2] * x.shape[3] >= 128)
 
 
 class _LinearFn(torch.autograd.Function):
@@ -244,7 +261,8 @@ class _LinearFn(torch.autograd.Function):
         t, k = x2.shape
         n = weight.shape[0]
         y = torch.empty((t, n), dtype=x2.dtype, device=x2.device)
-        gemm_raw(x2.data_ptr(), x2.stride(0), weight.data_ptr(), weight.stride(0), y.data_ptr(), n, t, n, k, x2.device)
+        gemm_raw(x2.data_ptr(), x2.stride(0), weight.data_ptr(), weight.stride(0), y.data_ptr(), n, t, n, k, x2.device,
+                 dtype=nat.dtype_code(x2.dtype))
         ctx.save_for_backward(x2, weight)
         return y
 
@@ -257,26 +275,28 @@ class _LinearFn(torch.autograd.Function):
         dx = dw = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty((t, k), dtype=dy.dtype, device=dy.device)
-            gemm_bmn_raw(dy.data_ptr(), n, weight.data_ptr(), weight.stride(0), dx.data_ptr(), k, t, k, n, dy.device)
+            gemm_bmn_raw(dy.data_ptr(), n, weight.data_ptr(), weight.stride(0), dx.data_ptr(), k, t, k, n, dy.device,
+                         dtype=nat.dtype_code(dy.dtype))
         if ctx.needs_input_grad[1]:
             dwf = torch.zeros((n, k), dtype=torch.float32, device=dy.device)
-            wgrad_raw(dy.data_ptr(), n, x2.data_ptr(), x2.stride(0), dwf, t, n, k, dy.device)
+            wgrad_raw(dy.data_ptr(), n, x2.data_ptr(), x2.stride(0), dwf, t, n, k, dy.device, dtype=nat.dtype_code(dy.dtype))
             dw = dwf.to(weight.dtype)
         return dx, dw
 
 
 def linear_supported(x, weight) -> bool:
-    if not available() or x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16 or weight.dim() != 2:
+    if not available() or x.dtype not in TC_DTYPES or weight.dtype != x.dtype or weight.dim() != 2:
         return False
     n, k = weight.shape
+    v = 8 if x.dtype == torch.bfloat16 else 4
     tokens = x.numel() // max(1, x.shape[-1])
-    return k % 8 == 0 and n % 8 == 0 and tokens >= 128 and weight.stride(1) == 1 and weight.stride(0) % 8 == 0
+    return k % v == 0 and n % v == 0 and tokens >= 128 and weight.stride(1) == 1 and weight.stride(0) % v == 0
 
 
 def linear(x, weight, bias=None):
     k = x.shape[-1]
     x2 = x.reshape(-1, k)
-    if x2.stride(1) != 1 or x2.stride(0) % 8 != 0 or (x2.data_ptr() & 15):
+    if x2.stride(1) != 1 or x2.stride(0) % (8 if x2.dtype == torch.bfloat16 else 4) != 0 or (x2.data_ptr() & 15):
         x2 = x2.contiguous()
     y = _LinearFn.apply(x2, weight).view(*x.shape[:-1], weight.shape[0])
     if bias is not None:

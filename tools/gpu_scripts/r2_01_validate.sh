@@ -3,11 +3,13 @@
 #   gpurun --timeout 1500 -- bash tools/gpu_scripts/r2_01_validate.sh
 mkdir -p gpurun_out; O=gpurun_out/r2_01; mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/gpu.txt
-echo "== gpu tests";       timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee $O/pytest_gpu.txt
+echo "== tf32 gemm tests"; timeout 600 python -m pytest tests/test_gpu_gemm_tf32.py -q 2>&1 | tail -15 | tee $O/pytest_tf32.txt
+echo "== gpu tests";       timeout 900 python -m pytest tests -m gpu -q --deselect tests/test_gpu_gemm_tf32.py 2>&1 | tail -8 | tee $O/pytest_gpu.txt
 echo "== experimental";    DLB_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_experimental.py -x -q 2>&1 | tail -8 | tee $O/pytest_exp.txt
 echo "== microbench";      timeout 300 python tools/bench_dgrad_gn.py 2>&1 | tail -10 | tee $O/bench_dgrad_gn.txt
 echo "== bench reference"; timeout 600 python bench.py --impl reference --steps 20 --warmup 5 2> $O/ref.err | tee $O/ref.json | cut -c1-300
 echo "== bench ours";      timeout 300 python bench.py --steps 20 --warmup 5 2> $O/ours.err | tee $O/ours.json | cut -c1-300
+echo "== bench ours tf32";  timeout 300 python bench.py --steps 20 --warmup 5 --dtype tf32 2> $O/ours_tf32.err | tee $O/ours_tf32.json | cut -c1-300
 echo "== bench ours FUSED_DGRAD"; DLB_FUSED_DGRAD=1 timeout 300 python bench.py --steps 20 --warmup 5 2> $O/ours_fd.err | tee $O/ours_fd.json | cut -c1-300
 for b in 512 64; do
   echo "== graph nodes, batch $b"
