@@ -44,6 +44,19 @@ struct CommArgs {
   unsigned long long timeout_ns;
 };
 
+// Optimizer step fused behind the collective (momentum SGD on the flat fp32 master / momentum buffers + bf16 shadow refresh
+// + clearing of the gradient accumulation buffer): runs as the last phase of the allreduce kernel of each bucket, so
+// "allreduce + optimizer" is ONE launch per bucket (reference: per-tensor scale + all_reduce + wait, then torch.optim.SGD's
+// per-tensor loop, dbs.py:291-301,238).
+struct SgdArgs {
+  float* master;            // fp32 parameters (flat, same element indexing as the gradient buffers); nullptr = no fused step
+  float* mom;
+  __nv_bfloat16* shadow;    // bf16 compute copy of the parameters (may be null)
+  const float* lr;          // device scalar
+  float mu, wd;
+  float* zero_in;           // this rank's gradient accumulation buffer, cleared after use (may be null)
+};
+
 __device__ __forceinline__ uint32_t cas_release_sys(uint32_t* addr, uint32_t cmp, uint32_t val) {
   uint32_t old;
   asm volatile("atom.global.release.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(addr), "r"(cmp), "r"(val) : "memory");
@@ -170,7 +183,7 @@ __device__ __forceinline__ void pull_reduce(const CommArgs& a, const float (&w)[
 
 template <typename T, int ALGO, int WORLD>
 __global__ void __launch_bounds__(kCommThreads, 1)
-weighted_allreduce_kernel(const __grid_constant__ CommArgs a, long long offset, long long count) {
+weighted_allreduce_kernel(const __grid_constant__ CommArgs a, long long offset, long long count, const SgdArgs sgd) {
   constexpr int V = Wire<T>::V;
   const int world = WORLD > 0 ? WORLD : a.world;
   float w[kMaxWorld];
@@ -236,6 +249,49 @@ weighted_allreduce_kernel(const __grid_constant__ CommArgs a, long long offset, 
   // ---- exit barrier: all pushes have landed / all peers are done reading my input --------------
   __threadfence_system();
   block_barrier(a, 1);
+
+  // ---- fused optimizer step ---------------------------------------------------------------------
+  // block_barrier orders block b here only against block b of every peer.  Peer r's block b produced / consumed exactly
+  // the vectors  c0_r + b*blockDim + t + k*grid*blockDim  of chunk r (two-shot / NVLS), and this rank's block b produced
+  // the vectors  b*blockDim + t + k*grid*blockDim  of the whole bucket (one-shot): block b therefore updates precisely
+  // those elements -- no grid-wide synchronisation is needed and every element is updated exactly once.
+  if (sgd.master != nullptr) {
+    const float lr = *sgd.lr;
+    const T* red = (const T*)a.out[a.rank] + offset;
+    auto update = [&](long long v) {
+      float g[V];
+      Wire<T>::load(red + v * V, g);
+      const long long e = offset + v * V;
+#pragma unroll
+      for (int q = 0; q < V; q += 4) {
+        float4 pv = *reinterpret_cast<float4*>(sgd.master + e + q);
+        float4 mv = *reinterpret_cast<float4*>(sgd.mom + e + q);
+        mv.x = fmaf(sgd.mu, mv.x, fmaf(sgd.wd, pv.x, g[q]));     mv.y = fmaf(sgd.mu, mv.y, fmaf(sgd.wd, pv.y, g[q + 1]));
+        mv.z = fmaf(sgd.mu, mv.z, fmaf(sgd.wd, pv.z, g[q + 2])); mv.w = fmaf(sgd.mu, mv.w, fmaf(sgd.wd, pv.w, g[q + 3]));
+        pv.x = fmaf(-lr, mv.x, pv.x); pv.y = fmaf(-lr, mv.y, pv.y); pv.z = fmaf(-lr, mv.z, pv.z); pv.w = fmaf(-lr, mv.w, pv.w);
+        *reinterpret_cast<float4*>(sgd.master + e + q) = pv;
+        *reinterpret_cast<float4*>(sgd.mom + e + q) = mv;
+        if (sgd.shadow) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(pv.x, pv.y), hi = __floats2bfloat162_rn(pv.z, pv.w);
+          uint2 raw; raw.x = *reinterpret_cast<unsigned*>(&lo); raw.y = *reinterpret_cast<unsigned*>(&hi);
+          *reinterpret_cast<uint2*>(sgd.shadow + e + q) = raw;
+        }
+        if (sgd.zero_in) *reinterpret_cast<float4*>(sgd.zero_in + e + q) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    const long long nvec = count / V;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if constexpr (ALGO == ONESHOT) {
+      for (long long v = first; v < nvec; v += stride) update(v);
+    } else {
+      const long long per = (nvec + world - 1) / world;
+      for (int r = 0; r < world; ++r) {
+        const long long c0 = min(nvec, per * r), c1 = min(nvec, c0 + per);
+        for (long long v = c0 + first; v < c1; v += stride) update(v);
+      }
+    }
+  }
 }
 
 // One launch: store my scalar into slot [rank] of every peer's table, barrier, done.
@@ -263,13 +319,13 @@ struct CommCtx {
 };
 
 template <typename T, int ALGO>
-void launch_allreduce(const CommArgs& a, long long offset, long long count, int blocks, cudaStream_t st) {
+void launch_allreduce(const CommArgs& a, long long offset, long long count, int blocks, cudaStream_t st, const SgdArgs& sgd) {
   switch (a.world) {
-    case 1: weighted_allreduce_kernel<T, ALGO, 1><<<blocks, kCommThreads, 0, st>>>(a, offset, count); break;
-    case 2: weighted_allreduce_kernel<T, ALGO, 2><<<blocks, kCommThreads, 0, st>>>(a, offset, count); break;
-    case 4: weighted_allreduce_kernel<T, ALGO, 4><<<blocks, kCommThreads, 0, st>>>(a, offset, count); break;
-    case 8: weighted_allreduce_kernel<T, ALGO, 8><<<blocks, kCommThreads, 0, st>>>(a, offset, count); break;
-    default: weighted_allreduce_kernel<T, ALGO, 0><<<blocks, kCommThreads, 0, st>>>(a, offset, count); break;
+    case 1: weighted_allreduce_kernel<T, ALGO, 1><<<blocks, kCommThreads, 0, st>>>(a, offset, count, sgd); break;
+    case 2: weighted_allreduce_kernel<T, ALGO, 2><<<blocks, kCommThreads, 0, st>>>(a, offset, count, sgd); break;
+    case 4: weighted_allreduce_kernel<T, ALGO, 4><<<blocks, kCommThreads, 0, st>>>(a, offset, count, sgd); break;
+    case 8: weighted_allreduce_kernel<T, ALGO, 8><<<blocks, kCommThreads, 0, st>>>(a, offset, count, sgd); break;
+    default: weighted_allreduce_kernel<T, ALGO, 0><<<blocks, kCommThreads, 0, st>>>(a, offset, count, sgd); break;
   }
 }
 
@@ -309,8 +365,8 @@ DLB_API int dlb_comm_max_blocks() { return kMaxBlocks; }
 
 // algo: 0 one-shot, 1 two-shot, 2 nvls.  wire: DLB_F32 / DLB_BF16.  offset/count in elements; count must be
 // a multiple of the 16-byte vector width.  weights_dev: device float[world] (or null with host weights / none).
-DLB_API int dlb_weighted_allreduce(void* ctx, int algo, int wire, long long offset, long long count, int blocks,
-                                   const float* weights_dev, const float* weights_host, void* stream) {
+static int weighted_allreduce_impl(void* ctx, int algo, int wire, long long offset, long long count, int blocks,
+                                   const float* weights_dev, const float* weights_host, const SgdArgs& sgd, void* stream) {
   CommCtx* c = (CommCtx*)ctx;
   CommArgs a = c->args;
   a.weights_dev = weights_dev;
@@ -324,13 +380,31 @@ DLB_API int dlb_weighted_allreduce(void* ctx, int algo, int wire, long long offs
   cudaStream_t st = (cudaStream_t)stream;
 #define GO(T)                                                              \
   do {                                                                     \
-    if (algo == ONESHOT) launch_allreduce<T, ONESHOT>(a, offset, count, blocks, st);      \
-    else if (algo == TWOSHOT) launch_allreduce<T, TWOSHOT>(a, offset, count, blocks, st); \
-    else launch_allreduce<T, NVLS>(a, offset, count, blocks, st);          \
+    if (algo == ONESHOT) launch_allreduce<T, ONESHOT>(a, offset, count, blocks, st, sgd);      \
+    else if (algo == TWOSHOT) launch_allreduce<T, TWOSHOT>(a, offset, count, blocks, st, sgd); \
+    else launch_allreduce<T, NVLS>(a, offset, count, blocks, st, sgd);          \
   } while (0)
   if (wire == DLB_BF16) GO(__nv_bfloat16); else GO(float);
 #undef GO
   return dlb_post_launch();
+}
+
+DLB_API int dlb_weighted_allreduce(void* ctx, int algo, int wire, long long offset, long long count, int blocks,
+                                   const float* weights_dev, const float* weights_host, void* stream) {
+  SgdArgs none = {};
+  return weighted_allreduce_impl(ctx, algo, wire, offset, count, blocks, weights_dev, weights_host, none, stream);
+}
+
+// Same collective with the optimizer step fused behind it (see SgdArgs): master/mom fp32 [numel], shadow bf16 or null,
+// zero_in = this rank's gradient accumulation buffer to clear (or null).
+DLB_API int dlb_weighted_allreduce_sgd(void* ctx, int algo, int wire, long long offset, long long count, int blocks,
+                                       const float* weights_dev, float* master, float* mom, void* shadow, const float* lr_ptr,
+                                       float* zero_in, float momentum, float weight_decay, void* unused, void* stream) {
+  (void)unused;
+  SgdArgs sgd;
+  sgd.master = master; sgd.mom = mom; sgd.shadow = (__nv_bfloat16*)shadow; sgd.lr = lr_ptr; sgd.mu = momentum; sgd.wd = weight_decay;
+  sgd.zero_in = zero_in;
+  return weighted_allreduce_impl(ctx, algo, wire, offset, count, blocks, weights_dev, nullptr, sgd, stream);
 }
 
 // tables: `out` pointers of a context created over the (small) symmetric time-table buffers.

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) mt_pack_kernel(const __grid_constant__ Te
 __global__ void __launch_bounds__(256) sgd_flat_kernel(float* __restrict__ p, float* __restrict__ v,
                                                        const float* __restrict__ g, __nv_bfloat16* __restrict__ shadow,
                                                        long long n, const float* __restrict__ lr_ptr, float mu, float wd,
-                                                       const float* __restrict__ sumsq, float max_norm) {
+                                                       const float* __restrict__ sumsq, float max_norm, float* __restrict__ zero_buf) {
   const float lr = *lr_ptr;
   // post-reduce ("global") gradient clipping: the coefficient of clip_grad_norm_ applied to the REDUCED gradient,
   // folded into the update so no separate scale pass runs (--clip_mode global; the reference clips locally, dbs.py:274)
@@ -105,6 +105,8 @@ __global__ void __launch_bounds__(256) sgd_flat_kernel(float* __restrict__ p, fl
     pv.z = fmaf(-lr, vv.z, pv.z); pv.w = fmaf(-lr, vv.w, pv.w);
     reinterpret_cast<float4*>(p)[i] = pv;
     reinterpret_cast<float4*>(v)[i] = vv;
+    // the gradient accumulation buffer (gradient sinks write into it with red.add) is cleared for the next step here
+    if (zero_buf) reinterpret_cast<float4*>(zero_buf)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (shadow) {
       __nv_bfloat162 lo = __floats2bfloat162_rn(pv.x, pv.y), hi = __floats2bfloat162_rn(pv.z, pv.w);
       uint2 raw;
@@ -118,6 +120,7 @@ __global__ void __launch_bounds__(256) sgd_flat_kernel(float* __restrict__ p, fl
     const float vv = fmaf(mu, v[i], fmaf(wd, p[i], gs * g[i]));
     const float pv = fmaf(-lr, vv, p[i]);
     v[i] = vv; p[i] = pv;
+    if (zero_buf) zero_buf[i] = 0.f;
     if (shadow) shadow[i] = __float2bfloat16(pv);
   }
 }
@@ -179,19 +182,19 @@ DLB_API int dlb_mt_pack(int count, const void* const* ptrs, const long long* off
 }
 
 DLB_API int dlb_sgd_flat_clip(float* p, float* v, const float* g, void* shadow, long long n, const float* lr_ptr,
-                              float momentum, float weight_decay, const float* sumsq, float max_norm, void* stream) {
+                              float momentum, float weight_decay, const float* sumsq, float max_norm, float* zero_buf, void* stream) {
   if (n <= 0) return 0;
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   sgd_flat_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, v, g, (__nv_bfloat16*)shadow, n, lr_ptr, momentum, weight_decay,
-                                                                  sumsq, max_norm);
+                                                                  sumsq, max_norm, zero_buf);
   return dlb_post_launch();
 }
 
 DLB_API int dlb_sgd_flat(float* p, float* v, const float* g, void* shadow, long long n, const float* lr_ptr,
                          float momentum, float weight_decay, void* stream) {
-  return dlb_sgd_flat_clip(p, v, g, shadow, n, lr_ptr, momentum, weight_decay, nullptr, 0.f, stream);
+  return dlb_sgd_flat_clip(p, v, g, shadow, n, lr_ptr, momentum, weight_decay, nullptr, 0.f, nullptr, stream);
 }
 
 DLB_API int dlb_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {

@@ -92,7 +92,8 @@ class Trainer:
         torch.manual_seed(cfg.seed)
         self.model = build_model(cfg.model, cfg.num_classes, self.ntokens)
         self.flat = FlatState(self.model, self.device, self.dtype, self.comm, cfg.learning_rate, cfg.momentum,
-                              0.0, cfg.bucket_mb, _DT[cfg.wire_dtype], cfg.resolved_clip(), cfg.clip_mode)
+                              0.0, cfg.bucket_mb, _DT[cfg.wire_dtype], cfg.resolved_clip(), cfg.clip_mode,
+                              seed_weighting=self.cuda and not self.is_lm)
         self.flat.sync_initial_params()
         if cfg.overlap_comm:
             self.flat.enable_overlap()
@@ -151,7 +152,7 @@ class Trainer:
                 loss = self.model.forward_loss(x, y)
             else:
                 out = self.model(x)
-                loss = ops.cross_entropy(out, y)
+                loss = ops.cross_entropy(out, y, grad_scale=self.flat.seed_scale())
         with self.tracer.range("backward"):
             loss.backward()
         return loss.detach()
@@ -195,8 +196,10 @@ class Trainer:
         b = int(yb.shape[0]) if not self.is_lm else int(xb.shape[1])
         # gloo collectives (several ranks sharing a GPU, reference `-gpu 0,0,0,1`) cannot be stream-captured
         # profiling runs stay eager: a replayed graph is one opaque launch, the NVTX ranges would be empty
+        # (DLB_PROFILE_GRAPHS=1 keeps the graph under --profile: CUPTI still records the replayed kernels with their streams,
+        # which is what tools/trace_overlap.py needs to show the bucket collectives overlapping the backward pass)
         use_graph = (self.cuda and self.cfg.cuda_graphs and ops._native.available() and self.comm.name != "gloo"
-                     and not self.cfg.profile)
+                     and not (self.cfg.profile and os.environ.get("DLB_PROFILE_GRAPHS", "0") != "1"))
         if use_graph:
             g = self._graphs.get(b)
             if g is None:

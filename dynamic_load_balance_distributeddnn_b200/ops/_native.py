@@ -71,7 +71,9 @@ def _declare(lib: ctypes.CDLL) -> None:
         "dlb_mt_sumsq": (i32, [i32, vp, vp, vp, vp, vp]),
         "dlb_mt_pack": (i32, [i32, vp, vp, vp, vp, vp, i32, vp, i32, vp, c_float, vp]),
         "dlb_sgd_flat": (i32, [vp, vp, vp, vp, i64, vp, c_float, c_float, vp]),
-        "dlb_sgd_flat_clip": (i32, [vp, vp, vp, vp, i64, vp, c_float, c_float, vp, c_float, vp]),
+        "dlb_sgd_flat_clip": (i32, [vp, vp, vp, vp, i64, vp, c_float, c_float, vp, c_float, vp, vp]),
+        "dlb_softmax_ce_small": (i32, [i32, vp, i64, vp, vp, vp, vp, i32, i32, vp]),
+        "dlb_weighted_allreduce_sgd": (i32, [vp, i32, i32, i64, i64, i32, vp, vp, vp, vp, vp, vp, c_float, c_float, vp, vp]),
         "dlb_cast_f32_bf16": (i32, [vp, vp, i64, vp]),
         "dlb_zero_f32": (i32, [vp, i64, vp]),
         "dlb_augment": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, c_uint, vp, vp]),

@@ -64,7 +64,8 @@ def _conv_fwd(x, w, pad):
 
 class _DenseBlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, eps, groups, *params):
+    def forward(ctx, x, eps, groups, sink, *params):
+        ctx.sink = sink
         try:
             return _DenseBlockFn._forward_impl(ctx, x, eps, groups, *params)
         finally:
@@ -213,6 +214,13 @@ class _DenseBlockFn(torch.autograd.Function):
             w_off.append(w_off[-1] + cm0 * (c0 + l * g))
         lib.dlb_norm_skip_zero(1)
         dw1_views = [None] * n_layers
+        # gradient sinks (parallel/buckets.py): parameter gradients are accumulated by the kernels below straight into their
+        # slices of the flat symmetric gradient buffer (fp32, zero at this point) -- no .grad tensor, no cast, no pack pass
+        sink = ctx.sink
+        sv = None
+        if sink is not None:
+            flat, sidx = sink
+            sv = [flat.sink_view(i) for i in sidx]
         main = torch.cuda.current_stream(buf.device)
         side = _side_stream(buf.device) if (_USE_SIDE and buf.dtype in gemm_tc.TC_DTYPES) else None
         conv3_ok = (buf.dtype in gemm_tc.TC_DTYPES and gemm_tc.available() and gemm_tc.conv3x3_profitable(h, w) and _USE_CONV3
@@ -252,6 +260,13 @@ class _DenseBlockFn(torch.autograd.Function):
             t1 = arena[o:o + sizes[l][3]]; o += sizes[l][3]
             dg1 = arena[o:o + cl]; o += cl
             db1 = arena[o:o + cl]
+            sunk = []
+            if sv is not None and ca2.numel() > 0:
+                dg2, db2 = sv[6 * l + 3], sv[6 * l + 4]
+                sunk += [sidx[6 * l + 3], sidx[6 * l + 4]]
+            if sv is not None and xhat.numel() == 0:
+                dg1, db1 = sv[6 * l + 0], sv[6 * l + 1]
+                sunk += [sidx[6 * l + 0], sidx[6 * l + 1], sidx[6 * l + 2]]
             if ca2.numel() > 0:
                 # ReLU mask recomputed from the forward's affine coefficients: yhat is not re-read by the GN2 backward
                 kp2 = ca2.shape[1]
@@ -278,14 +293,15 @@ class _DenseBlockFn(torch.autograd.Function):
                     dxhat = torch.empty((n, cl, h, w), dtype=buf.dtype, device=buf.device, memory_format=torch.channels_last)
                     gemm_tc.gemm_bmn_raw(dy.data_ptr(), cm, w1_2d.data_ptr(), w1_2d.stride(0), dxhat.data_ptr(), cl, n * hw, cl, cm,
                                          buf.device, dtype=dt)
+                dw1_sunk = sv is not None
                 if side is not None:
                     ev_dy = torch.cuda.Event(); ev_dy.record(main)
                     side.wait_event(ev_dy)
-                    dw1f = dw1_arena[w_off[l]:w_off[l + 1]].view(cm, cl)
+                    dw1f = sv[6 * l + 2].view(cm, cl) if dw1_sunk else dw1_arena[w_off[l]:w_off[l + 1]].view(cm, cl)
                     with torch.cuda.stream(side):
                         gemm_tc.wgrad_raw(dy.data_ptr(), cm, xs, ct, dw1f, n * hw, cm, cl, buf.device, ca, cb, hw, dtype=dt)
                 else:
-                    dw1f = dw1_arena[w_off[l]:w_off[l + 1]].view(cm, cl)
+                    dw1f = sv[6 * l + 2].view(cm, cl) if dw1_sunk else dw1_arena[w_off[l]:w_off[l + 1]].view(cm, cl)
                     gemm_tc.wgrad_raw(dy.data_ptr(), cm, xs, ct, dw1f, n * hw, cm, cl, buf.device, ca, cb, hw, dtype=dt)
                 dw1 = None                      # cast for all layers at once after the loop
                 kpad = ca.shape[1]
@@ -319,6 +335,11 @@ class _DenseBlockFn(torch.autograd.Function):
                 main.wait_event(ev_out)            # per-layer join: every tensor the side stream touched is still referenced here
             grads[6 * l:6 * l + 6] = [dg1.to(g1w.dtype), db1.to(g1b.dtype), dw1.to(w1.dtype) if dw1 is not None else None,
                                       dg2.to(g2w.dtype), db2.to(g2b.dtype), dw2.to(w2.dtype)]
+            if sunk:
+                for k in range(6):
+                    if sidx[6 * l + k] in sunk:
+                        grads[6 * l + k] = False          # placeholder: written into its sink, nothing to return
+                flat.mark_sunk(sunk)                     # may fire this bucket's collective (all writes are ordered before it)
         lib.dlb_norm_skip_zero(0)
         if any(grads[6 * l + 2] is None for l in range(n_layers)):
             dw1_cast = dw1_arena.to(params[2].dtype)            # ONE cast kernel for every 1x1 weight gradient
@@ -328,7 +349,8 @@ class _DenseBlockFn(torch.autograd.Function):
                     grads[6 * l + 2] = dw1_cast[w_off[l]:w_off[l + 1]].view(cm0, cl_, 1, 1)
         dx = torch.empty((n, c0, h, w), dtype=buf.dtype, device=buf.device, memory_format=torch.channels_last)
         _copy_slice(lib, dbuf[:, ct - c0:], dx, st)
-        return (dx, None, None, *grads)
+        grads = [None if g_ is False else g_ for g_ in grads]
+        return (dx, None, None, None, *grads)
 
 
 def run(stage, x: torch.Tensor) -> torch.Tensor:
@@ -336,6 +358,12 @@ def run(stage, x: torch.Tensor) -> torch.Tensor:
     for blk in stage:
         params += [blk.gn1.weight, blk.gn1.bias, blk.conv1.weight, blk.gn2.weight, blk.gn2.bias, blk.conv2.weight]
     first = stage[0]
-    out, table = _DenseBlockFn.apply(x, float(first.gn1.eps), int(first.gn1.num_groups), *params)
+    sink = None
+    hs = [getattr(p, "_dlb_sink", None) for p in params]
+    if torch.is_grad_enabled() and all(h is not None for h in hs):
+        flat = hs[0].flat()
+        if flat is not None and flat.sinks_enabled and x.dtype in gemm_tc.TC_DTYPES:
+            sink = (flat, [h.index for h in hs])
+    out, table = _DenseBlockFn.apply(x, float(first.gn1.eps), int(first.gn1.num_groups), sink, *params)
     out._dlb_nc_table = table           # (Σx, Σx²) per (sample, channel): lets the next GroupNorm skip its stats pass
     return out

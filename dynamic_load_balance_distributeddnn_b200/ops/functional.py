@@ -45,9 +45,40 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return F.linear(x, weight, bias)
 
 
-def cross_entropy(logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-    """Mean cross-entropy in fp32 regardless of the logits dtype."""
-    return F.cross_entropy(logits.float(), target)
+class _SoftmaxCEFn(torch.autograd.Function):
+    """mean softmax cross-entropy: loss and d(loss)/d(logits) from ONE kernel (``csrc/loss.cu``); the gradient seed is
+    multiplied by ``grad_scale`` (a device scalar: the rank's DBS weight) inside that kernel."""
+
+    @staticmethod
+    def forward(ctx, logits, target, grad_scale):
+        lib = nat.require()
+        b, c = logits.shape
+        lg = logits if logits.stride(1) == 1 else logits.contiguous()
+        dlog = torch.empty((b, c), dtype=torch.float32, device=logits.device)
+        loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        nat.check(lib.dlb_softmax_ce_small(nat.dtype_code(lg.dtype), lg.data_ptr(), lg.stride(0), target.data_ptr(), dlog.data_ptr(),
+                                           loss.data_ptr(), nat.ptr(grad_scale), b, c, nat.stream_ptr(logits.device)), "softmax_ce")
+        ctx.save_for_backward(dlog)
+        ctx.in_dtype = logits.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, go):
+        (dlog,) = ctx.saved_tensors
+        return (dlog * go).to(ctx.in_dtype), None, None
+
+
+def cross_entropy(logits: torch.Tensor, target: torch.Tensor, grad_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Mean cross-entropy in fp32 regardless of the logits dtype.  ``grad_scale`` (device scalar) multiplies the gradient
+    seed only -- the returned loss value is unscaled."""
+    if (logits.is_cuda and nat.available() and logits.dim() == 2 and logits.shape[1] <= 1024 and target.dtype == torch.int64
+            and logits.dtype in (torch.float32, torch.bfloat16) and hasattr(nat.get(), "dlb_softmax_ce_small")):
+        return _SoftmaxCEFn.apply(logits, target.contiguous(), grad_scale)
+    loss = F.cross_entropy(logits.float(), target)
+    if grad_scale is not None and loss.requires_grad:
+        # value unchanged, gradient scaled:  loss + (s - 1) * (loss - loss.detach())
+        loss = loss.detach() + grad_scale.reshape(()).to(loss.dtype) * (loss - loss.detach())
+    return loss
 
 
 def nll_loss(log_probs: torch.Tensor, target: torch.Tensor) -> torch.Tensor:

@@ -19,7 +19,9 @@ from __future__ import annotations
 
 import ctypes
 import math
-from typing import List, Sequence, Tuple
+import os
+import weakref
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.nn as nn
@@ -34,6 +36,16 @@ def _is_conv_weight(p: torch.Tensor) -> bool:
     return p.dim() == 4
 
 
+class GradSink:
+    """Handle attached to a parameter (``p._dlb_sink``): ops with hand-written backward kernels write that parameter's
+    gradient straight into its slice of the flat (symmetric) gradient buffer instead of returning a ``.grad`` tensor."""
+    __slots__ = ("flat", "index")
+
+    def __init__(self, flat: "FlatState", index: int):
+        self.flat = weakref.ref(flat)
+        self.index = index
+
+
 def _flat_order(t: torch.Tensor) -> torch.Tensor:
     """1-D view/copy of ``t`` in the order it is stored in the flat buffers: conv weights are kept
     O-H-W-I (channels-last), i.e. exactly the K-major [Cout][kh][kw][Cin] operand layout the implicit-GEMM
@@ -46,7 +58,8 @@ def _flat_order(t: torch.Tensor) -> torch.Tensor:
 class FlatState:
     def __init__(self, model: nn.Module, device, compute_dtype: torch.dtype, comm: Comm,
                  lr: float, momentum: float = 0.9, weight_decay: float = 0.0, bucket_mb: float = 8.0,
-                 wire_dtype: torch.dtype = torch.float32, clip_norm: float = 0.0, clip_mode: str = "local"):
+                 wire_dtype: torch.dtype = torch.float32, clip_norm: float = 0.0, clip_mode: str = "local",
+                 seed_weighting: bool = False):
         self.device = torch.device(device)
         self.comm = comm
         self.params: List[nn.Parameter] = [p for p in model.parameters()]
@@ -88,6 +101,21 @@ class FlatState:
         self._pack_cache = None
         self._rank = getattr(comm, "rank", 0)
         self._keep_overlap = []
+        # ---- gradient path without a scale / pack pass (north star: "no separate elementwise kernel on that path") --------
+        # seed weighting: the DBS weight w_r multiplies the loss-gradient seed (fused CE kernel), so every gradient the
+        #   backward pass produces is already weighted and the collective runs unweighted (NVLS in-switch reduction);
+        # sinks: backward kernels (dense-block wgrad, GroupNorm affine grads) accumulate straight into the flat symmetric
+        #   buffer; only the few remaining .grad tensors still go through the multi-tensor pack;
+        # fused SGD: the optimizer step runs as the last phase of each bucket's allreduce kernel.
+        self.seed_weighting = bool(seed_weighting) and self.native
+        self.sinks_enabled = (self.seed_weighting and wire_dtype == torch.float32 and self.clip_norm == 0
+                              and os.environ.get("DLB_GRAD_SINKS", "1") == "1")
+        self.fused_sgd = (self.native and max(1, comm.world) > 1 and self.global_clip == 0 and hasattr(comm, "allreduce_buckets_sgd")
+                          and os.environ.get("DLB_FUSED_SGD", "1") == "1")
+        self._sunk = [False] * len(self.params)
+        if self.sinks_enabled:
+            for i, p in enumerate(self.params):
+                p._dlb_sink = GradSink(self, i)
 
     # ---- parameter adoption -----------------------------------------------------------------------
     def _adopt(self, model: nn.Module) -> None:
@@ -154,6 +182,56 @@ class FlatState:
             self._hooks.append(p.register_post_accumulate_grad_hook(lambda _p, i=i: self._on_grad(i)))
         return True
 
+    # ---- gradient sinks ----------------------------------------------------------------------------------
+    def sinks_active(self) -> bool:
+        return self.sinks_enabled and torch.is_grad_enabled() is not None
+
+    def sink_view(self, i: int) -> torch.Tensor:
+        """fp32 view of parameter i's slice of the (zero-initialised, cleared by the optimizer step) gradient buffer, in the
+        flat layout: conv weights [O][kh][kw][I], everything else the parameter's own shape."""
+        p, off = self.params[i], self.offsets[i]
+        v = self.grad_in[off:off + p.numel()]
+        if _is_conv_weight(p):
+            o, c, kh, kw = p.shape
+            return v.view(o, kh, kw, c)
+        return v.view(p.shape)
+
+    def mark_sunk(self, indices: Sequence[int]) -> None:
+        """The gradients of these parameters have been written into their sinks (on the current stream)."""
+        for i in indices:
+            self._sunk[i] = True
+        if getattr(self, "_overlap", False):
+            for i in indices:
+                self._on_grad(i)
+
+    def seed_scale(self) -> Optional[torch.Tensor]:
+        """device scalar the loss-gradient seed is multiplied by (this rank's DBS weight), or None"""
+        return self.weights_t[self._rank:self._rank + 1] if self.seed_weighting else None
+
+    def _sgd_args(self):
+        return {"master": self.master.data_ptr(), "mom": self.mom.data_ptr(), "shadow": nat.ptr(self.shadow),
+                "lr": self.lr_t.data_ptr(), "momentum": float(self.momentum), "weight_decay": float(self.weight_decay),
+                "zero_in": self.grad_in.data_ptr() if self.sinks_enabled else 0}
+
+    def _allreduce(self, buckets) -> float:
+        if self.fused_sgd:
+            return self.comm.allreduce_buckets_sgd(self.grad_in, self.grad_out, buckets, self._sgd_args())
+        return self.comm.allreduce_buckets(self.grad_in, self.grad_out, buckets)
+
+    def _pack(self, subset, rank: int, use_clip: bool = False) -> None:
+        lib = nat.require()
+        st = nat.stream_ptr(self.device)
+        ptrs, offs, numels, dtypes, n, keep = self._grad_lists(subset)
+        if n == 0:
+            return keep
+        if use_clip:
+            nat.check(lib.dlb_zero_f32(self.sumsq_t.data_ptr(), 1, st), "zero")
+            nat.check(lib.dlb_mt_sumsq(n, ptrs, numels, dtypes, self.sumsq_t.data_ptr(), st), "mt_sumsq")
+        nat.check(lib.dlb_mt_pack(n, ptrs, offs, numels, dtypes, self.grad_in.data_ptr(), nat.dtype_code(self.wire_dtype),
+                                  None if self.seed_weighting else self.weights_t.data_ptr(), rank,
+                                  self.sumsq_t.data_ptr() if use_clip else None, float(self.clip_norm), st), "mt_pack")
+        return keep
+
     def _on_grad(self, i: int) -> None:
         b = self._bucket_of[i]
         self._pending[b] -= 1
@@ -161,19 +239,14 @@ class FlatState:
             self._fire(b)
 
     def _fire(self, b: int) -> None:
-        lib = nat.require()
         main = torch.cuda.current_stream(self.device)
         ev = torch.cuda.Event()
         ev.record(main)
         self._comm_stream.wait_event(ev)
-        idxs = self.bucket_params[b]
+        idxs = [i for i in self.bucket_params[b] if not self._sunk[i]]
         with torch.cuda.stream(self._comm_stream):
-            ptrs, offs, numels, dtypes, n, keep = self._grad_lists(idxs)
-            nat.check(lib.dlb_mt_pack(n, ptrs, offs, numels, dtypes, self.grad_in.data_ptr(), nat.dtype_code(self.wire_dtype),
-                                      self.weights_t.data_ptr(), self._rank, None, 0.0,
-                                      nat.stream_ptr(self.device)), "mt_pack")
-            self._keep_overlap.append(keep)
-            self.comm.allreduce_buckets(self.grad_in, self.grad_out, [self.buckets[b]])
+            self._keep_overlap.append(self._pack(idxs, self._rank))
+            self._allreduce([self.buckets[b]])
         self._fired[b] = True
 
     # ---- synchronisation helpers ------------------------------------------------------------------
@@ -202,7 +275,9 @@ class FlatState:
     # ---- the post-backward pipeline ---------------------------------------------------------------
     def _grad_lists(self, subset=None):
         ptrs, offs, numels, dtypes, keep = [], [], [], [], []
-        it = zip(self.params, self.offsets) if subset is None else ((self.params[i], self.offsets[i]) for i in subset)
+        if subset is None:
+            subset = [i for i in range(len(self.params)) if not self._sunk[i]]
+        it = ((self.params[i], self.offsets[i]) for i in subset)
         for p, off in it:
             g = p.grad
             if g is None:
@@ -243,11 +318,9 @@ class FlatState:
             sumsq = self.sumsq_t
         nat.check(lib.dlb_sgd_flat_clip(self.master.data_ptr(), self.mom.data_ptr(), g.data_ptr(), nat.ptr(self.shadow), self.numel,
                                         self.lr_t.data_ptr(), float(self.momentum), float(self.weight_decay), nat.ptr(sumsq),
-                                        float(self.global_clip), st), "sgd_flat")
+                                        float(self.global_clip), self.grad_in.data_ptr() if self.sinks_enabled else None, st), "sgd_flat")
 
     def _reduce_and_step_native(self, rank: int) -> float:
-        lib = nat.require()
-        st = nat.stream_ptr(self.device)
         if getattr(self, "_overlap", False):
             # buckets were (mostly) fired from the autograd hooks; flush stragglers, join the comm stream, update
             for b in range(len(self.buckets)):
@@ -256,26 +329,22 @@ class FlatState:
             ev = torch.cuda.Event()
             ev.record(self._comm_stream)
             torch.cuda.current_stream(self.device).wait_event(ev)
-            self._sgd_native(self.grad_out)
+            if not self.fused_sgd:
+                self._sgd_native(self.grad_out)
             self._pending = [len(gp) for gp in self.bucket_params]
             self._fired = [False] * len(self.buckets)
             self._keep, self._keep_overlap = self._keep_overlap, []
+            self._sunk = [False] * len(self.params)
             return 0.0
-        ptrs, offs, numels, dtypes, n, keep = self._grad_lists()
-        use_clip = self.clip_norm > 0
-        if use_clip:
-            nat.check(lib.dlb_zero_f32(self.sumsq_t.data_ptr(), 1, st), "zero")
-            nat.check(lib.dlb_mt_sumsq(n, ptrs, numels, dtypes, self.sumsq_t.data_ptr(), st), "mt_sumsq")
-        nat.check(lib.dlb_mt_pack(n, ptrs, offs, numels, dtypes, self.grad_in.data_ptr(), nat.dtype_code(self.wire_dtype),
-                                  self.weights_t.data_ptr(), rank, self.sumsq_t.data_ptr() if use_clip else None,
-                                  float(self.clip_norm), st), "mt_pack")
-        self._keep = keep
+        self._keep = self._pack(None, rank, use_clip=self.clip_norm > 0)
+        waited = 0.0
         if self.comm.world > 1:
-            waited = self.comm.allreduce_buckets(self.grad_in, self.grad_out, self.buckets)
-            g = self.grad_out
+            waited = self._allreduce(self.buckets)
+            if not self.fused_sgd:
+                self._sgd_native(self.grad_out)
         else:                              # single rank: the packed (weighted, clipped) gradient IS the result
-            waited, g = 0.0, self.grad_in
-        self._sgd_native(g)
+            self._sgd_native(self.grad_in)
+        self._sunk = [False] * len(self.params)
         return waited
 
     def _reduce_and_step_torch(self, rank: int) -> float:

@@ -200,6 +200,20 @@ class SymmComm(Comm):
             nat.check(rc, "weighted_allreduce")
         return 0.0
 
+    def allreduce_buckets_sgd(self, grad_in, grad_out, buckets, sgd: dict) -> float:
+        """Allreduce of each bucket with the momentum-SGD step (+ bf16 shadow refresh, + clearing of the gradient buffer)
+        fused behind it as the kernel's last phase: ONE launch per bucket for "collective + optimizer"."""
+        st = nat.stream_ptr(self.device)
+        wire = nat.dtype_code(self._wire)
+        esize = 2 if self._wire == torch.bfloat16 else 4
+        for (off, n) in buckets:
+            algo = self.pick_algo(n * esize)
+            rc = self.lib.dlb_weighted_allreduce_sgd(self._ctx, ALGO_CODES[algo], wire, off, n, self.pick_blocks(n * esize, algo),
+                                                     None, sgd["master"], sgd["mom"], sgd["shadow"], sgd["lr"], sgd["zero_in"],
+                                                     sgd["momentum"], sgd["weight_decay"], None, st)
+            nat.check(rc, "weighted_allreduce_sgd")
+        return 0.0
+
     def barrier(self) -> None:
         nat.check(self.lib.dlb_device_barrier(self._time_ctx, 2, nat.stream_ptr(self.device)), "device_barrier")
 

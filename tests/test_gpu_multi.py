@@ -51,6 +51,35 @@ for wire in (torch.float32, torch.bfloat16):
         ref2 = (local * w[rank]).to(wire).float().clone(); dist.all_reduce(ref2)
         err2 = (gout.float() - ref2).abs().max().item()
         assert err2 < tol * max(1.0, ref2.abs().max().item()), (algo, wire, "unweighted", err2)
+# ---- optimizer step fused behind the collective: allreduce + momentum SGD + bf16 shadow + clearing of the input, ONE launch
+n2 = (1 << 18) + 32 * world
+gin, gout = c.alloc_grad_buffers(n2, torch.float32, f"cuda:{rank}")
+for algo in ["oneshot", "twoshot"] + (["nvls"] if c.has_multicast else []):
+    c.algo = algo
+    torch.manual_seed(7)
+    master = torch.randn(n2, device="cuda"); mom = torch.randn(n2, device="cuda") * 0.1
+    shadow = torch.zeros(n2, device="cuda", dtype=torch.bfloat16)
+    lr = torch.full((1,), 0.05, device="cuda")
+    torch.manual_seed(200 + rank)
+    local = torch.randn(n2, device="cuda")
+    ref_g = local.clone(); dist.all_reduce(ref_g)
+    ref_m = 0.9 * mom + ref_g
+    ref_p = master - 0.05 * ref_m
+    gin.copy_(local); gout.zero_()
+    torch.cuda.synchronize(); dist.barrier()
+    c.allreduce_buckets_sgd(gin, gout, [(0, n2 // 2), (n2 // 2, n2 - n2 // 2)],
+                            {"master": master.data_ptr(), "mom": mom.data_ptr(), "shadow": shadow.data_ptr(), "lr": lr.data_ptr(),
+                             "momentum": 0.9, "weight_decay": 0.0, "zero_in": gin.data_ptr()})
+    torch.cuda.synchronize(); c.check_errors()
+    assert (master - ref_p).abs().max().item() < 1e-4, (algo, (master - ref_p).abs().max().item())
+    assert (mom - ref_m).abs().max().item() < 1e-4, algo
+    assert (shadow.float() - ref_p).abs().max().item() < 2e-2 * ref_p.abs().max().item(), algo
+    assert gin.abs().max().item() == 0.0, (algo, "gradient buffer not cleared")
+    chk = master.double().sum().reshape(1).clone()
+    lst = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(lst, chk)
+    assert all(torch.equal(lst[0], x) for x in lst), (algo, "replicas diverged")
+    if rank == 0: print("ok fused-sgd", algo, flush=True)
 t = c.gather_times(10.0 + rank)
 assert t == [10.0 + r for r in range(world)], t
 t = c.gather_times(20.0 + rank)
@@ -74,7 +103,7 @@ def test_weighted_allreduce_all_algos(tmp_path):
     p.write_text(WORKER % {"root": ROOT})
     r = _torchrun(str(p), n, 29701)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert "ok twoshot" in r.stdout
+    assert "ok twoshot" in r.stdout and "ok fused-sgd twoshot" in r.stdout
 
 
 def test_end_to_end_two_ranks_rebalance(tmp_path):

@@ -1,0 +1,31 @@
+#!/bin/bash
+# Multi-GPU evidence, N = $1 GPUs of one box:   gpurun --gpus N --timeout 1500 -- bash tools/gpu_scripts/r2_multi.sh N [quick]
+#   collective numerics at N GPUs, allreduce bus-bandwidth sweep 1 KB-1 GB vs scale+NCCL, both bench arms, DBS models A/B,
+#   a profiler trace of graph-replayed steps (stream overlap, absence of nccl kernels), compute-sanitizer on the collectives.
+N=${1:-2}; QUICK=${2:-}
+mkdir -p gpurun_out; O=gpurun_out/r2_multi_n$N; mkdir -p $O
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+nvidia-smi topo -m > $O/topo.txt 2>&1
+echo "== collective tests ($N GPUs)"; timeout 600 python -m pytest tests/test_gpu_multi.py -q -rA 2>&1 | tail -15 | tee $O/pytest_multi.txt
+echo "== allreduce sweep";  SWEEP_MAX_BYTES=$((1<<30)) timeout 600 $TR --master-port 29801 tools/allreduce_sweep.py > $O/sweep.jsonl 2> $O/sweep.err; tail -4 $O/sweep.jsonl | cut -c1-400
+cp gpurun_out/allreduce_sweep_n$N.json $O/ 2>/dev/null
+echo "== bench reference";  timeout 900 $TR --master-port 29802 bench.py --impl reference --gpus $N --steps 20 --warmup 5 2> $O/ref.err | tee $O/ref.json | cut -c1-400
+echo "== bench ours (default)"; timeout 600 $TR --master-port 29803 bench.py --gpus $N --steps 20 --warmup 5 2> $O/ours.err | tee $O/ours.json | cut -c1-500
+if [ -z "$QUICK" ]; then
+echo "== bench ours --dbs-model affine"; timeout 600 $TR --master-port 29804 bench.py --gpus $N --steps 20 --warmup 5 --dbs-model affine --dbs-rounds 3 2> $O/ours_affine.err | tee $O/ours_affine.json | cut -c1-500
+echo "== bench ours --dbs-model proportional"; timeout 600 $TR --master-port 29805 bench.py --gpus $N --steps 20 --warmup 5 --dbs-model proportional 2> $O/ours_prop.err | tee $O/ours_prop.json | cut -c1-500
+echo "== bench ours --no-dbs"; timeout 600 $TR --master-port 29806 bench.py --gpus $N --steps 20 --warmup 5 --no-dbs 2> $O/ours_nodbs.err | tee $O/ours_nodbs.json | cut -c1-500
+echo "== bench ours tf32"; timeout 600 $TR --master-port 29807 bench.py --gpus $N --steps 20 --warmup 5 --dtype tf32 2> $O/ours_tf32.err | tee $O/ours_tf32.json | cut -c1-500
+fi
+echo "== profiler trace of graph-replayed steps (rank 0)"
+DLB_PROFILE_GRAPHS=1 timeout 600 $TR --master-port 29808 dbs.py -d false -ws $N -b 512 -m densenet -ds cifar10 -e 1 --synthetic true \
+    --train_samples 10240 --test_samples 256 --validate false --profile true --throttle_rank $((N-1)) --throttle_ms 3 --throttle_mode burn \
+    --log_dir $O/logs --stats_dir $O/statis --force true > $O/profile.out 2> $O/profile.err
+T=$(ls $O/logs/*node0*.trace.json 2>/dev/null | head -1)
+[ -n "$T" ] && python tools/trace_overlap.py $T | tee $O/trace_overlap.txt && rm -f $O/logs/*.trace.json
+if [ "$N" = "2" ]; then
+  echo "== compute-sanitizer on the collectives"
+  bash tools/gpu_scripts/sanitize.sh comm-only 2>&1 | tail -6 | tee $O/sanitize.txt
+  cp gpurun_out/sanitize_comm_* $O/ 2>/dev/null
+fi
+tail -2 $O/*.err | tail -40

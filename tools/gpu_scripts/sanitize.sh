@@ -12,13 +12,15 @@ run() {   # name, tool, pytest selection...
       > gpurun_out/sanitize_${name}_${tool}.txt 2>&1
   echo "rc=$? $(grep -E 'ERROR SUMMARY|passed|failed' gpurun_out/sanitize_${name}_${tool}.txt | tail -2 | tr '\n' ' ')"
 }
+if [ "$1" != "comm-only" ]; then
 # GroupNorm / pooling / optimizer / augment kernels (shared-memory reductions -> racecheck is the interesting tool)
 run norm memcheck  tests/test_gpu_kernels.py -k "groupnorm or gn_ or pool or sgd or pack or augment"
 run norm racecheck tests/test_gpu_kernels.py -k "groupnorm or gn_ or pool or sgd or pack or augment"
 # tcgen05 GEMMs: memcheck + synccheck (mbarrier / bulk-async misuse); racecheck does not model the async proxy
 run gemm memcheck  tests/test_gpu_gemm.py -k "plain_gemm or prologue or wgrad"
 run gemm synccheck tests/test_gpu_gemm.py -k "plain_gemm or prologue or wgrad"
-if [ "$1" = "comm" ]; then
+fi
+if [ "$1" = "comm" ] || [ "$1" = "comm-only" ]; then
   run comm memcheck  tests/test_gpu_multi.py -k "allreduce or gather or barrier"
   run comm racecheck tests/test_gpu_multi.py -k "allreduce or gather or barrier"
 fi
