@@ -231,25 +231,45 @@ class _DenseBlockFn(torch.autograd.Function):
             cl = c0 + l * g
             off = ct - cl
             cm = y.shape[1]
-            dnew = torch.empty((n, g, h, w), dtype=buf.dtype, device=buf.device, memory_format=torch.channels_last)
-            _copy_slice(lib, dbuf[:, off - g:off], dnew, st)
             w2c = w2 if w2.dtype == yhat.dtype else w2.to(yhat.dtype)
+            own_w3 = gemm_tc.wgrad3x3_supported(n, h, w, cm, buf.dtype) and w2.dtype == buf.dtype
+            own_d3 = conv3_ok and w2.dtype == buf.dtype
+            dnew = None
+            if not (own_w3 and own_d3):
+                # a vendor kernel needs the gradient of the g new channels as a dense tensor; our kernels read the slice in place
+                dnew = torch.empty((n, g, h, w), dtype=buf.dtype, device=buf.device, memory_format=torch.channels_last)
+                _copy_slice(lib, dbuf[:, off - g:off], dnew, st)
+            dslice = dbuf.data_ptr() + (off - g) * esz
+            dw2_sunk = own_w3 and sv is not None
+            dw2 = None
+
+            def _wgrad2():
+                nonlocal dw2
+                if own_w3:
+                    # 9-tap MN-major split-K tcgen05 weight gradient, accumulated straight into the parameter's gradient sink
+                    dw2f = sv[6 * l + 5] if dw2_sunk else torch.zeros((g, 3, 3, cm), dtype=torch.float32, device=buf.device)
+                    gemm_tc.wgrad3x3_raw(yhat.data_ptr(), cm, dslice, ct, dw2f, n, h, w, cm, g, buf.device, dtype=dt)
+                    if not dw2_sunk:
+                        dw2 = dw2f.permute(0, 3, 1, 2)
+                else:
+                    _, dw2, _ = _CONV_BWD(dnew, yhat, w2c, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [False, True, False])
+
             if side is not None:
                 # weight gradients are off the critical path: run them on a second stream so they overlap the
                 # dgrad -> GroupNorm-backward chain of the same layer (joined at the end of the layer)
                 ev_in = torch.cuda.Event(); ev_in.record(main)
                 side.wait_event(ev_in)
                 with torch.cuda.stream(side):
-                    _, dw2, _ = _CONV_BWD(dnew, yhat, w2c, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [False, True, False])
-                if conv3_ok and w2.dtype == buf.dtype:
-                    # data gradient on the tcgen05 3x3 kernel, reading dY in place from the gradient-buffer slice
-                    dyhat = torch.empty((n, cm, h, w), dtype=buf.dtype, device=buf.device, memory_format=torch.channels_last)
-                    gemm_tc.conv3x3_raw(True, dbuf.data_ptr() + (off - g) * esz, ct, gemm_tc._w_ohwi(w2).data_ptr(), dyhat.data_ptr(),
-                                        cm, n, h, w, cm, g, buf.device, dtype=dt)
-                else:
-                    dyhat, _, _ = _CONV_BWD(dnew, yhat, w2c, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [True, False, False])
+                    _wgrad2()
             else:
-                dyhat, dw2, _ = _CONV_BWD(dnew, yhat, w2c, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [True, True, False])
+                _wgrad2()
+            if own_d3:
+                # data gradient on the tcgen05 3x3 kernel, reading dY in place from the gradient-buffer slice
+                dyhat = torch.empty((n, cm, h, w), dtype=buf.dtype, device=buf.device, memory_format=torch.channels_last)
+                gemm_tc.conv3x3_raw(True, dslice, ct, gemm_tc._w_ohwi(w2).data_ptr(), dyhat.data_ptr(),
+                                    cm, n, h, w, cm, g, buf.device, dtype=dt)
+            else:
+                dyhat, _, _ = _CONV_BWD(dnew, yhat, w2c, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [True, False, False])
             dyhat = dyhat.contiguous(memory_format=torch.channels_last)
             # GN2 + ReLU backward
             dy = torch.empty_like(y, memory_format=torch.channels_last)
@@ -267,6 +287,8 @@ class _DenseBlockFn(torch.autograd.Function):
             if sv is not None and xhat.numel() == 0:
                 dg1, db1 = sv[6 * l + 0], sv[6 * l + 1]
                 sunk += [sidx[6 * l + 0], sidx[6 * l + 1], sidx[6 * l + 2]]
+            if dw2_sunk:
+                sunk.append(sidx[6 * l + 5])
             if ca2.numel() > 0:
                 # ReLU mask recomputed from the forward's affine coefficients: yhat is not re-read by the GN2 backward
                 kp2 = ca2.shape[1]
@@ -334,7 +356,7 @@ class _DenseBlockFn(torch.autograd.Function):
                 ev_out = torch.cuda.Event(); ev_out.record(side)
                 main.wait_event(ev_out)            # per-layer join: every tensor the side stream touched is still referenced here
             grads[6 * l:6 * l + 6] = [dg1.to(g1w.dtype), db1.to(g1b.dtype), dw1.to(w1.dtype) if dw1 is not None else None,
-                                      dg2.to(g2w.dtype), db2.to(g2b.dtype), dw2.to(w2.dtype)]
+                                      dg2.to(g2w.dtype), db2.to(g2b.dtype), dw2.to(w2.dtype) if dw2 is not None else None]
             if sunk:
                 for k in range(6):
                     if sidx[6 * l + k] in sunk:

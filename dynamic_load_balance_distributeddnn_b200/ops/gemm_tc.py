@@ -23,6 +23,7 @@ def _lib():
         nat.declare("dlb_gemm_tc_dt", i32, [i32, vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, i32, vp, i64, i32, vp])
         nat.declare("dlb_gemm_tc_bmn_dt", i32, [i32, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp])
         nat.declare("dlb_conv3x3_tc_dt", i32, [i32, i32, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, vp, i64, i32, vp])
+        nat.declare("dlb_wgrad3x3_tc_dt", i32, [i32, vp, i64, vp, i64, vp, i32, i32, i32, i32, i32, i32, vp])
         nat.declare("dlb_wgrad_tc_dt", i32, [i32, vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, i32, i32, vp])
         nat.declare("dlb_dgrad_gn", i32, [i32, vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, i64, vp, i64,
                                           i32, vp])
@@ -161,6 +162,23 @@ def conv3x3_raw(dgrad: bool, x_ptr: int, ldx: int, w_ptr: int, y_ptr: int, ldy: 
     nat.check(rc, "conv3x3_tc")
 
 
+WGRAD3 = os.environ.get("DLB_TC_WGRAD3", "1") == "1"
+
+
+def wgrad3x3_supported(n: int, h: int, w: int, ci: int, dtype: torch.dtype) -> bool:
+    return (WGRAD3 and available() and hasattr(nat.get(), "dlb_wgrad3x3_tc_dt") and dtype in TC_DTYPES and conv3x3_geometry_ok(h, w)
+            and (n * h * w) % 128 == 0 and ci % (8 if dtype == torch.bfloat16 else 4) == 0)
+
+
+def wgrad3x3_raw(x_ptr: int, ldx: int, dy_ptr: int, lddy: int, dw: torch.Tensor, n: int, h: int, w: int, ci: int, co: int, device,
+                 dtype: int = nat.BF16, sm_limit: int = 0) -> None:
+    """dw[co][3][3][ci] (fp32, contiguous, pre-zeroed or accumulated into) += 3x3/s1/p1 weight gradient; x [n,h,w,ci] and
+    dy [n,h,w,co] are NHWC with pixel strides ldx / lddy (channel slices of wider buffers are read in place)."""
+    assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == co * 9 * ci
+    rc = _lib().dlb_wgrad3x3_tc_dt(dtype, x_ptr, ldx, dy_ptr, lddy, dw.data_ptr(), n, h, w, ci, co, sm_limit, nat.stream_ptr(device))
+    nat.check(rc, "wgrad3x3_tc")
+
+
 def _w_ohwi(weight: torch.Tensor) -> torch.Tensor:
     """weight [O,I,3,3] -> tensor whose memory is [O][3][3][I] (no copy when already channels-last)."""
     return weight if weight.is_contiguous(memory_format=torch.channels_last) else weight.contiguous(memory_format=torch.channels_last)
@@ -190,8 +208,12 @@ class _Conv3x3Fn(torch.autograd.Function):
             dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
             conv3x3_raw(True, dyv.data_ptr(), lddy, wk.data_ptr(), dx.data_ptr(), c, n, h, w, c, o, dy.device,
                         dtype=nat.dtype_code(dy.dtype))
-        if ctx.needs_input_grad[1]:
-            # weight gradient of the 3x3: vendor kernel (a 9-tap MN-major split-K tcgen05 variant is future work)
+        if ctx.needs_input_grad[1] and wgrad3x3_supported(n, h, w, c, dy.dtype):
+            # 9-tap MN-major split-K tcgen05 weight gradient (csrc/conv_wgrad.cu), both operands read in place
+            dwf = torch.zeros((o, 3, 3, c), dtype=torch.float32, device=dy.device)
+            wgrad3x3_raw(xv.data_ptr(), ld, dyv.data_ptr(), lddy, dwf, n, h, w, c, o, dy.device, dtype=nat.dtype_code(dy.dtype))
+            dw = dwf.permute(0, 3, 1, 2).to(weight.dtype)              # logical OIHW, channels-last memory
+        elif ctx.needs_input_grad[1]:
             x4 = torch.as_strided(xv, (n, c, h, w), (h * w * ld, 1, w * ld, ld))
             _, dw, _ = torch.ops.aten.convolution_backward(dyv if dyv.is_contiguous(memory_format=torch.channels_last) else
                                                            dyv.contiguous(memory_format=torch.channels_last),

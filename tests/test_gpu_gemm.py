@@ -194,3 +194,27 @@ def test_conv3x3_strided_io_and_stats(g):
     assert out[..., :16].abs().sum().item() == 0 and out[..., 48:].abs().sum().item() == 0
     assert torch.allclose(table[:, 16:48, 0], got.sum((1, 2)), atol=5e-2, rtol=5e-3)
     assert torch.allclose(table[:, 16:48, 1], (got * got).sum((1, 2)), atol=5e-2, rtol=5e-3)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 1e-2), (torch.float32, 4e-3)])
+@pytest.mark.parametrize("n,ci,co,hw", [(8, 128, 32, 32), (6, 128, 32, 16), (16, 128, 32, 8), (32, 128, 32, 4), (4, 64, 64, 32),
+                                         (8, 96, 160, 16), (4, 256, 256, 8)])
+def test_wgrad3x3_tcgen05(g, dtype, tol, n, ci, co, hw):
+    """9-tap MN-major split-K weight gradient (csrc/conv_wgrad.cu): x and dy are channel slices of wider NHWC buffers"""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(n + ci + co + hw)
+    xin = torch.randn(n, hw, hw, ci + 64, device="cuda").to(dtype)
+    dyin = (torch.randn(n, hw, hw, co + 96, device="cuda") / 8).to(dtype)
+    x, dy = xin[..., 32:32 + ci], dyin[..., 64:64 + co]
+    assert g.wgrad3x3_supported(n, hw, hw, ci, dtype)
+    dw = torch.zeros(co, 3, 3, ci, device="cuda")
+    from dynamic_load_balance_distributeddnn_b200.ops import _native as nat
+    g.wgrad3x3_raw(x.data_ptr(), ci + 64, dy.data_ptr(), co + 96, dw, n, hw, hw, ci, co, x.device, dtype=nat.dtype_code(dtype))
+    torch.cuda.synchronize()
+    xr = x.float().permute(0, 3, 1, 2).contiguous()
+    dyr = dy.float().permute(0, 3, 1, 2).contiguous()
+    wr = torch.zeros(co, ci, 3, 3, device="cuda", requires_grad=True)
+    torch.nn.functional.conv2d(xr, wr, padding=1).backward(dyr)
+    ref = wr.grad.permute(0, 2, 3, 1)                  # [co][3][3][ci]
+    err = (dw - ref).abs().max().item()
+    assert err < tol * max(1.0, ref.abs().max().item()), (err, ref.abs().max().item())
