@@ -108,8 +108,9 @@ class TransformerModel(nn.Module):
         nn.init.uniform_(self.decoder.weight, -0.1, 0.1)
 
     def features(self, src):                                # src: int64 [S, B]
-        x = self.encoder(src) * math.sqrt(self.ninp)
-        x = self.pos_encoder(x)
+        # gather * sqrt(d) + positional table + dropout: one fused kernel on CUDA (ops/embedding.py), the plain ops elsewhere
+        from ..ops import embedding as fused_embed
+        x = fused_embed.embed_pe_dropout(src, self.encoder.weight, self.pos_encoder.pe, self.pos_encoder.p, self.training)
         return self.transformer_encoder(x)
 
     def forward(self, src, has_mask=True):

@@ -334,3 +334,33 @@ def test_fused_linear_cross_entropy_native(nat, dtype, tol):
     assert abs(float(l1) - float(l2)) < tol * max(1.0, float(l2)), (float(l1), float(l2))
     for a, r in ((feats.grad, fr.grad), (w.grad, wr.grad), (b.grad, br.grad)):
         assert float((a.float() - r).abs().max()) < tol * max(1e-3, float(r.abs().max())) * 3, (a.float() - r).abs().max()
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+def test_fused_embedding_frontend(nat, dtype, tol):
+    """gather * sqrt(d) + positional table (+ dropout) in one kernel, scatter-add backward (csrc/embed.cu)"""
+    from dynamic_load_balance_distributeddnn_b200.ops import embedding as E
+    torch.manual_seed(3)
+    v, d, s, b = 1000, 200, 35, 64
+    w = (torch.randn(v, d, device="cuda") * 0.1).to(dtype).requires_grad_(True)
+    pe = torch.randn(5000, 1, d, device="cuda")
+    tok = torch.randint(0, v, (s, b), device="cuda")
+    assert E.supported(tok, w)
+    out = E.embed_pe_dropout(tok, w, pe, 0.2, training=False)
+    ref = F.embedding(tok, w.float()) * math.sqrt(d) + pe[:s]
+    assert (out.float() - ref).abs().max().item() < tol * ref.abs().max().item()
+    go = torch.randn_like(out)
+    out.backward(go)
+    wr = w.detach().float().requires_grad_(True)
+    (F.embedding(tok, wr) * math.sqrt(d)).backward(go.float())
+    assert (w.grad.float() - wr.grad).abs().max().item() < max(tol, 1e-4) * wr.grad.abs().max().item()
+    # dropout: ~p of the elements are zero, the survivors are scaled by 1/(1-p), and the backward uses the same mask
+    w.grad = None
+    o2 = E.embed_pe_dropout(tok, w, pe, 0.25, training=True)
+    frac = (o2 == 0).float().mean().item()
+    assert abs(frac - 0.25) < 0.02, frac
+    keep = o2 != 0
+    assert (o2.float()[keep] - (ref / 0.75)[keep]).abs().max().item() < max(tol, 1e-4) * ref.abs().max().item() / 0.75 + 1e-3
+    o2.backward(torch.ones_like(o2))
+    cnt = torch.zeros(v, d, device="cuda").index_put_((tok.reshape(-1),), keep.reshape(-1, d).float(), accumulate=True)
+    assert (w.grad.float() - cnt * math.sqrt(d) / 0.75).abs().max().item() < 2e-2 * (cnt.max().item() * math.sqrt(d) / 0.75)
