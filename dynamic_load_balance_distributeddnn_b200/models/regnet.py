@@ -28,9 +28,9 @@ class SE(nn.Module):
         self.se2 = Conv2d(se_planes, in_planes, kernel_size=1, bias=True)
 
     def forward(self, x):
-        s = F.adaptive_avg_pool2d(x, (1, 1))
-        s = self.se2(F.relu(self.se1(s))).sigmoid()
-        return x * s
+        # squeeze, both 1x1 projections, the gate and the scaling: one fused kernel per direction on CUDA (ops/se.py)
+        from ..ops import se as fused_se
+        return fused_se.squeeze_excite(x, self.se1.weight, self.se1.bias, self.se2.weight, self.se2.bias)
 
 
 class Block(nn.Module):

@@ -364,3 +364,26 @@ def test_fused_embedding_frontend(nat, dtype, tol):
     o2.backward(torch.ones_like(o2))
     cnt = torch.zeros(v, d, device="cuda").index_put_((tok.reshape(-1),), keep.reshape(-1, d).float(), accumulate=True)
     assert (w.grad.float() - cnt * math.sqrt(d) / 0.75).abs().max().item() < 2e-2 * (cnt.max().item() * math.sqrt(d) / 0.75)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])
+@pytest.mark.parametrize("n,c,cs,hw", [(8, 32, 8, 32), (5, 160, 40, 8), (3, 384, 96, 4)])
+def test_fused_squeeze_excite(nat, dtype, tol, n, c, cs, hw):
+    from dynamic_load_balance_distributeddnn_b200.ops import se
+    torch.manual_seed(n + c)
+    x = _cl(torch.randn(n, c, hw, hw, device="cuda")).to(dtype).requires_grad_(True)
+    w1 = (torch.randn(cs, c, 1, 1, device="cuda") / c ** 0.5).to(dtype).requires_grad_(True)
+    b1 = (torch.randn(cs, device="cuda") * 0.1).to(dtype).requires_grad_(True)
+    w2 = (torch.randn(c, cs, 1, 1, device="cuda") / cs ** 0.5).to(dtype).requires_grad_(True)
+    b2 = (torch.randn(c, device="cuda") * 0.1).to(dtype).requires_grad_(True)
+    assert se.supported(x, w1, b1, w2, b2)
+    out = se.squeeze_excite(x, w1, b1, w2, b2)
+    go = torch.randn_like(out)
+    out.backward(go)
+    ps = [t.detach().float().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    s = F.adaptive_avg_pool2d(ps[0], (1, 1))
+    ref = ps[0] * F.conv2d(F.relu(F.conv2d(s, ps[1], ps[2])), ps[3], ps[4]).sigmoid()
+    ref.backward(go.float())
+    assert (out.float() - ref).abs().max().item() < tol * ref.abs().max().item()
+    for a, r in zip((x, w1, b1, w2, b2), ps):
+        assert (a.grad.float() - r.grad).abs().max().item() < 3 * tol * max(1e-3, r.grad.abs().max().item()), a.shape
