@@ -17,6 +17,20 @@
 #include <stdlib.h>
 
 static int g_skip_zero = 0;      // callers that pre-zero one big arena set this to skip the per-call memsets
+// rows in flight per thread (independent 16-byte loads issued before the first use) of the streaming kernels; tunable at run
+// time for sweeps (dlb_norm_tune / DLB_GN_UNR_{RED,FWD,BWD}); defaults are the measured optimum on B200
+static int g_unr_red = 0, g_unr_fwd = 0, g_unr_bwd = 0, g_min_kb = 0;
+static int unr_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  const int v = e ? atoi(e) : dflt;
+  return (v == 1 || v == 2 || v == 4) ? v : dflt;
+}
+static void unr_init() {
+  if (g_unr_red) return;
+  g_unr_red = unr_env("DLB_GN_UNR_RED", 2);
+  g_unr_fwd = unr_env("DLB_GN_UNR_FWD", 2);
+  g_unr_bwd = unr_env("DLB_GN_UNR_BWD", 1);
+}
 
 namespace {
 
@@ -29,7 +43,7 @@ constexpr int kThreads = 256;
 // MODE 2: q0 = dy, q1 = dy*x                  (inputs: x, dy)     [no relu]
 // MODE 3: as MODE 1 but the ReLU mask is recomputed as (ca[n,c]*x + cb[n,c] > 0) from the forward's affine
 //         coefficients, so the normalised activation y never has to exist in memory
-template <typename T, int V, int MODE>
+template <typename T, int V, int MODE, int UNR>
 __global__ void __launch_bounds__(kThreads)
 nc_reduce2_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy,
                   const T* __restrict__ y, int64_t ldy, float* __restrict__ table, int64_t table_ns,
@@ -59,7 +73,6 @@ nc_reduce2_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy
 #pragma unroll
         for (int i = 0; i < V; ++i) { ka[i] = coef_a[(int64_t)n * coef_ld + c + i]; kb[i] = coef_b[(int64_t)n * coef_ld + c + i]; }
       }
-      constexpr int UNR = (MODE == 0) ? 2 : 1;
       for (int rb = r0 + rl; rb < r1; rb += row_lanes * UNR) {
         float xv[UNR][V], gv[UNR][V], yv[UNR][V];
 #pragma unroll
@@ -178,7 +191,7 @@ __global__ void gn_coeff_kernel(const float* __restrict__ table, int64_t table_n
 
 // ---------------------------------------------------------------------------------------------
 // (2a) forward apply: y = act(gamma*(x-mu)*rstd + beta (+ res))
-template <typename T, int V, bool RELU, bool RES>
+template <typename T, int V, bool RELU, bool RES, int UNR>
 __global__ void __launch_bounds__(kThreads)
 gn_fwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ res, int64_t ldr,
                     T* __restrict__ y, int64_t ldy, const float* __restrict__ gamma,
@@ -209,7 +222,6 @@ gn_fwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
       float a[V], b[V];
 #pragma unroll
       for (int k = 0; k < V; ++k) { a[k] = sa[c + k]; b[k] = sb[c + k]; }
-      constexpr int UNR = 2;
       for (int rb = r0 + rl; rb < r1; rb += row_lanes * UNR) {
         float xv[UNR][V], rv[UNR][V];
 #pragma unroll
@@ -265,7 +277,7 @@ gn_fwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 // (2b) backward apply: dx (+)= k1[c]*dz + k2[c]*x + k3[c];  optional dres = dz
 // RELU: 0 = no activation, 1 = mask from the saved output y, 2 = mask recomputed from (coef_a, coef_b)
-template <typename T, int V, int RELU, bool RES, bool ACC>
+template <typename T, int V, int RELU, bool RES, bool ACC, int UNR>
 __global__ void __launch_bounds__(kThreads)
 gn_bwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy,
                     const T* __restrict__ y, int64_t ldy, T* __restrict__ dx, int64_t lddx,
@@ -319,7 +331,6 @@ gn_bwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
 #pragma unroll
         for (int k = 0; k < V; ++k) { ka[k] = coef_a[(int64_t)n * coef_ld + c + k]; kb[k] = coef_b[(int64_t)n * coef_ld + c + k]; }
       }
-      constexpr int UNR = 1;
       for (int rb = r0 + rl; rb < r1; rb += row_lanes * UNR) {
         float xv[UNR][V], gv[UNR][V], yv[UNR][V], old[UNR][V];
 #pragma unroll
@@ -422,8 +433,8 @@ inline void grid_for(int N, int HW, int C, int V, dim3& grid, int& rows_per_bloc
   // every block pays a per-sample preamble (coefficients / zeroing / 2C atomics): give it >= ~96 KB (tuned: 24/48/96/192/384 KB sweep on B200) of rows to
   // stream, otherwise small per-rank batches drown in fixed cost (profiles: 16 us reduce kernels at batch 128)
   const long long bytes_per_sample = (long long)HW * C * (V == 4 ? 4 : 2);
-  static int min_kb = 0;
-  if (!min_kb) { const char* e = getenv("DLB_GN_MIN_KB"); min_kb = e ? atoi(e) : 96; if (min_kb < 1) min_kb = 96; }
+  if (!g_min_kb) { const char* e = getenv("DLB_GN_MIN_KB"); g_min_kb = e ? atoi(e) : 96; if (g_min_kb < 1) g_min_kb = 96; }
+  const int min_kb = g_min_kb;
   int by_work = (int)(bytes_per_sample / ((long long)min_kb * 1024));
   if (by_work < 1) by_work = 1;
   if (chunks > by_work) chunks = by_work;
@@ -445,10 +456,15 @@ int reduce2_launch(int mode, const void* x, int64_t ldx, const void* dy, int64_t
   grid_for(N, HW, C, V, grid, rpb);
   const size_t sm = 2 * C * sizeof(float);
   const T* X = (const T*)x; const T* DY = (const T*)dy; const T* Y = (const T*)y;
-  if (mode == 0) dlb_launch(nc_reduce2_kernel<T, V, 0>, grid, dim3(kThreads), sm, st, X, (int64_t)ldx, DY, (int64_t)lddy, Y, (int64_t)ldy, table, (int64_t)table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, (int64_t)cld, (T*)copy_dst, (int64_t)ldc);
-  else if (mode == 1) dlb_launch(nc_reduce2_kernel<T, V, 1>, grid, dim3(kThreads), sm, st, X, (int64_t)ldx, DY, (int64_t)lddy, Y, (int64_t)ldy, table, (int64_t)table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, (int64_t)cld, (T*)copy_dst, (int64_t)ldc);
-  else if (mode == 3) dlb_launch(nc_reduce2_kernel<T, V, 3>, grid, dim3(kThreads), sm, st, X, (int64_t)ldx, DY, (int64_t)lddy, Y, (int64_t)ldy, table, (int64_t)table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, (int64_t)cld, (T*)copy_dst, (int64_t)ldc);
-  else dlb_launch(nc_reduce2_kernel<T, V, 2>, grid, dim3(kThreads), sm, st, X, (int64_t)ldx, DY, (int64_t)lddy, Y, (int64_t)ldy, table, (int64_t)table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, (int64_t)cld, (T*)copy_dst, (int64_t)ldc);
+  unr_init();
+#define RGO(MD, U) dlb_launch(nc_reduce2_kernel<T, V, MD, U>, grid, dim3(kThreads), sm, st, X, (int64_t)ldx, DY, (int64_t)lddy, Y, (int64_t)ldy, table, (int64_t)table_ns, HW, C, rpb, mean, rstd, G, dgamma, dbeta, ca, cb, (int64_t)cld, (T*)copy_dst, (int64_t)ldc)
+#define RGU(MD) do { if (g_unr_red == 4) RGO(MD, 4); else if (g_unr_red == 2) RGO(MD, 2); else RGO(MD, 1); } while (0)
+  if (mode == 0) RGU(0);
+  else if (mode == 1) RGU(1);
+  else if (mode == 3) RGU(3);
+  else RGU(2);
+#undef RGU
+#undef RGO
   return dlb_post_launch();
 }
 
@@ -460,10 +476,13 @@ int fwd_apply_launch(const void* x, int64_t ldx, const void* res, int64_t ldr, v
   grid_for(N, HW, C, V, grid, rpb);
   const size_t sm = 2 * C * sizeof(float);
   const T* X = (const T*)x; const T* R = (const T*)res; T* Y = (T*)y;
-#define GO(RL, RS) dlb_launch(gn_fwd_apply_kernel<T, V, RL, RS>, grid, dim3(kThreads), sm, st, X, (int64_t)ldx, R, (int64_t)ldr, Y, (int64_t)ldy, gamma, beta, mean, rstd, HW, C, G, rpb)
+  unr_init();
+#define GOU(RL, RS, U) dlb_launch(gn_fwd_apply_kernel<T, V, RL, RS, U>, grid, dim3(kThreads), sm, st, X, (int64_t)ldx, R, (int64_t)ldr, Y, (int64_t)ldy, gamma, beta, mean, rstd, HW, C, G, rpb)
+#define GO(RL, RS) do { if (g_unr_fwd == 4) GOU(RL, RS, 4); else if (g_unr_fwd == 2) GOU(RL, RS, 2); else GOU(RL, RS, 1); } while (0)
   if (relu) { if (res) GO(true, true); else GO(true, false); }
   else { if (res) GO(false, true); else GO(false, false); }
 #undef GO
+#undef GOU
   return dlb_post_launch();
 }
 
@@ -479,11 +498,14 @@ int bwd_apply_launch(const void* x, int64_t ldx, const void* dy, int64_t lddy, c
   const T* X = (const T*)x; const T* DY = (const T*)dy; const T* Y = (const T*)y;
   T* DX = (T*)dx; T* DR = (T*)dres;
   const int msrc = !relu ? 0 : (ca ? 2 : 1);
-#define GO(RL, RS, AC) dlb_launch(gn_bwd_apply_kernel<T, V, RL, RS, AC>, grid, dim3(kThreads), sm, st, X, (int64_t)ldx, DY, (int64_t)lddy, Y, (int64_t)ldy, DX, (int64_t)lddx, DR, (int64_t)lddr, gamma, mean, rstd, table, (int64_t)table_ns, HW, C, G, rpb, ca, cb, (int64_t)cld)
+  unr_init();
+#define GOU(RL, RS, AC, U) dlb_launch(gn_bwd_apply_kernel<T, V, RL, RS, AC, U>, grid, dim3(kThreads), sm, st, X, (int64_t)ldx, DY, (int64_t)lddy, Y, (int64_t)ldy, DX, (int64_t)lddx, DR, (int64_t)lddr, gamma, mean, rstd, table, (int64_t)table_ns, HW, C, G, rpb, ca, cb, (int64_t)cld)
+#define GO(RL, RS, AC) do { if (g_unr_bwd == 4) GOU(RL, RS, AC, 4); else if (g_unr_bwd == 2) GOU(RL, RS, AC, 2); else GOU(RL, RS, AC, 1); } while (0)
 #define GO2(RL) do { if (dres) { if (acc) GO(RL, true, true); else GO(RL, true, false); } else { if (acc) GO(RL, false, true); else GO(RL, false, false); } } while (0)
   if (msrc == 0) GO2(0); else if (msrc == 1) GO2(1); else GO2(2);
 #undef GO2
 #undef GO
+#undef GOU
   return dlb_post_launch();
 }
 
@@ -506,6 +528,14 @@ inline bool vec_ok(int dtype, int C, std::initializer_list<int64_t> lds, std::in
   } while (0)
 
 DLB_API void dlb_norm_skip_zero(int flag) { g_skip_zero = flag; }
+// rows in flight per thread of the reduce / forward-apply / backward-apply kernels (1, 2 or 4; 0 keeps the current value)
+DLB_API void dlb_norm_tune(int unr_red, int unr_fwd, int unr_bwd) {
+  unr_init();
+  if (unr_red == 1 || unr_red == 2 || unr_red == 4) g_unr_red = unr_red;
+  if (unr_fwd == 1 || unr_fwd == 2 || unr_fwd == 4) g_unr_fwd = unr_fwd;
+  if (unr_bwd == 1 || unr_bwd == 2 || unr_bwd == 4) g_unr_bwd = unr_bwd;
+}
+DLB_API void dlb_norm_tune_kb(int min_kb) { if (min_kb > 0) g_min_kb = min_kb; }
 
 // table: fp32 [N][table_ns] with (q0,q1) pairs for C channels starting at `table`; zeroed here.
 DLB_API int dlb_nc_reduce2(int mode, int dtype, const void* x, int64_t ldx, const void* dy, int64_t lddy,

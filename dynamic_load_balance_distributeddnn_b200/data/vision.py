@@ -116,25 +116,27 @@ def load_image_dataset(name: str, train: bool, root: str = "./data", synthetic: 
 
 
 class BatchStager:
-    """Host gather → pinned staging → async H2D, double-buffered on a copy stream.
+    """Host gather → pinned staging → async H2D on a copy stream, ``slots`` buffers deep (the host only blocks when it is
+    ``slots`` steps ahead of the device: the wait inside ``stage`` is back-pressure, not host work).
 
     ``stage(indices)`` returns device tensors ``(uint8 [b,H,W,C], int64 [b])`` valid on the
     current stream.  On CPU it is a plain index_select."""
 
-    def __init__(self, ds: ImageDataset, max_batch: int, device: torch.device):
+    def __init__(self, ds: ImageDataset, max_batch: int, device: torch.device, slots: int = 4):
         self.ds = ds
+        self.slots = slots
         self.device = torch.device(device)
         self.cuda = self.device.type == "cuda"
         self.bytes_per_step = 0
         if self.cuda:
             h, w, c = ds.shape
-            self._host_img = [torch.empty(max_batch, h, w, c, dtype=torch.uint8).pin_memory() for _ in range(2)]
-            self._host_lab = [torch.empty(max_batch, dtype=torch.int64).pin_memory() for _ in range(2)]
-            self._dev_img = [torch.empty(max_batch, h, w, c, dtype=torch.uint8, device=self.device) for _ in range(2)]
-            self._dev_lab = [torch.empty(max_batch, dtype=torch.int64, device=self.device) for _ in range(2)]
+            self._host_img = [torch.empty(max_batch, h, w, c, dtype=torch.uint8).pin_memory() for _ in range(slots)]
+            self._host_lab = [torch.empty(max_batch, dtype=torch.int64).pin_memory() for _ in range(slots)]
+            self._dev_img = [torch.empty(max_batch, h, w, c, dtype=torch.uint8, device=self.device) for _ in range(slots)]
+            self._dev_lab = [torch.empty(max_batch, dtype=torch.int64, device=self.device) for _ in range(slots)]
             self._stream = torch.cuda.Stream(self.device)
-            self._done = [torch.cuda.Event() for _ in range(2)]
-            self._consumed = [torch.cuda.Event() for _ in range(2)]
+            self._done = [torch.cuda.Event() for _ in range(slots)]
+            self._consumed = [torch.cuda.Event() for _ in range(slots)]
             self._slot = 0
 
     def stage(self, indices) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -143,7 +145,7 @@ class BatchStager:
         if not self.cuda:
             return self.ds.images.index_select(0, idx), self.ds.labels.index_select(0, idx)
         s = self._slot
-        self._slot ^= 1
+        self._slot = (s + 1) % self.slots
         self._consumed[s].synchronize()           # previous user of this slot has finished
         torch.index_select(self.ds.images, 0, idx, out=self._host_img[s][:b])
         torch.index_select(self.ds.labels, 0, idx, out=self._host_lab[s][:b])
