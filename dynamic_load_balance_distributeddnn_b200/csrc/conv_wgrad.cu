@@ -138,11 +138,11 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         for (int t = t0; t < t1; ++t) {
           mbar_wait(smem_u32(&b_full[bs]), bph);
           tc_fence_after();
-          const uint64_t bdesc = make_smem_desc_mn(smem_u32(b_base + bs * C::kBoxBytes), C::kBoxBytes);
+          const uint64_t bdesc = make_smem_desc_mn(smem_u32(b_base + bs * C::kBoxBytes), C::kBoxBytes, EL::kMn32);
           for (int tap = tap0; tap < tap1; ++tap) {
             mbar_wait(smem_u32(&a_full[as]), aph);
             tc_fence_after();
-            const uint64_t adesc = make_smem_desc_mn(smem_u32(smem + as * C::kABytes), C::kBoxBytes);
+            const uint64_t adesc = make_smem_desc_mn(smem_u32(smem + as * C::kABytes), C::kBoxBytes, EL::kMn32);
             const uint32_t tmem_d = tmem_base + (uint32_t)((tap - tap0) * C::kN);
 #pragma unroll
             for (int k = 0; k < 128 / UMMA_K; ++k)
@@ -224,7 +224,7 @@ int wgrad3x3_impl(const void* x, long long ldx, const void* dy, long long lddy, 
     long long dims[4] = {Ci, W, H, N};
     long long strides[4] = {1, ldx, (long long)W * ldx, (long long)H * W * ldx};
     int box[4] = {AT, W, hb, nb};
-    int rc = make_map_nd(&tx, x, 4, dims, strides, box, EB);
+    int rc = make_map_nd(&tx, x, 4, dims, strides, box, EB, Elt<E>::kMn32);
     if (rc) return rc - 10;
   }
   // dY box: [128 pixels][128 bytes of channels]; the tensor map declares only the Co real channels, so for Co narrower than
@@ -244,7 +244,7 @@ int wgrad3x3_impl(const void* x, long long ldx, const void* dy, long long lddy, 
   p.tiles_per_split = (p.num_tiles + splits - 1) / splits;
   p.num_splits = (p.num_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   {
-    int rc = make_map(&tdy, dy, M, Co, lddy, 128, EB);
+    int rc = make_map(&tdy, dy, M, Co, lddy, 128, EB, Elt<E>::kMn32);
     if (rc) return rc - 20;
   }
   auto kern = wgrad3x3_tc_kernel<E>;

@@ -184,7 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
           const uint32_t sb = sa + C::kABytes;
-          const uint64_t adesc = make_smem_desc(sa), bdesc = B_MN ? make_smem_desc_mn(sb, kMnBox) : make_smem_desc(sb);
+          const uint64_t adesc = make_smem_desc(sa), bdesc = B_MN ? make_smem_desc_mn(sb, kMnBox, EL::kMn32) : make_smem_desc(sb);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // K-major: advance 32 bytes (one UMMA_K) inside the 128-byte swizzle atom: +2 in 16-byte units;
@@ -508,7 +508,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
           const uint32_t sb = sa + C::kABytes;
-          const uint64_t adesc = make_smem_desc_mn(sa, C::kBoxBytes), bdesc = make_smem_desc_mn(sb, C::kBoxBytes);
+          const uint64_t adesc = make_smem_desc_mn(sa, C::kBoxBytes, EL::kMn32), bdesc = make_smem_desc_mn(sb, C::kBoxBytes, EL::kMn32);
 #pragma unroll
           for (int k = 0; k < 64 / UMMA_K; ++k) {
             // advance UMMA_K pixel rows of 128 bytes along K: +8*UMMA_K in 16-byte units
@@ -585,7 +585,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
 #pragma unroll
           for (int j = 0; j < kBatch; ++j) {
             const int r = r_base + kRowStep * (i0 + j);
-            raw[j] = lds128(sb + r * 128 + ((cc ^ (r & 7)) << 4));
+            raw[j] = lds128(sb + swz_chunk<EL::kMn32>(r, cc));
           }
 #pragma unroll
           for (int j = 0; j < kBatch; ++j) {
@@ -603,7 +603,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
 #pragma unroll
           for (int j = 0; j < kBatch; ++j) {
             const int r = r_base + kRowStep * (i0 + j);
-            sts128(sb + r * 128 + ((cc ^ (r & 7)) << 4), raw[j]);
+            sts128(sb + swz_chunk<EL::kMn32>(r, cc), raw[j]);
           }
         }
         fence_proxy_async();
@@ -682,7 +682,7 @@ int gemm_bmn_impl(const void* a, long long lda, const void* b, long long ldb, vo
   CUtensorMap ta, tb, td;
   int rc = make_map(&ta, a, M, K, lda, BM, EB);
   if (rc) return rc - 10;
-  rc = make_map(&tb, b, K, N, ldb, AT, EB);                 // boxes of [BK k-rows][128 bytes of n]
+  rc = make_map(&tb, b, K, N, ldb, AT, EB, Elt<E>::kMn32);  // boxes of [BK k-rows][128 bytes of n], MN-major operand
   if (rc) return rc - 20;
   rc = make_map(&td, d, M, N, ldd, 32, EB);
   if (rc) return rc - 30;
@@ -767,9 +767,9 @@ int wgrad_impl(const void* dy, long long lddy, const void* x, long long ldx, flo
   rows = (rows + 63) / 64 * 64;
   splits = (M + rows - 1) / rows;
   CUtensorMap tdy, tx;
-  int rc = make_map(&tdy, dy, M, Co, lddy, 64, EB);
+  int rc = make_map(&tdy, dy, M, Co, lddy, 64, EB, Elt<E>::kMn32);      // both operands are MN-major
   if (rc) return rc;
-  rc = make_map(&tx, x, M, Ci, ldx, 64, EB);
+  rc = make_map(&tx, x, M, Ci, ldx, 64, EB, Elt<E>::kMn32);
   if (rc) return rc;
   WgradParams p;
   p.M = M; p.Co = Co; p.Ci = Ci; p.dw = dw; p.ldw = ldw; p.rows_per_split = rows; p.num_splits = splits;
@@ -829,7 +829,7 @@ int conv3x3_impl(int dgrad, const void* x, long long ldx, const void* w, void* y
     long long dims[3] = {Ci, 9, Co};                                     // w[co][tap][ci]: {ci (n, contiguous), tap, co (k rows)}
     long long strides[3] = {1, Ci, 9LL * Ci};
     int box[3] = {AT, 1, AT};
-    int rc = make_map_nd(&tb, w, 3, dims, strides, box, EB);
+    int rc = make_map_nd(&tb, w, 3, dims, strides, box, EB, Elt<E>::kMn32);   // MN-major B operand
     if (rc) return rc - 20;
   }
   int rc = make_map(&td, y, M, Cout, ldy, 32, EB);

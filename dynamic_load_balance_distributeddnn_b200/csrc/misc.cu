@@ -97,3 +97,38 @@ DLB_API int dlb_stamp_acc(const unsigned long long* start, unsigned long long* a
   stamp_acc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(start, acc);
   return dlb_post_launch();
 }
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-graph introspection: node counts by type of a captured step graph (cudaGraph_t handle from torch's
+// CUDAGraph.raw_cuda_graph()).  out[0] = total nodes, out[1] = kernel, out[2] = memcpy, out[3] = memset, out[4] = host,
+// out[5] = event record, out[6] = event wait, out[7] = other, out[8] = number of dependency edges.
+DLB_API int dlb_graph_node_counts(void* graph, long long* out) {
+  cudaGraph_t g = (cudaGraph_t)graph;
+  size_t n = 0;
+  cudaError_t e = cudaGraphGetNodes(g, nullptr, &n);
+  if (e != cudaSuccess) return (int)e;
+  for (int i = 0; i < 9; ++i) out[i] = 0;
+  out[0] = (long long)n;
+  if (n == 0) return 0;
+  cudaGraphNode_t* nodes = new cudaGraphNode_t[n];
+  e = cudaGraphGetNodes(g, nodes, &n);
+  if (e == cudaSuccess) {
+    for (size_t i = 0; i < n; ++i) {
+      cudaGraphNodeType t;
+      if (cudaGraphNodeGetType(nodes[i], &t) != cudaSuccess) { out[7]++; continue; }
+      switch (t) {
+        case cudaGraphNodeTypeKernel: out[1]++; break;
+        case cudaGraphNodeTypeMemcpy: out[2]++; break;
+        case cudaGraphNodeTypeMemset: out[3]++; break;
+        case cudaGraphNodeTypeHost: out[4]++; break;
+        case cudaGraphNodeTypeEventRecord: out[5]++; break;
+        case cudaGraphNodeTypeWaitEvent: out[6]++; break;
+        default: out[7]++; break;
+      }
+    }
+    size_t ne = 0;
+    if (cudaGraphGetEdges(g, nullptr, nullptr, &ne) == cudaSuccess) out[8] = (long long)ne;
+  }
+  delete[] nodes;
+  return (int)e;
+}

@@ -110,6 +110,7 @@ template <> struct Elt<__nv_bfloat16> {
   static constexpr int kAtom = 64;          // elements per 128-byte swizzle row
   static constexpr int kUmmaK = 16;
   static constexpr int kPer16 = 8;          // elements per 16-byte chunk
+  static constexpr bool kMn32 = false;      // MN-major operands use the plain SWIZZLE_128B layout
   static constexpr uint32_t kFmt = 1;       // UMMA instruction-descriptor operand format: BF16
   static constexpr CUtensorMapDataType kTmap = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   __device__ static __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) { umma_f16(d, a, b, idesc, acc); }
@@ -119,6 +120,7 @@ template <> struct Elt<float> {
   static constexpr int kAtom = 32;
   static constexpr int kUmmaK = 8;
   static constexpr int kPer16 = 4;
+  static constexpr bool kMn32 = true;       // MN-major operands need SWIZZLE_128B_BASE32B (see make_smem_desc_mn)
   static constexpr uint32_t kFmt = 2;       // TF32
   static constexpr CUtensorMapDataType kTmap = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   __device__ static __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) { umma_tf32(d, a, b, idesc, acc); }
@@ -167,14 +169,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes = 8192) {
+// MN-major operand descriptor.  16-bit types: SWIZZLE_128B, 8-row K groups 1024 B apart.  32-bit types (TF32): the only legal
+// MN-major layout is SWIZZLE_128B_BASE32B (layout type 1): 32-byte chunks of a 128-byte row XOR-ed with (row & 3), 4-row K
+// groups 512 B apart -- written by TMA with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (CUTLASS: "for mn-major tf32 operands,
+// SW128_32B is the only available smem layout").
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes = 8192, bool base32b = false) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
   d |= (uint64_t)(lbo_bytes >> 4) << 16;  // LBO: next 128-byte-wide MN group (one TMA box further)
-  d |= (uint64_t)(1024 >> 4) << 32;       // SBO: next 8-row K group
+  d |= (uint64_t)((base32b ? 512 : 1024) >> 4) << 32;       // SBO: next K group (8 rows, or 4 rows for BASE32B)
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  d |= (uint64_t)(base32b ? 1 : 2) << 61; // SWIZZLE_128B_BASE32B / SWIZZLE_128B
   return d;
+}
+// byte offset of logical 16-byte chunk `j` (0..7) of 128-byte row `r` inside a swizzled tile
+template <bool BASE32B>
+__device__ __forceinline__ uint32_t swz_chunk(int r, int j) {
+  if constexpr (BASE32B) return (uint32_t)(r * 128 + (((((j >> 1) ^ (r & 3)) << 1) | (j & 1)) << 4));
+  else return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
 }
 
 // ---- host side: TMA tensor maps (driver entry point fetched through the runtime, no libcuda link dependency) ----
@@ -192,7 +204,7 @@ inline PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 // 2-D bf16 tensor map: inner dim `cols` (contiguous), outer dim `rows` with row stride `ld` elements.
 inline int make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows,
-                    int esize = 2) {
+                    int esize = 2, bool atom32 = false) {
   // inner box is always 128 bytes = the swizzle span (64 bf16 or 32 fp32)
   auto enc = get_encode();
   if (!enc) return -10;
@@ -205,8 +217,8 @@ inline int make_map(CUtensorMap* map, const void* ptr, long long rows, long long
   cuuint32_t box[2] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS && getenv("DLB_DEBUG_TMAP"))
     fprintf(stderr, "[dlb] cuTensorMapEncodeTiled failed (%d): ptr=%p rows=%lld cols=%lld ld=%lld box_rows=%d\n", (int)r, ptr, rows, cols, ld, box_rows);
   return r == CUDA_SUCCESS ? 0 : -11;
@@ -214,7 +226,7 @@ inline int make_map(CUtensorMap* map, const void* ptr, long long rows, long long
 
 // general rank-n bf16 tensor map (dims/strides innermost first; strides in elements for dims 1..n-1)
 inline int make_map_nd(CUtensorMap* map, const void* ptr, int rank, const long long* dims, const long long* strides, const int* box,
-                       int esize = 2) {
+                       int esize = 2, bool atom32 = false) {
   auto enc = get_encode();
   if (!enc) return -10;
   static thread_local bool ctx_bound = false;
@@ -223,8 +235,8 @@ inline int make_map_nd(CUtensorMap* map, const void* ptr, int rank, const long l
   for (int i = 0; i < rank; ++i) { d[i] = (cuuint64_t)dims[i]; b[i] = (cuuint32_t)box[i]; es[i] = 1; }
   for (int i = 1; i < rank; ++i) sbytes[i - 1] = (cuuint64_t)strides[i] * (cuuint64_t)esize;
   CUresult r = enc(map, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), d, sbytes, b, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS && getenv("DLB_DEBUG_TMAP"))
     fprintf(stderr, "[dlb] cuTensorMapEncodeTiled(rank %d) failed (%d)\n", rank, (int)r);
   return r == CUDA_SUCCESS ? 0 : -11;

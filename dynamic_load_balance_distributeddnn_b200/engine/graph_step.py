@@ -23,7 +23,15 @@ class GraphedStep:
         self.y = torch.empty_like(yb)
         self.x.copy_(xb)
         self.y.copy_(yb)
-        self.graph = torch.cuda.CUDAGraph()
+        # keep_graph: the cudaGraph_t stays alive after capture so its nodes can be counted (dlb_graph_node_counts) -- the
+        # number of dependent nodes, not FLOPs, bounds the step at small per-rank batches
+        try:
+            self.graph = torch.cuda.CUDAGraph(keep_graph=True)
+            self._keep = True
+        except TypeError:
+            self.graph = torch.cuda.CUDAGraph()
+            self._keep = False
+        self.node_counts = None
         # DLB_GRAPH_DUMP=<prefix>: write the captured graph as <prefix>.b<batch>.rank<r>.dot (cudaGraphDebugDotPrint);
         # `python tools/graph_nodes.py <file>` reports node counts per kind / kernel and the critical-path length --
         # the quantity that bounds the step at small per-rank batches
@@ -46,6 +54,21 @@ class GraphedStep:
             t.loss_acc += loss.float()
             t.step_t += 1
         self.native_launches = ops._native.launch_count() - launches0
+        if self._keep:
+            try:
+                import ctypes
+                lib = ops._native.get()
+                if lib is not None and hasattr(lib, "dlb_graph_node_counts"):
+                    lib.dlb_graph_node_counts.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+                    lib.dlb_graph_node_counts.restype = ctypes.c_int
+                    buf = (ctypes.c_longlong * 9)()
+                    if lib.dlb_graph_node_counts(ctypes.c_void_p(int(self.graph.raw_cuda_graph())), buf) == 0:
+                        keys = ("total", "kernel", "memcpy", "memset", "host", "event_record", "event_wait", "other", "edges")
+                        self.node_counts = dict(zip(keys, [int(v) for v in buf]))
+                        t.graph_nodes = self.node_counts
+            except Exception:          # noqa: BLE001 - introspection only
+                self.node_counts = None
+            self.graph.instantiate()
         if dump:
             b = int(yb.shape[0]) if not t.is_lm else int(xb.shape[1])
             self.graph.debug_dump(f"{dump}.b{b}.rank{t.rank}.dot")
