@@ -27,8 +27,10 @@ static int unr_env(const char* name, int dflt) {
 }
 static void unr_init() {
   if (g_unr_red) return;
-  g_unr_red = unr_env("DLB_GN_UNR_RED", 2);
-  g_unr_fwd = unr_env("DLB_GN_UNR_FWD", 2);
+  // sweep on B200 (profiles/r2_03_gn_sweep.txt): one row in flight per thread wins everywhere -- more rows cost registers,
+  // i.e. resident warps, and the kernels are occupancy- not MLP-limited (backward reduce 97 us at 1 row, 124 at 2, 183 at 4)
+  g_unr_red = unr_env("DLB_GN_UNR_RED", 1);
+  g_unr_fwd = unr_env("DLB_GN_UNR_FWD", 1);
   g_unr_bwd = unr_env("DLB_GN_UNR_BWD", 1);
 }
 
@@ -191,23 +193,61 @@ __global__ void gn_coeff_kernel(const float* __restrict__ table, int64_t table_n
 
 // ---------------------------------------------------------------------------------------------
 // (2a) forward apply: y = act(gamma*(x-mu)*rstd + beta (+ res))
+// `tab` (optional): derive the group statistics from the per-(sample, channel) (sum, sumsq) table inside the kernel instead of
+// reading precomputed mean/rstd -- folds the finalize/coefficient kernel into the apply pass; block x == 0 of each sample then
+// also publishes mean/rstd and the affine coefficient rows (coef_a, coef_b) the backward pass needs.
+struct FwdFromTable {
+  const float* tab; int64_t tab_ns; float eps;
+  float* mean_out; float* rstd_out; float* coef_a; float* coef_b; int64_t coef_ld;
+};
+
 template <typename T, int V, bool RELU, bool RES, int UNR>
 __global__ void __launch_bounds__(kThreads)
 gn_fwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ res, int64_t ldr,
                     T* __restrict__ y, int64_t ldy, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ mean,
-                    const float* __restrict__ rstd, int HW, int C, int G, int rows_per_block) {
+                    const float* __restrict__ rstd, int HW, int C, int G, int rows_per_block, const FwdFromTable ft) {
   dlb_pdl_wait();
-  extern __shared__ float smem[];            // a[C], b[C]
+  extern __shared__ float smem[];            // a[C], b[C] (+ mu[G], rs[G] with ft.tab)
   float* sa = smem;
   float* sb = smem + C;
   const int n = blockIdx.y, cpg = C / G;
-  for (int c = threadIdx.x; c < C; c += kThreads) {
-    const int g = c / cpg;
-    const float r = rstd[n * G + g], mu = mean[n * G + g];
-    const float a = gamma[c] * r;
-    sa[c] = a;
-    sb[c] = beta[c] - mu * a;
+  if (ft.tab != nullptr) {
+    float* smu = smem + 2 * C;
+    float* srs = smu + G;
+    for (int g = threadIdx.x; g < G; g += kThreads) {
+      const float* t = ft.tab + (int64_t)n * ft.tab_ns + (int64_t)g * cpg * 2;
+      float s = 0.f, ss = 0.f;
+      for (int i = 0; i < cpg; ++i) { s += t[2 * i]; ss += t[2 * i + 1]; }
+      const float m = 1.f / ((float)cpg * (float)HW);
+      const float mu = s * m;
+      const float r = rsqrtf(fmaxf(ss * m - mu * mu, 0.f) + ft.eps);
+      smu[g] = mu; srs[g] = r;
+      if (blockIdx.x == 0) { ft.mean_out[n * G + g] = mu; ft.rstd_out[n * G + g] = r; }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+      const int g = c / cpg;
+      const float a = gamma[c] * srs[g];
+      sa[c] = a;
+      sb[c] = beta[c] - smu[g] * a;
+    }
+    if (blockIdx.x == 0 && ft.coef_a != nullptr) {
+      for (int c = threadIdx.x; c < ft.coef_ld; c += kThreads) {
+        float a = 0.f, b = 0.f;
+        if (c < C) { const int g = c / cpg; a = gamma[c] * srs[g]; b = beta[c] - smu[g] * a; }
+        ft.coef_a[(int64_t)n * ft.coef_ld + c] = a;
+        ft.coef_b[(int64_t)n * ft.coef_ld + c] = b;
+      }
+    }
+  } else {
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+      const int g = c / cpg;
+      const float r = rstd[n * G + g], mu = mean[n * G + g];
+      const float a = gamma[c] * r;
+      sa[c] = a;
+      sb[c] = beta[c] - mu * a;
+    }
   }
   __syncthreads();
   const int lanes = C / V;
@@ -399,6 +439,171 @@ gn_bwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// (1)+(2b) in ONE launch: GroupNorm(+ReLU) backward with the ReLU mask recomputed from the forward coefficients.
+//   phase 1: per-(n, c) sums (sum dz, sum dz*x) of this block's rows -> table[n] (atomics), affine-parameter gradients
+//   per-sample barrier: the `gridDim.x` blocks of sample n count themselves in done[n] and wait for each other (they are
+//            launched back to back and are all resident long before the first one gets here; watchdog instead of a hang)
+//   phase 2: dx (+)= k1*dz + k2*x + k3 over the same rows -- x and dy were read a few microseconds ago by this very block
+// Saves a kernel launch per GroupNorm backward (two per DenseNet layer) and turns the second pass into cache hits.
+template <typename T, int V, bool ACC>
+__global__ void __launch_bounds__(kThreads)
+gn_bwd_fused_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy, T* __restrict__ dx, int64_t lddx,
+                    const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    float* __restrict__ table, int64_t table_ns, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                    const float* __restrict__ coef_a, const float* __restrict__ coef_b, int64_t coef_ld,
+                    unsigned* __restrict__ done, int HW, int C, int G, int rows_per_block) {
+  dlb_pdl_wait();
+  extern __shared__ float smem[];            // phase 1: acc[2C];  phase 2: k1[C], k2[C], k3[C], s1[G], s2[G]
+  const int n = blockIdx.y, cpg = C / G;
+  const int lanes = C / V;                   // <= kThreads (checked by the host)
+  const int row_lanes = kThreads / lanes;
+  const int lane = threadIdx.x % lanes, rl = threadIdx.x / lanes;
+  const bool active = rl < row_lanes;
+  const int c = lane * V;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(HW, r0 + rows_per_block);
+  for (int i = threadIdx.x; i < 2 * C; i += kThreads) smem[i] = 0.f;
+  float ka[V], kb[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { ka[i] = coef_a[(int64_t)n * coef_ld + c + i]; kb[i] = coef_b[(int64_t)n * coef_ld + c + i]; }
+  __syncthreads();
+  // ---- phase 1 ----
+  if (active) {
+    float a0[V], a1[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { a0[i] = 0.f; a1[i] = 0.f; }
+    constexpr int UNR = 1;                   // one row in flight per thread: registers -> occupancy beats MLP (profiles/r2_03_gn_sweep.txt)
+    for (int rb = r0 + rl; rb < r1; rb += row_lanes * UNR) {
+      float xv[UNR][V], gv[UNR][V];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int r = rb + u * row_lanes;
+        if (r < r1) {
+          const int64_t row = (int64_t)n * HW + r;
+          load_vec<T, V>(x + row * ldx + c, xv[u]);
+          load_vec<T, V>(dy + row * lddy + c, gv[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int r = rb + u * row_lanes;
+        if (r < r1) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            const float gz = fmaf(ka[i], xv[u][i], kb[i]) > 0.f ? gv[u][i] : 0.f;
+            a0[i] += gz; a1[i] += gz * xv[u][i];
+          }
+        }
+      }
+    }
+    bool owner = true;
+    if (lanes < 32 && (lanes & (lanes - 1)) == 0) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        for (int o = lanes; o < 32; o <<= 1) {
+          a0[i] += __shfl_xor_sync(0xffffffffu, a0[i], o);
+          a1[i] += __shfl_xor_sync(0xffffffffu, a1[i], o);
+        }
+      }
+      owner = (threadIdx.x & 31) < lanes;
+    }
+    if (owner) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        atomicAdd(&smem[2 * (c + i)], a0[i]);
+        atomicAdd(&smem[2 * (c + i) + 1], a1[i]);
+      }
+    }
+  }
+  __syncthreads();
+  float* tab = table + (int64_t)n * table_ns;
+  for (int i = threadIdx.x; i < 2 * C; i += kThreads) atomicAdd(&tab[i], smem[i]);
+  if (dgamma != nullptr) {
+    for (int cc = threadIdx.x; cc < C; cc += kThreads) {
+      const float A = smem[2 * cc], B = smem[2 * cc + 1];
+      const int g = cc / cpg;
+      atomicAdd(&dbeta[cc], A);
+      atomicAdd(&dgamma[cc], rstd[n * G + g] * (B - mean[n * G + g] * A));
+    }
+  }
+  // ---- per-sample barrier ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(&done[n], 1u);
+    unsigned spins = 0;
+    while (true) {
+      unsigned v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(done + n) : "memory");
+      if (v >= gridDim.x) break;
+      if (++spins > (1u << 24)) __trap();      // watchdog: a sibling block never arrived
+    }
+  }
+  __syncthreads();
+  // ---- phase 2 ----
+  float* k1 = smem;
+  float* k2 = smem + C;
+  float* k3 = smem + 2 * C;
+  float* s1 = smem + 3 * C;
+  float* s2 = s1 + G;
+  for (int g = threadIdx.x; g < G; g += kThreads) {
+    const float mu = mean[n * G + g], r = rstd[n * G + g];
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < cpg; ++i) {
+      const int cc = g * cpg + i;
+      const float A = __ldcg(tab + 2 * cc), B = __ldcg(tab + 2 * cc + 1);
+      a += gamma[cc] * A;
+      b += gamma[cc] * r * (B - mu * A);
+    }
+    s1[g] = a;
+    s2[g] = b;
+  }
+  __syncthreads();
+  const float inv_m = 1.f / ((float)cpg * (float)HW);
+  for (int cc = threadIdx.x; cc < C; cc += kThreads) {
+    const int g = cc / cpg;
+    const float mu = mean[n * G + g], r = rstd[n * G + g];
+    k1[cc] = gamma[cc] * r;
+    const float q = r * r * s2[g] * inv_m;
+    k2[cc] = -q;
+    k3[cc] = -r * s1[g] * inv_m + q * mu;
+  }
+  __syncthreads();
+  if (!active) return;
+  float q1[V], q2[V], q3[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { q1[k] = k1[c + k]; q2[k] = k2[c + k]; q3[k] = k3[c + k]; }
+  constexpr int UNR2 = 1;
+  for (int rb = r0 + rl; rb < r1; rb += row_lanes * UNR2) {
+    float xv[UNR2][V], gv[UNR2][V], old[UNR2][V];
+#pragma unroll
+    for (int u = 0; u < UNR2; ++u) {
+      const int r = rb + u * row_lanes;
+      if (r < r1) {
+        const int64_t row = (int64_t)n * HW + r;
+        load_vec<T, V>(x + row * ldx + c, xv[u]);
+        load_vec<T, V>(dy + row * lddy + c, gv[u]);
+        if constexpr (ACC) load_vec<T, V>(dx + row * lddx + c, old[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR2; ++u) {
+      const int r = rb + u * row_lanes;
+      if (r < r1) {
+        float out[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const float gz = fmaf(ka[k], xv[u][k], kb[k]) > 0.f ? gv[u][k] : 0.f;
+          out[k] = fmaf(q1[k], gz, fmaf(q2[k], xv[u][k], q3[k]));
+          if constexpr (ACC) out[k] += old[u][k];
+        }
+        store_vec<T, V>(dx + ((int64_t)n * HW + r) * lddx + c, out);
+      }
+    }
+  }
+}
+
 // dgamma[c] = sum_n rstd*(B - mu*A), dbeta[c] = sum_n A.   Block = 32 channels x 8 sample-lanes.
 __global__ void __launch_bounds__(256) gn_param_grad_kernel(const float* __restrict__ table, int64_t table_ns, const float* __restrict__ mean,
                                      const float* __restrict__ rstd, float* __restrict__ dgamma,
@@ -428,17 +633,23 @@ __global__ void __launch_bounds__(256) gn_param_grad_kernel(const float* __restr
 inline void grid_for(int N, int HW, int C, int V, dim3& grid, int& rows_per_block) {
   const int lanes = C / V;
   const int row_lanes = lanes >= kThreads ? 1 : kThreads / lanes;
-  int chunks = (148 * 8 + N - 1) / N;                     // about one full wave of resident blocks
   int max_chunks = HW / (row_lanes * 4);                  // keep >= 4 rows per row-lane per block
-  // every block pays a per-sample preamble (coefficients / zeroing / 2C atomics): give it >= ~96 KB (tuned: 24/48/96/192/384 KB sweep on B200) of rows to
-  // stream, otherwise small per-rank batches drown in fixed cost (profiles: 16 us reduce kernels at batch 128)
-  const long long bytes_per_sample = (long long)HW * C * (V == 4 ? 4 : 2);
-  if (!g_min_kb) { const char* e = getenv("DLB_GN_MIN_KB"); g_min_kb = e ? atoi(e) : 96; if (g_min_kb < 1) g_min_kb = 96; }
-  const int min_kb = g_min_kb;
-  int by_work = (int)(bytes_per_sample / ((long long)min_kb * 1024));
-  if (by_work < 1) by_work = 1;
-  if (chunks > by_work) chunks = by_work;
   if (max_chunks < 1) max_chunks = 1;
+  // Every block pays a per-sample preamble (coefficients / zeroing / 2C atomics).  Large problems: give each block
+  // >= ~192 KB of rows to stream (48/96/192 KB sweep on B200 at batch 512: 70.6/62.5/56.3 us), at most about one full wave of
+  // resident blocks.  Small problems (per-rank batches of 32..128 after the DBS split): the 96 KB rule would leave one block
+  // per sample -- 64 blocks on 148 SMs, each streaming its sample serially (measured 14-19 us for kernels that move < 10 MB)
+  // -- so parallelism wins: aim for two blocks per SM as long as a block still gets >= 16 KB.
+  const long long bytes_per_sample = (long long)HW * C * (V == 4 ? 4 : 2);
+  if (!g_min_kb) { const char* e = getenv("DLB_GN_MIN_KB"); g_min_kb = e ? atoi(e) : 192; if (g_min_kb < 1) g_min_kb = 192; }
+  const long long total = (long long)N * bytes_per_sample;
+  long long want = total / ((long long)g_min_kb * 1024);
+  long long floor_ctas = total / (16 * 1024);
+  if (floor_ctas > 2 * 148) floor_ctas = 2 * 148;
+  if (want < floor_ctas) want = floor_ctas;
+  if (want > 148 * 8) want = 148 * 8;
+  if (want < 1) want = 1;
+  int chunks = (int)((want + N - 1) / N);
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
   rows_per_block = (HW + chunks - 1) / chunks;
@@ -471,13 +682,13 @@ int reduce2_launch(int mode, const void* x, int64_t ldx, const void* dy, int64_t
 template <typename T, int V>
 int fwd_apply_launch(const void* x, int64_t ldx, const void* res, int64_t ldr, void* y, int64_t ldy,
                      const float* gamma, const float* beta, const float* mean, const float* rstd,
-                     int N, int HW, int C, int G, int relu, cudaStream_t st) {
+                     int N, int HW, int C, int G, int relu, cudaStream_t st, FwdFromTable ft = FwdFromTable{}) {
   dim3 grid; int rpb;
   grid_for(N, HW, C, V, grid, rpb);
-  const size_t sm = 2 * C * sizeof(float);
+  const size_t sm = (2 * C + 2 * G) * sizeof(float);
   const T* X = (const T*)x; const T* R = (const T*)res; T* Y = (T*)y;
   unr_init();
-#define GOU(RL, RS, U) dlb_launch(gn_fwd_apply_kernel<T, V, RL, RS, U>, grid, dim3(kThreads), sm, st, X, (int64_t)ldx, R, (int64_t)ldr, Y, (int64_t)ldy, gamma, beta, mean, rstd, HW, C, G, rpb)
+#define GOU(RL, RS, U) dlb_launch(gn_fwd_apply_kernel<T, V, RL, RS, U>, grid, dim3(kThreads), sm, st, X, (int64_t)ldx, R, (int64_t)ldr, Y, (int64_t)ldy, gamma, beta, mean, rstd, HW, C, G, rpb, ft)
 #define GO(RL, RS) do { if (g_unr_fwd == 4) GOU(RL, RS, 4); else if (g_unr_fwd == 2) GOU(RL, RS, 2); else GOU(RL, RS, 1); } while (0)
   if (relu) { if (res) GO(true, true); else GO(true, false); }
   else { if (res) GO(false, true); else GO(false, false); }
@@ -594,6 +805,29 @@ DLB_API int dlb_gn_bwd_apply_coef(int dtype, const void* x, int64_t ldx, const v
   return rc;
 }
 
+
+// GroupNorm(+ReLU) backward, reduce + apply in one launch (gn_bwd_fused_kernel).  `table` [N][table_ns], `dgamma`/`dbeta` [C] and
+// `done` [N] (32-bit counters) must be zero on entry.  Returns 1 when the shape is not supported (caller falls back to
+// dlb_nc_reduce2_bwd_coef + dlb_gn_bwd_apply_coef), 0 on success.
+DLB_API int dlb_gn_bwd_fused(int dtype, const void* x, int64_t ldx, const void* dy, int64_t lddy, void* dx, int64_t lddx,
+                             const float* gamma, const float* mean, const float* rstd, float* table, int64_t table_ns,
+                             float* dgamma, float* dbeta, const float* ca, const float* cb, int64_t cld, void* done,
+                             int N, int HW, int C, int G, int acc, void* stream) {
+  if (table_ns <= 0) table_ns = 2 * (int64_t)C;
+  const int V = dtype == DLB_BF16 ? 8 : 4;
+  if (!vec_ok(dtype, C, {ldx, lddy, lddx}, {x, dy, dx}) || C / V > kThreads || C > 6000 || (C % G)) return 1;
+  dim3 grid; int rpb;
+  grid_for(N, HW, C, V, grid, rpb);
+  if (grid.x > 64) return 1;                 // keep a sample's blocks trivially co-resident
+  const size_t sm = (size_t)(3 * C + 2 * G) * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+#define FGO(TT, VV, AC) dlb_launch(gn_bwd_fused_kernel<TT, VV, AC>, grid, dim3(kThreads), sm, st, (const TT*)x, (int64_t)ldx, (const TT*)dy, (int64_t)lddy, (TT*)dx, (int64_t)lddx, gamma, mean, rstd, table, (int64_t)table_ns, dgamma, dbeta, ca, cb, (int64_t)cld, (unsigned*)done, HW, C, G, rpb)
+  if (dtype == DLB_BF16) { if (acc) FGO(__nv_bfloat16, 8, true); else FGO(__nv_bfloat16, 8, false); }
+  else { if (acc) FGO(float, 4, true); else FGO(float, 4, false); }
+#undef FGO
+  return dlb_post_launch();
+}
+
 // Per-(sample, channel) statistics of x fused with a strided copy of x into `dst` (moves a conv output into its
 // channel slice of the dense-block buffer and produces its GroupNorm statistics in the same pass).
 DLB_API int dlb_copy_stats(int dtype, const void* x, int64_t ldx, void* dst, int64_t ldd, float* table, int64_t table_ns,
@@ -629,6 +863,20 @@ DLB_API int dlb_gn_fwd_apply(int dtype, const void* x, int64_t ldx, const void* 
   int rc = 0;
   const bool vec = vec_ok(dtype, C, {ldx, res ? ldr : 0, ldy}, {x, res, y});
   DISPATCH(dtype, vec, (rc = fwd_apply_launch<T, V>(x, ldx, res, ldr, y, ldy, gamma, beta, mean, rstd, N, HW, C, G, relu, (cudaStream_t)stream)));
+  return rc;
+}
+
+// GroupNorm(+ReLU) apply with the group statistics derived in-kernel from the (sum, sumsq) table; also writes mean/rstd [N*G]
+// and the coefficient rows ca/cb [N][cld] (zero padded) for the backward pass.  Replaces dlb_gn_coeff + dlb_gn_fwd_apply.
+DLB_API int dlb_gn_fwd_apply_table(int dtype, const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma, const float* beta,
+                                   const float* table, int64_t table_ns, float* mean, float* rstd, float* ca, float* cb, int64_t cld,
+                                   int N, int HW, int C, int G, float eps, int relu, void* stream) {
+  int rc = 0;
+  if (table_ns <= 0) table_ns = 2 * (int64_t)C;
+  FwdFromTable ft;
+  ft.tab = table; ft.tab_ns = table_ns; ft.eps = eps; ft.mean_out = mean; ft.rstd_out = rstd; ft.coef_a = ca; ft.coef_b = cb; ft.coef_ld = cld;
+  const bool vec = vec_ok(dtype, C, {ldx, ldy}, {x, y});
+  DISPATCH(dtype, vec, (rc = fwd_apply_launch<T, V>(x, ldx, nullptr, 0, y, ldy, gamma, beta, mean, rstd, N, HW, C, G, relu, (cudaStream_t)stream, ft)));
   return rc;
 }
 

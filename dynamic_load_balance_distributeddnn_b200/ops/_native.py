@@ -55,6 +55,8 @@ def _declare(lib: ctypes.CDLL) -> None:
         "dlb_nc_reduce2_bwd": (i32, [i32, i32, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
         "dlb_nc_reduce2_bwd_coef": (i32, [i32, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
         "dlb_gn_bwd_apply_coef": (i32, [i32, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, vp]),
+        "dlb_gn_fwd_apply_table": (i32, [i32, vp, i64, vp, i64, vp, vp, vp, i64, vp, vp, vp, vp, i64, i32, i32, i32, i32, c_float, i32, vp]),
+        "dlb_gn_bwd_fused": (i32, [i32, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, vp]),
         "dlb_copy_stats": (i32, [i32, vp, i64, vp, i64, vp, i64, i32, i32, i32, vp]),
         "dlb_norm_skip_zero": (None, [i32]),
         "dlb_gn_coeff": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, c_float, vp]),

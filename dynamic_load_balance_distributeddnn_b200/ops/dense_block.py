@@ -30,6 +30,7 @@ _CONV_BWD = torch.ops.aten.convolution_backward
 _SIDE = {}
 _USE_SIDE = os.environ.get("DLB_SIDE_STREAM", "1") == "1"
 _USE_CONV3 = os.environ.get("DLB_TC_CONV3", "1") == "1"
+_FUSED_GN_BWD = os.environ.get("DLB_FUSED_GN_BWD", "1") == "1"
 
 
 def _side_stream(device) -> torch.cuda.Stream:
@@ -141,11 +142,12 @@ class _DenseBlockFn(torch.autograd.Function):
                 kpad2 = (cm + 63) // 64 * 64
                 ca2 = torch.empty((n, kpad2), dtype=torch.float32, device=x.device)
                 cb2 = torch.empty((n, kpad2), dtype=torch.float32, device=x.device)
-                nat.check(lib.dlb_gn_coeff(t2.data_ptr(), 2 * cm, g2w.data_ptr(), g2b.data_ptr(), mean2.data_ptr(), rstd2.data_ptr(),
-                                           ca2.data_ptr(), cb2.data_ptr(), kpad2, n, cm, groups, hw, eps, st), "dense.coeff2")
                 yhat = torch.empty_like(yv, memory_format=torch.channels_last)
-                nat.check(lib.dlb_gn_fwd_apply(dt, yv.data_ptr(), cm, 0, 0, yhat.data_ptr(), cm, g2w.data_ptr(), g2b.data_ptr(),
-                                               mean2.data_ptr(), rstd2.data_ptr(), n, hw, cm, groups, 1, st), "dense.apply2")
+                # GN2 statistics -> coefficients -> apply + ReLU in ONE launch: the group statistics are derived from the
+                # epilogue's (sum, sumsq) table inside the apply kernel (which also saves mean/rstd/coefficients for backward)
+                nat.check(lib.dlb_gn_fwd_apply_table(dt, yv.data_ptr(), cm, yhat.data_ptr(), cm, g2w.data_ptr(), g2b.data_ptr(), t2.data_ptr(),
+                                                     2 * cm, mean2.data_ptr(), rstd2.data_ptr(), ca2.data_ptr(), cb2.data_ptr(), kpad2,
+                                                     n, hw, cm, groups, eps, 1, st), "dense.apply2")
                 xhat = None
                 coefs = (ca, cb, ca2, cb2)
             else:
@@ -205,7 +207,7 @@ class _DenseBlockFn(torch.autograd.Function):
         sizes = []
         for l in range(n_layers):
             cl_ = c0 + l * g
-            sizes.append((n * cm0 * 2, cm0, cm0, n * cl_ * 2, cl_, cl_))
+            sizes.append((n * cm0 * 2, cm0, cm0, n * cl_ * 2, cl_, cl_, n, n))     # tables, affine grads, 2 x per-sample barrier counters
         arena = torch.zeros(sum(sum(sz) for sz in sizes), dtype=torch.float32, device=buf.device)
         dw1_arena = torch.zeros(sum(cm0 * (c0 + l * g) for l in range(n_layers)), dtype=torch.float32, device=buf.device)
         a_off, w_off = [0], [0]
@@ -279,7 +281,9 @@ class _DenseBlockFn(torch.autograd.Function):
             db2 = arena[o:o + cm]; o += cm
             t1 = arena[o:o + sizes[l][3]]; o += sizes[l][3]
             dg1 = arena[o:o + cl]; o += cl
-            db1 = arena[o:o + cl]
+            db1 = arena[o:o + cl]; o += cl
+            done2 = arena[o:o + n]; o += n
+            done1 = arena[o:o + n]
             sunk = []
             if sv is not None and ca2.numel() > 0:
                 dg2, db2 = sv[6 * l + 3], sv[6 * l + 4]
@@ -292,12 +296,21 @@ class _DenseBlockFn(torch.autograd.Function):
             if ca2.numel() > 0:
                 # ReLU mask recomputed from the forward's affine coefficients: yhat is not re-read by the GN2 backward
                 kp2 = ca2.shape[1]
-                nat.check(lib.dlb_nc_reduce2_bwd_coef(dt, y.data_ptr(), cm, dyhat.data_ptr(), cm, t2.data_ptr(), 0, mean2.data_ptr(),
-                                                      rstd2.data_ptr(), dg2.data_ptr(), db2.data_ptr(), ca2.data_ptr(), cb2.data_ptr(),
-                                                      kp2, n, hw, cm, groups, st), "dense.gn2_red")
-                nat.check(lib.dlb_gn_bwd_apply_coef(dt, y.data_ptr(), cm, dyhat.data_ptr(), cm, dy.data_ptr(), cm, g2w.data_ptr(),
-                                                    mean2.data_ptr(), rstd2.data_ptr(), t2.data_ptr(), 0, ca2.data_ptr(), cb2.data_ptr(),
-                                                    kp2, n, hw, cm, groups, 0, st), "dense.gn2_app")
+                rc = 1
+                if _FUSED_GN_BWD:
+                    # reduce + apply in ONE launch (per-sample barrier inside the kernel)
+                    rc = lib.dlb_gn_bwd_fused(dt, y.data_ptr(), cm, dyhat.data_ptr(), cm, dy.data_ptr(), cm, g2w.data_ptr(), mean2.data_ptr(),
+                                              rstd2.data_ptr(), t2.data_ptr(), 0, dg2.data_ptr(), db2.data_ptr(), ca2.data_ptr(),
+                                              cb2.data_ptr(), kp2, done2.data_ptr(), n, hw, cm, groups, 0, st)
+                    if rc not in (0, 1):
+                        nat.check(rc, "dense.gn2_fused")
+                if rc == 1:
+                    nat.check(lib.dlb_nc_reduce2_bwd_coef(dt, y.data_ptr(), cm, dyhat.data_ptr(), cm, t2.data_ptr(), 0, mean2.data_ptr(),
+                                                          rstd2.data_ptr(), dg2.data_ptr(), db2.data_ptr(), ca2.data_ptr(), cb2.data_ptr(),
+                                                          kp2, n, hw, cm, groups, st), "dense.gn2_red")
+                    nat.check(lib.dlb_gn_bwd_apply_coef(dt, y.data_ptr(), cm, dyhat.data_ptr(), cm, dy.data_ptr(), cm, g2w.data_ptr(),
+                                                        mean2.data_ptr(), rstd2.data_ptr(), t2.data_ptr(), 0, ca2.data_ptr(), cb2.data_ptr(),
+                                                        kp2, n, hw, cm, groups, 0, st), "dense.gn2_app")
             else:
                 nat.check(lib.dlb_gn_backward(dt, y.data_ptr(), cm, dyhat.data_ptr(), cm, yhat.data_ptr(), cm, dy.data_ptr(), cm,
                                               0, 0, g2w.data_ptr(), mean2.data_ptr(), rstd2.data_ptr(), t2.data_ptr(),
@@ -338,12 +351,20 @@ class _DenseBlockFn(torch.autograd.Function):
                     gemm_tc.dgrad_gn_raw(2, dy.data_ptr(), cm, w1_2d.data_ptr(), w1_2d.stride(0), xs, ct, dxs, ct, n * hw, cl, cm, hw,
                                          ca, cb, k23[0], k23[1], 0, 0, buf.device)
                 else:
-                    nat.check(lib.dlb_nc_reduce2_bwd_coef(dt, xs, ct, dxhat.data_ptr(), cl, t1.data_ptr(), 0, mean1.data_ptr(),
-                                                          rstd1.data_ptr(), dg1.data_ptr(), db1.data_ptr(), ca.data_ptr(),
-                                                          cb.data_ptr(), kpad, n, hw, cl, groups, st), "dense.gn1_red")
-                    nat.check(lib.dlb_gn_bwd_apply_coef(dt, xs, ct, dxhat.data_ptr(), cl, dxs, ct, g1w.data_ptr(), mean1.data_ptr(),
-                                                        rstd1.data_ptr(), t1.data_ptr(), 0, ca.data_ptr(), cb.data_ptr(), kpad,
-                                                        n, hw, cl, groups, 1, st), "dense.gn1_app")
+                    rc = 1
+                    if _FUSED_GN_BWD:
+                        rc = lib.dlb_gn_bwd_fused(dt, xs, ct, dxhat.data_ptr(), cl, dxs, ct, g1w.data_ptr(), mean1.data_ptr(), rstd1.data_ptr(),
+                                                  t1.data_ptr(), 0, dg1.data_ptr(), db1.data_ptr(), ca.data_ptr(), cb.data_ptr(), kpad,
+                                                  done1.data_ptr(), n, hw, cl, groups, 1, st)
+                        if rc not in (0, 1):
+                            nat.check(rc, "dense.gn1_fused")
+                    if rc == 1:
+                        nat.check(lib.dlb_nc_reduce2_bwd_coef(dt, xs, ct, dxhat.data_ptr(), cl, t1.data_ptr(), 0, mean1.data_ptr(),
+                                                              rstd1.data_ptr(), dg1.data_ptr(), db1.data_ptr(), ca.data_ptr(),
+                                                              cb.data_ptr(), kpad, n, hw, cl, groups, st), "dense.gn1_red")
+                        nat.check(lib.dlb_gn_bwd_apply_coef(dt, xs, ct, dxhat.data_ptr(), cl, dxs, ct, g1w.data_ptr(), mean1.data_ptr(),
+                                                            rstd1.data_ptr(), t1.data_ptr(), 0, ca.data_ptr(), cb.data_ptr(), kpad,
+                                                            n, hw, cl, groups, 1, st), "dense.gn1_app")
             else:
                 w1c = w1 if w1.dtype == xhat.dtype else w1.to(xhat.dtype)
                 dxhat, dw1, _ = _CONV_BWD(dy, xhat, w1c, None, [1, 1], [0, 0], [1, 1], False, [0, 0], 1, [True, True, False])

@@ -174,7 +174,12 @@ def test_dense_stage_tf32_matches_fp32_torch(g):
         z = F.conv2d(F.relu(F.group_norm(y, 32, blk.gn2.weight, blk.gn2.bias, blk.gn2.eps)), blk.conv2.weight, padding=1)
         ref = torch.cat([z, ref], 1)
     ref.backward(gy)
+    # forward: element-wise.  backward: relative L2 -- TF32 rounding of the forward flips a few ReLU decisions near zero, which
+    # moves individual gradient entries by O(10 %) of the maximum even in a bit-exact CPU emulation of TF32 truncation
+    # (measured: 12.8 % max-norm vs 0.06 % forward), while the gradient as a whole stays within ~1 %
+    def rel_l2(a, b):
+        return ((a - b).pow(2).sum().sqrt() / b.pow(2).sum().sqrt().clamp_min(1e-12)).item()
     assert (out - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
-    assert (gx - x.grad).abs().max().item() < 2e-2 * x.grad.abs().max().item()
+    assert rel_l2(gx, x.grad) < 3e-2, rel_l2(gx, x.grad)
     for a, p in zip(got, stage.parameters()):
-        assert (a - p.grad).abs().max().item() < 2e-2 * max(1e-3, p.grad.abs().max().item()), p.shape
+        assert rel_l2(a, p.grad) < 3e-2, (p.shape, rel_l2(a, p.grad))

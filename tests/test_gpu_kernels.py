@@ -366,10 +366,11 @@ def test_fused_embedding_frontend(nat, dtype, tol):
     assert (w.grad.float() - cnt * math.sqrt(d) / 0.75).abs().max().item() < 2e-2 * (cnt.max().item() * math.sqrt(d) / 0.75)
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 3e-2)])
 @pytest.mark.parametrize("n,c,cs,hw", [(8, 32, 8, 32), (5, 160, 40, 8), (3, 384, 96, 4)])
 def test_fused_squeeze_excite(nat, dtype, tol, n, c, cs, hw):
     from dynamic_load_balance_distributeddnn_b200.ops import se
+    torch.backends.cudnn.allow_tf32 = False          # the reference below must be true fp32 (cuDNN defaults to TF32 convolutions)
     torch.manual_seed(n + c)
     x = _cl(torch.randn(n, c, hw, hw, device="cuda")).to(dtype).requires_grad_(True)
     w1 = (torch.randn(cs, c, 1, 1, device="cuda") / c ** 0.5).to(dtype).requires_grad_(True)
