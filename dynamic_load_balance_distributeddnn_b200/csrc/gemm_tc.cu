@@ -50,13 +50,18 @@ struct GemmParams {
   int conv_H, conv_W, conv_C;   // input spatial size and channels (K = 9 * conv_C)
   int conv_kchunks;             // ceil(conv_C / 64)
   int conv_sign;                // +1 forward (x[h+dy, w+dx]), -1 dgrad (dy[h-dy, w-dx])
+  int conv_halo_rows;           // HALO: (hb + 2) * W pixels per stage tile
 };
 
-template <typename E, int BN> struct Cfg {
+// HALO (3x3 on maps with >= 128 pixels per image): one stage holds, for one horizontal tap dx and one channel chunk, the
+// input rows h0-1 .. h0+R of the tile (R+2 image rows, loaded ONCE) and the weights of the three vertical taps; the three
+// A operands of a stage are the same shared-memory tile at row offsets 0, W, 2W (whole 1024-byte swizzle groups), so the
+// activations cross L2->SM three times per tile instead of nine.
+template <typename E, int BN, bool HALO = false> struct Cfg {
   static constexpr int kEB = Elt<E>::kBytes;
-  static constexpr int kABytes = BM * 128;                         // 128 rows x one 128-byte swizzle row of K
+  static constexpr int kABytes = (HALO ? 192 : BM) * 128;          // 128 rows (or up to 192 halo rows) x one 128-byte swizzle row of K
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStageBytes = kABytes + (HALO ? 3 : 1) * kBBytes;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   // epilogue staging: per epilogue warp, kBoxes boxes of [32 rows][128 bytes] = 4 KB each, 128B-swizzled,
   // drained with cp.async.bulk.tensor stores (fully coalesced, tails clipped by the tensor map)
@@ -76,11 +81,12 @@ template <typename E, int BN> struct Cfg {
 // through an MN-major shared-memory descriptor, so no transposed copy of the weights is ever made.
 // CONV3: implicit-GEMM 3x3 convolution (see GemmParams); with B_MN it is the data-gradient (flipped taps, weights
 // consumed untransposed through a 3-D tensor map {Cin, 9, Cout}).
-template <typename E, int BN, bool PRO_GN, bool EPI_STATS, bool B_MN = false, bool CONV3 = false>
+template <typename E, int BN, bool PRO_GN, bool EPI_STATS, bool B_MN = false, bool CONV3 = false, bool HALO = false>
 __global__ void __launch_bounds__(PRO_GN ? 512 : 256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
-  using C = Cfg<E, BN>;
+  static_assert(!HALO || CONV3, "HALO is a flavour of the 3x3 implicit GEMM");
+  using C = Cfg<E, BN, HALO>;
   using EL = Elt<E>;
   constexpr int BK = EL::kAtom;
   constexpr int UMMA_K = EL::kUmmaK;
@@ -100,7 +106,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
-  const int num_kb = CONV3 ? 9 * p.conv_kchunks : (p.K + BK - 1) / BK;
+  const int num_kb = CONV3 ? (HALO ? 3 : 9) * p.conv_kchunks : (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -141,8 +147,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
           const uint32_t sb = sa + C::kABytes;
           const uint32_t fb = smem_u32(&full_bar[stage]);
-          mbar_expect_tx(fb, C::kStageBytes);
-          if constexpr (CONV3) {
+          if constexpr (HALO) {
+            // stage = (horizontal tap dxi, channel chunk kc): rows h0-1 .. h0+hb of ONE image (box {ch, W, hb+2, 1}; rows
+            // outside the image are zero-filled by the TMA unit) + the weights of the vertical taps dy = -1, 0, +1
+            const int dxi = kb / p.conv_kchunks, kc = kb - dxi * p.conv_kchunks;
+            const int hw = p.conv_H * p.conv_W;
+            const int img = m0 / hw, h0 = (m0 - img * hw) / p.conv_W;
+            mbar_expect_tx(fb, (uint32_t)(p.conv_halo_rows * 128 + 3 * C::kBBytes));
+            tma_load_4d(sa, &tmap_a, fb, kc * BK, (dxi - 1) * p.conv_sign, h0 - 1, img);
+#pragma unroll
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              const int tap = dyi * 3 + dxi;
+              if constexpr (B_MN) {
+#pragma unroll
+                for (int gi = 0; gi < kMnBoxes; ++gi)
+                  tma_load_3d(sb + dyi * C::kBBytes + gi * kMnBox, &tmap_b, fb, n0 + gi * BK, tap, kc * BK);
+              } else {
+                tma_load_2d(sb + dyi * C::kBBytes, &tmap_b, fb, tap * p.conv_C + kc * BK, n0);
+              }
+            }
+          } else if constexpr (CONV3) {
+            mbar_expect_tx(fb, C::kStageBytes);
             const int tap = kb / p.conv_kchunks, kc = kb - tap * p.conv_kchunks;
             const int dy = (tap / 3 - 1) * p.conv_sign, dx = (tap % 3 - 1) * p.conv_sign;
             const int hw = p.conv_H * p.conv_W;
@@ -155,6 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               tma_load_2d(sb, &tmap_b, fb, tap * p.conv_C + kc * BK, n0);
             }
           } else {
+            mbar_expect_tx(fb, C::kStageBytes);
             tma_load_2d(sa, &tmap_a, fb, kb * BK, m0);
             if constexpr (B_MN) {
 #pragma unroll
@@ -184,12 +210,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
           const uint32_t sb = sa + C::kABytes;
+          if constexpr (HALO) {
+#pragma unroll
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              // rows (h + dy*sign) of the halo tile: start (1 + dy*sign) image rows into it (W*128 bytes = whole swizzle groups)
+              const uint32_t a_off = (uint32_t)((1 + (dyi - 1) * p.conv_sign) * p.conv_W * 128);
+              const uint64_t adesc = make_smem_desc(sa + a_off);
+              const uint64_t bdesc = B_MN ? make_smem_desc_mn(sb + dyi * C::kBBytes, kMnBox, EL::kMn32) : make_smem_desc(sb + dyi * C::kBBytes);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                EL::mma(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)((B_MN ? 8 * UMMA_K : 2) * k), idesc, (kb | dyi | k) != 0 ? 1u : 0u);
+            }
+          } else {
           const uint64_t adesc = make_smem_desc(sa), bdesc = B_MN ? make_smem_desc_mn(sb, kMnBox, EL::kMn32) : make_smem_desc(sb);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // K-major: advance 32 bytes (one UMMA_K) inside the 128-byte swizzle atom: +2 in 16-byte units;
             // MN-major: advance UMMA_K k-rows of 128 bytes: +8*UMMA_K
             EL::mma(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)((B_MN ? 8 * UMMA_K : 2) * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
           }
           umma_commit(smem_u32(&empty_bar[stage]));            // frees the smem stage when these MMAs retire
           if (kb == num_kb - 1) umma_commit(smem_u32(&tmem_full[acc]));
@@ -623,10 +662,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
   }
 }
 
-template <typename E, int BN, bool PRO, bool STATS, bool BMN = false, bool CONV3 = false>
+template <typename E, int BN, bool PRO, bool STATS, bool BMN = false, bool CONV3 = false, bool HALO = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p, int sms, cudaStream_t st) {
-  using C = Cfg<E, BN>;
-  auto kern = gemm_tc_kernel<E, BN, PRO, STATS, BMN, CONV3>;
+  using C = Cfg<E, BN, HALO>;
+  auto kern = gemm_tc_kernel<E, BN, PRO, STATS, BMN, CONV3, HALO>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
@@ -669,7 +708,7 @@ inline GemmParams base_params(int M, int N, int K, void* d, long long ldd) {
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.d = d; p.ldd = ldd; p.accumulate_out = 0;
   p.pro_a = nullptr; p.pro_b = nullptr; p.pro_ld = 0; p.rows_per_sample = M; p.stats = nullptr; p.stats_ns = 0;
-  p.conv_H = p.conv_W = p.conv_C = 0; p.conv_kchunks = 1; p.conv_sign = 1;
+  p.conv_H = p.conv_W = p.conv_C = 0; p.conv_kchunks = 1; p.conv_sign = 1; p.conv_halo_rows = 0;
   return p;
 }
 
@@ -799,6 +838,36 @@ bool conv_tile_geometry(int N, int H, int W, int& hb, int& nb) {
   return true;
 }
 
+template <typename E, bool HALO>
+int conv3x3_launch(int dgrad, bool stats, int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p,
+                   int sms, cudaStream_t st) {
+  constexpr int EB = Elt<E>::kBytes;
+  if (dgrad) {
+    if constexpr (EB == 2) {
+      if (bn == 64) return launch<E, 64, false, false, true, true, HALO>(ta, tb, td, p, sms, st);
+      if (bn == 128) return launch<E, 128, false, false, true, true, HALO>(ta, tb, td, p, sms, st);
+      if constexpr (!HALO) return launch<E, 256, false, false, true, true, HALO>(ta, tb, td, p, sms, st);
+      return -9;
+    } else {
+      if (bn == 32) return launch<E, 32, false, false, true, true, HALO>(ta, tb, td, p, sms, st);
+      if (bn == 64) return launch<E, 64, false, false, true, true, HALO>(ta, tb, td, p, sms, st);
+      return launch<E, 128, false, false, true, true, HALO>(ta, tb, td, p, sms, st);
+    }
+  }
+  if (stats) {
+    if (bn == 32) return launch<E, 32, false, true, false, true, HALO>(ta, tb, td, p, sms, st);
+    if (bn == 64) return launch<E, 64, false, true, false, true, HALO>(ta, tb, td, p, sms, st);
+    if (bn == 128) return launch<E, 128, false, true, false, true, HALO>(ta, tb, td, p, sms, st);
+    if constexpr (EB == 2 && !HALO) return launch<E, 256, false, true, false, true, HALO>(ta, tb, td, p, sms, st);
+    return -9;
+  }
+  if (bn == 32) return launch<E, 32, false, false, false, true, HALO>(ta, tb, td, p, sms, st);
+  if (bn == 64) return launch<E, 64, false, false, false, true, HALO>(ta, tb, td, p, sms, st);
+  if (bn == 128) return launch<E, 128, false, false, false, true, HALO>(ta, tb, td, p, sms, st);
+  if constexpr (EB == 2 && !HALO) return launch<E, 256, false, false, false, true, HALO>(ta, tb, td, p, sms, st);
+  return -9;
+}
+
 template <typename E>
 int conv3x3_impl(int dgrad, const void* x, long long ldx, const void* w, void* y, long long ldy, int N, int H, int W, int Ci,
                  int Co, float* stats, long long stats_ns, int sm_limit, cudaStream_t st) {
@@ -811,23 +880,30 @@ int conv3x3_impl(int dgrad, const void* x, long long ldx, const void* w, void* y
   if (stats && ((H * W) % 32)) return -4;
   const int M = N * H * W;
   const int sms = sms_for(sm_limit);
-  CUtensorMap ta, tb, td;
-  {
-    long long dims[4] = {Cin, W, H, N};
-    long long strides[4] = {1, ldx, (long long)W * ldx, (long long)H * W * ldx};
-    int box[4] = {AT, W, hb, nb};
-    int rc = make_map_nd(&ta, x, 4, dims, strides, box, EB);
-    if (rc) return rc - 10;
-  }
   int bn;
   if (!dgrad) {
     bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256));
     if (EB == 4 && bn > 128) bn = 128;
-    int rc = make_map(&tb, w, Cout, 9LL * Cin, 9LL * Cin, bn, EB);          // [Co][9*Ci], K-major
-    if (rc) return rc - 20;
   } else {
     bn = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
     if (EB == 4) bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128);
+  }
+  // halo flavour: tiles made of whole rows of ONE image, (hb + 2) * W <= 192 pixels, row offsets in whole swizzle groups
+  static int halo_on = -1;
+  if (halo_on < 0) { const char* e = getenv("DLB_CONV3_HALO"); halo_on = (e && atoi(e) == 0) ? 0 : 1; }
+  const bool halo = halo_on && nb == 1 && (W % 8) == 0 && (hb + 2) * W <= 192 && bn <= 128;
+  CUtensorMap ta, tb, td;
+  {
+    long long dims[4] = {Cin, W, H, N};
+    long long strides[4] = {1, ldx, (long long)W * ldx, (long long)H * W * ldx};
+    int box[4] = {AT, W, halo ? hb + 2 : hb, nb};
+    int rc = make_map_nd(&ta, x, 4, dims, strides, box, EB);
+    if (rc) return rc - 10;
+  }
+  if (!dgrad) {
+    int rc = make_map(&tb, w, Cout, 9LL * Cin, 9LL * Cin, bn, EB);          // [Co][9*Ci], K-major
+    if (rc) return rc - 20;
+  } else {
     long long dims[3] = {Ci, 9, Co};                                     // w[co][tap][ci]: {ci (n, contiguous), tap, co (k rows)}
     long long strides[3] = {1, Ci, 9LL * Ci};
     int box[3] = {AT, 1, AT};
@@ -839,29 +915,9 @@ int conv3x3_impl(int dgrad, const void* x, long long ldx, const void* w, void* y
   GemmParams p = base_params(M, Cout, 9 * Cin, y, ldy);
   p.rows_per_sample = H * W; p.stats = stats; p.stats_ns = stats_ns;
   p.conv_H = H; p.conv_W = W; p.conv_C = Cin; p.conv_kchunks = (Cin + AT - 1) / AT; p.conv_sign = dgrad ? -1 : 1;
-  if (dgrad) {
-    if constexpr (EB == 2) {
-      if (bn == 64) return launch<E, 64, false, false, true, true>(ta, tb, td, p, sms, st);
-      if (bn == 128) return launch<E, 128, false, false, true, true>(ta, tb, td, p, sms, st);
-      return launch<E, 256, false, false, true, true>(ta, tb, td, p, sms, st);
-    } else {
-      if (bn == 32) return launch<E, 32, false, false, true, true>(ta, tb, td, p, sms, st);
-      if (bn == 64) return launch<E, 64, false, false, true, true>(ta, tb, td, p, sms, st);
-      return launch<E, 128, false, false, true, true>(ta, tb, td, p, sms, st);
-    }
-  }
-  if (stats) {
-    if (bn == 32) return launch<E, 32, false, true, false, true>(ta, tb, td, p, sms, st);
-    if (bn == 64) return launch<E, 64, false, true, false, true>(ta, tb, td, p, sms, st);
-    if (bn == 128) return launch<E, 128, false, true, false, true>(ta, tb, td, p, sms, st);
-    if constexpr (EB == 2) return launch<E, 256, false, true, false, true>(ta, tb, td, p, sms, st);
-    return -9;
-  }
-  if (bn == 32) return launch<E, 32, false, false, false, true>(ta, tb, td, p, sms, st);
-  if (bn == 64) return launch<E, 64, false, false, false, true>(ta, tb, td, p, sms, st);
-  if (bn == 128) return launch<E, 128, false, false, false, true>(ta, tb, td, p, sms, st);
-  if constexpr (EB == 2) return launch<E, 256, false, false, false, true>(ta, tb, td, p, sms, st);
-  return -9;
+  p.conv_halo_rows = halo ? (hb + 2) * W : 0;
+  if (halo) return conv3x3_launch<E, true>(dgrad, stats != nullptr, bn, ta, tb, td, p, sms, st);
+  return conv3x3_launch<E, false>(dgrad, stats != nullptr, bn, ta, tb, td, p, sms, st);
 }
 
 }  // namespace

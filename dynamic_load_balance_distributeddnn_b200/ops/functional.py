@@ -21,6 +21,10 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     """2-D convolution.  bf16/fp32; dispatches to the tcgen05 implicit-GEMM kernel when the shape is
     supported (``ops/conv.py``), else to the vendor library through ATen."""
     from . import conv as _conv
+    if x.is_cuda and bias is None and weight.shape[1] <= 4:
+        from . import stem as _stem
+        if _stem.supported(x, weight, stride, padding, groups):
+            return _stem.conv2d(x, weight)                  # RGB stem: direct SIMT kernel (K = 27 is below any tensor-core tile)
     if x.is_cuda and _conv.tc_supported(x, weight, stride, padding, groups):
         return _conv.conv2d_tc(x, weight, bias, stride, padding)
     if bias is not None and bias.dtype != x.dtype:

@@ -146,11 +146,24 @@ def conv3x3_geometry_ok(h: int, w: int) -> bool:
     return (h % rows == 0) if rows <= h else (rows % h == 0)
 
 
+HALO = os.environ.get("DLB_CONV3_HALO", "1") == "1"
+
+
+def conv3x3_halo_ok(h: int, w: int) -> bool:
+    """shapes the halo flavour of the 3x3 kernel takes (csrc/gemm_tc.cu, HALO): 128-pixel tiles made of whole rows of ONE image,
+    (rows + 2) * W <= 192 pixels per stage, row offsets in whole 1024-byte swizzle groups -- i.e. 16x16 and 32x32 maps"""
+    if not HALO or w <= 0 or 128 % w or w % 8:
+        return False
+    rows = 128 // w
+    return rows <= h and h % rows == 0 and (rows + 2) * w <= 192
+
+
 def conv3x3_profitable(h: int, w: int) -> bool:
     """Measured on B200 (tools/bench_gemm.py, 128->32 channels): the tap-by-tap implicit GEMM re-reads its input tile
-    nine times from L2, which the vendor kernel avoids; it wins or ties at 8x8 / 4x4 feature maps and loses 1.3-1.9x
-    at 16x16 / 32x32.  Dispatch accordingly (override with DLB_TC_CONV3_MAX_HW)."""
-    return conv3x3_geometry_ok(h, w) and h * w <= CONV3_MAX_HW
+    nine times from L2; it wins or ties against the vendor kernel at 8x8 / 4x4 feature maps and lost 1.3-1.9x at
+    16x16 / 32x32 -- those maps take the halo flavour instead (input rows loaded once per horizontal tap: 3 L2->SM passes
+    instead of 9).  Anything else above DLB_TC_CONV3_MAX_HW pixels goes to the vendor library."""
+    return conv3x3_geometry_ok(h, w) and (h * w <= CONV3_MAX_HW or conv3x3_halo_ok(h, w))
 
 
 def conv3x3_raw(dgrad: bool, x_ptr: int, ldx: int, w_ptr: int, y_ptr: int, ldy: int, n: int, h: int, w: int, ci: int, co: int,

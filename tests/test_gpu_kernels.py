@@ -388,3 +388,24 @@ def test_fused_squeeze_excite(nat, dtype, tol, n, c, cs, hw):
     assert (out.float() - ref).abs().max().item() < tol * ref.abs().max().item()
     for a, r in zip((x, w1, b1, w2, b2), ps):
         assert (a.grad.float() - r.grad).abs().max().item() < 3 * tol * max(1e-3, r.grad.abs().max().item()), a.shape
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("n,co,hw", [(16, 64, 32), (5, 32, 28), (3, 128, 8)])
+def test_stem_conv_kernel(nat, dtype, tol, n, co, hw):
+    """RGB stem 3x3 convolution (direct SIMT kernel) forward + weight gradient vs F.conv2d in true fp32"""
+    from dynamic_load_balance_distributeddnn_b200 import ops
+    from dynamic_load_balance_distributeddnn_b200.ops import stem
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(n + co)
+    x = _cl(torch.randn(n, 3, hw, hw, device="cuda")).to(dtype)
+    w = _cl(torch.randn(co, 3, 3, 3, device="cuda") / 5).to(dtype).requires_grad_(True)
+    assert stem.supported(x, w, 1, 1, 1)
+    y = ops.conv2d(x, w, None, 1, 1)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    wr = w.detach().float().requires_grad_(True)
+    yr = F.conv2d(x.float(), wr, padding=1)
+    yr.backward(gy.float())
+    assert (y.float() - yr).abs().max().item() < tol * max(1.0, yr.abs().max().item())
+    assert (w.grad.float() - wr.grad).abs().max().item() < 2 * tol * max(1.0, wr.grad.abs().max().item())
