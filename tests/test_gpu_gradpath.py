@@ -134,3 +134,41 @@ def test_tf32_training_decreases_loss_like_bf16(nat, tmp_path):
     for dtype, (first, last) in finals.items():
         assert last < 0.8 * first, (dtype, first, last)
     assert abs(finals["tf32"][1] - finals["bf16"][1]) < 0.25 * finals["tf32"][0], finals
+
+
+@pytest.mark.parametrize("model,ref_mod,ref_cls,dtype,tol", [
+    ("resnet18", "Resnet", "ResNet18", "bf16", 0.15), ("resnet50", "Resnet", "ResNet50", "bf16", 0.15),
+    ("regnet", "RegNet", "RegNetY_400MF", "bf16", 0.2), ("resnet18", "Resnet", "ResNet18", "tf32", 3e-2),
+    ("regnet", "RegNet", "RegNetY_400MF", "tf32", 3e-2)])
+def test_family_step_matches_reference_model(nat, tmp_path, model, ref_mod, ref_cls, dtype, tol):
+    """Full optimisation step of a zoo family through the native kernels (GN fusions, tcgen05 convs, SE / stem kernels, flat
+    optimizer) vs the REFERENCE's own class (stock torch.nn, true fp32) on the same weights: loss + relative L2 of the update."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "baseline", "_ref", "Net", ref_mod + ".py")
+    if not os.path.isfile(path):
+        pytest.skip("baseline/_ref not installed")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    t = _trainer(tmp_path, model + dtype, dtype=dtype, model=model, bs=16)
+    spec = importlib.util.spec_from_file_location("_ref_" + ref_mod, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ref = getattr(mod, ref_cls)(10).cuda().float()
+    ref.load_state_dict({k: v.detach().float().clone() for k, v in t.model.state_dict().items()})
+    xb, yb = t.stager.stage(list(range(16)))
+    x = t._prepare_images(xb).float()
+    before = {k: v.detach().float().clone() for k, v in t.model.named_parameters()}
+    loss_ref = F.cross_entropy(ref(x.contiguous()), yb)
+    loss_ref.backward()
+    t.train_step(xb, yb)
+    t.stager.release()
+    torch.cuda.synchronize()
+    assert abs(t.loss_acc.item() - loss_ref.item()) < tol * max(1.0, loss_ref.item()), (t.loss_acc.item(), loss_ref.item())
+    num = den = 0.0
+    for (k, p), (_, pr) in zip(t.model.named_parameters(), ref.named_parameters()):
+        upd = (before[k] - p.detach().float()) / 0.05
+        num += (upd - pr.grad).pow(2).sum().item()
+        den += pr.grad.pow(2).sum().item()
+    assert math.sqrt(num / den) < 3 * tol, math.sqrt(num / den)
+    t.close()
