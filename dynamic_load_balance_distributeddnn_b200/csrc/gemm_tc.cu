@@ -42,6 +42,7 @@ struct GemmParams {
   const float* pro_b;
   long long pro_ld;   // row stride (floats) of pro_a / pro_b, a multiple of 64, zero padded
   int rows_per_sample;
+  int pro_tma;        // coefficient tiles are staged by TMA with the operands (<= 8 samples per 128-row tile)
   // EPI_STATS: table fp32 [num_samples][table_ns] holding (sum, sumsq) pairs per output channel
   float* stats;
   long long stats_ns;
@@ -57,8 +58,11 @@ struct GemmParams {
 // input rows h0-1 .. h0+R of the tile (R+2 image rows, loaded ONCE) and the weights of the three vertical taps; the three
 // A operands of a stage are the same shared-memory tile at row offsets 0, W, 2W (whole 1024-byte swizzle groups), so the
 // activations cross L2->SM three times per tile instead of nine.
-template <typename E, int BN, bool HALO = false> struct Cfg {
+template <typename E, int BN, bool HALO = false, bool PRO = false> struct Cfg {
   static constexpr int kEB = Elt<E>::kBytes;
+  // PRO: per stage, the GroupNorm coefficients a[.], b[.] of the (up to 8) samples the tile touches for this k-block, fetched
+  // by TMA with the operands: 2 arrays x 8 samples x BK floats
+  static constexpr int kCoefStage = PRO ? 2 * 8 * Elt<E>::kAtom * 4 : 0;
   static constexpr int kABytes = (HALO ? 192 : BM) * 128;          // 128 rows (or up to 192 halo rows) x one 128-byte swizzle row of K
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + (HALO ? 3 : 1) * kBBytes;
@@ -68,9 +72,10 @@ template <typename E, int BN, bool HALO = false> struct Cfg {
   static constexpr int kBoxes = (BN * kEB + 127) / 128;
   static constexpr int kEpiBytes = kNumEpiWarps * kBoxes * 4096;
   static constexpr int kStagesWanted = BN >= 256 ? 3 : (BN >= 128 ? 5 : 6);
-  static constexpr int kStagesFit = (227 * 1024 - kEpiBytes - 1024 - 256) / kStageBytes;
+  static constexpr int kStagesFit = (227 * 1024 - kEpiBytes - 1024 - 256) / (kStageBytes + kCoefStage);
   static constexpr int kStages = kStagesWanted < kStagesFit ? kStagesWanted : kStagesFit;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kCoefBytes = kStages * kCoefStage;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kCoefBytes + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(kStages >= 2, "tile does not fit");
 };
 
@@ -84,9 +89,10 @@ template <typename E, int BN, bool HALO = false> struct Cfg {
 template <typename E, int BN, bool PRO_GN, bool EPI_STATS, bool B_MN = false, bool CONV3 = false, bool HALO = false>
 __global__ void __launch_bounds__(PRO_GN ? 512 : 256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_ca,
+               const __grid_constant__ CUtensorMap tmap_cb, const GemmParams p) {
   static_assert(!HALO || CONV3, "HALO is a flavour of the 3x3 implicit GEMM");
-  using C = Cfg<E, BN, HALO>;
+  using C = Cfg<E, BN, HALO, PRO_GN>;
   using EL = Elt<E>;
   constexpr int BK = EL::kAtom;
   constexpr int UMMA_K = EL::kUmmaK;
@@ -95,7 +101,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* epi_base = smem + C::kStages * C::kStageBytes;                  // 1024-byte aligned (stage sizes are)
-  uint8_t* bar_base = epi_base + C::kEpiBytes;
+  uint8_t* coef_base = epi_base + C::kEpiBytes;                           // PRO_GN: [stage][a | b][8 samples][BK] fp32
+  uint8_t* bar_base = coef_base + C::kCoefBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);              // TMA bytes landed
   uint64_t* empty_bar = full_bar + C::kStages;                             // MMA done reading the stage
   uint64_t* ready_bar = empty_bar + C::kStages;                            // PRO_GN: transform done
@@ -112,6 +119,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_d) : "memory");
+    if constexpr (PRO_GN) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_ca) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_cb) : "memory");
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -180,7 +191,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               tma_load_2d(sb, &tmap_b, fb, tap * p.conv_C + kc * BK, n0);
             }
           } else {
-            mbar_expect_tx(fb, C::kStageBytes);
+            mbar_expect_tx(fb, C::kStageBytes + ((PRO_GN && p.pro_tma) ? C::kCoefStage : 0));
+            if constexpr (PRO_GN) {
+              if (p.pro_tma) {
+                // coefficient rows of the samples this tile touches, columns of this k-block (rows past the last sample: zeros)
+                const uint32_t cd = smem_u32(coef_base + stage * C::kCoefStage);
+                const int s_first = m0 / p.rows_per_sample;
+                tma_load_2d(cd, &tmap_ca, fb, kb * BK, s_first);
+                tma_load_2d(cd + C::kCoefStage / 2, &tmap_cb, fb, kb * BK, s_first);
+              }
+            }
             tma_load_2d(sa, &tmap_a, fb, kb * BK, m0);
             if constexpr (B_MN) {
 #pragma unroll
@@ -375,7 +395,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 8; ++i) { ca[i] = 0.f; cb[i] = 0.f; }
         const long long coff = (long long)kb * BK + cc * EL::kPer16;
-        if (uniform) load_coef<E>(p.pro_a + (long long)s_first * p.pro_ld + coff, p.pro_b + (long long)s_first * p.pro_ld + coff, ca, cb);
+        // coefficients: staged in shared memory by TMA together with the operands (p.pro_tma) -- a global/L2 load here sits on
+        // the critical path of EVERY k-block (ncu r2_03: long-scoreboard stalls dominate, DRAM 10 %, tensor pipe 6 %)
+        const uint32_t cs = smem_u32(coef_base + stage * C::kCoefStage) + (uint32_t)(cc * 16 * (EL::kPer16 / 4));
+        auto coef_from_smem = [&](int local) {
+          const uint32_t pa = cs + (uint32_t)(local * BK * 4), pb = pa + C::kCoefStage / 2;
+          const uint4 a0 = lds128(pa), b0 = lds128(pb);
+          ca[0] = __uint_as_float(a0.x); ca[1] = __uint_as_float(a0.y); ca[2] = __uint_as_float(a0.z); ca[3] = __uint_as_float(a0.w);
+          cb[0] = __uint_as_float(b0.x); cb[1] = __uint_as_float(b0.y); cb[2] = __uint_as_float(b0.z); cb[3] = __uint_as_float(b0.w);
+          if constexpr (sizeof(E) == 2) {
+            const uint4 a1 = lds128(pa + 16), b1 = lds128(pb + 16);
+            ca[4] = __uint_as_float(a1.x); ca[5] = __uint_as_float(a1.y); ca[6] = __uint_as_float(a1.z); ca[7] = __uint_as_float(a1.w);
+            cb[4] = __uint_as_float(b1.x); cb[5] = __uint_as_float(b1.y); cb[6] = __uint_as_float(b1.z); cb[7] = __uint_as_float(b1.w);
+          }
+        };
+        if (uniform) {
+          if (p.pro_tma) coef_from_smem(0);
+          else load_coef<E>(p.pro_a + (long long)s_first * p.pro_ld + coff, p.pro_b + (long long)s_first * p.pro_ld + coff, ca, cb);
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = r_base + 32 * i;
@@ -384,7 +421,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int sample = uniform ? s_first : min(grow, p.M - 1) / p.rows_per_sample;
           if (!uniform && sample != cur) {
             // coefficient rows are padded to a multiple of 64 and zero-filled by the host (a = b = 0 beyond K)
-            load_coef<E>(p.pro_a + (long long)sample * p.pro_ld + coff, p.pro_b + (long long)sample * p.pro_ld + coff, ca, cb);
+            if (p.pro_tma) coef_from_smem(sample - s_first);
+            else load_coef<E>(p.pro_a + (long long)sample * p.pro_ld + coff, p.pro_b + (long long)sample * p.pro_ld + coff, ca, cb);
             cur = sample;
           }
           affine_relu_chunk<E>(raw[i], ca, cb);
@@ -663,8 +701,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
 }
 
 template <typename E, int BN, bool PRO, bool STATS, bool BMN = false, bool CONV3 = false, bool HALO = false>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p, int sms, cudaStream_t st) {
-  using C = Cfg<E, BN, HALO>;
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p, int sms, cudaStream_t st,
+           const CUtensorMap* tca = nullptr, const CUtensorMap* tcb = nullptr) {
+  using C = Cfg<E, BN, HALO, PRO>;
   auto kern = gemm_tc_kernel<E, BN, PRO, STATS, BMN, CONV3, HALO>;
   static bool configured = false;
   if (!configured) {
@@ -674,18 +713,18 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
   }
   const int num_tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   const int grid = num_tiles < sms ? num_tiles : sms;
-  dlb_launch(kern, dim3(grid), dim3(PRO ? 512 : 256), (size_t)C::kSmemBytes, st, ta, tb, td, p);
+  dlb_launch(kern, dim3(grid), dim3(PRO ? 512 : 256), (size_t)C::kSmemBytes, st, ta, tb, td, tca ? *tca : ta, tcb ? *tcb : ta, p);
   return dlb_post_launch();
 }
 
 template <typename E, int BN>
 int dispatch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p, bool pro, bool stats, int sms, cudaStream_t st,
-             bool b_mn = false) {
+             bool b_mn = false, const CUtensorMap* tca = nullptr, const CUtensorMap* tcb = nullptr) {
   if constexpr (BN * Elt<E>::kBytes >= 128) {
     if (b_mn) return launch<E, BN, false, false, true>(ta, tb, td, p, sms, st);
   }
-  if (pro && stats) return launch<E, BN, true, true>(ta, tb, td, p, sms, st);
-  if (pro) return launch<E, BN, true, false>(ta, tb, td, p, sms, st);
+  if (pro && stats) return launch<E, BN, true, true>(ta, tb, td, p, sms, st, tca, tcb);
+  if (pro) return launch<E, BN, true, false>(ta, tb, td, p, sms, st, tca, tcb);
   if (stats) return launch<E, BN, false, true>(ta, tb, td, p, sms, st);
   return launch<E, BN, false, false>(ta, tb, td, p, sms, st);
 }
@@ -707,7 +746,7 @@ inline int sms_for(int sm_limit) {
 inline GemmParams base_params(int M, int N, int K, void* d, long long ldd) {
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.d = d; p.ldd = ldd; p.accumulate_out = 0;
-  p.pro_a = nullptr; p.pro_b = nullptr; p.pro_ld = 0; p.rows_per_sample = M; p.stats = nullptr; p.stats_ns = 0;
+  p.pro_a = nullptr; p.pro_b = nullptr; p.pro_ld = 0; p.rows_per_sample = M; p.pro_tma = 0; p.stats = nullptr; p.stats_ns = 0;
   p.conv_H = p.conv_W = p.conv_C = 0; p.conv_kchunks = 1; p.conv_sign = 1; p.conv_halo_rows = 0;
   return p;
 }
@@ -765,12 +804,28 @@ int gemm_impl(const void* a, long long lda, const void* b, long long ldb, void* 
   p.pro_a = pro_a; p.pro_b = pro_b; p.pro_ld = pro_ld; p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : M;
   p.stats = stats; p.stats_ns = stats_ns;
   const bool pro = pro_a != nullptr, sts = stats != nullptr;
+  CUtensorMap tca, tcb;
+  if (pro) {
+    // coefficient tiles [<= 8 samples][BK] ride the operand pipeline when a 128-row tile touches at most 8 samples
+    static int tma_on = -1;
+    if (tma_on < 0) { const char* e = getenv("DLB_PRO_TMA"); tma_on = (e && atoi(e) == 0) ? 0 : 1; }
+    const int rps = p.rows_per_sample;
+    const long long nsamp = ((long long)M + rps - 1) / rps;
+    const int per_tile = (rps >= BM) ? ((BM % rps == 0 || rps % BM == 0) ? 1 : 2) : (BM + rps - 1) / rps + ((BM % rps) ? 1 : 0);
+    if (tma_on && per_tile <= 8) {
+      int r1 = make_map_f32_plain(&tca, pro_a, nsamp, pro_ld, pro_ld, Elt<E>::kAtom, 8);
+      int r2 = make_map_f32_plain(&tcb, pro_b, nsamp, pro_ld, pro_ld, Elt<E>::kAtom, 8);
+      if (r1 == 0 && r2 == 0) p.pro_tma = 1;
+    }
+  }
+  const CUtensorMap* pca = p.pro_tma ? &tca : nullptr;
+  const CUtensorMap* pcb = p.pro_tma ? &tcb : nullptr;
   switch (bn) {
-    case 32: return dispatch<E, 32>(ta, tb, td, p, pro, sts, sms, st);
-    case 64: return dispatch<E, 64>(ta, tb, td, p, pro, sts, sms, st);
-    case 128: return dispatch<E, 128>(ta, tb, td, p, pro, sts, sms, st);
+    case 32: return dispatch<E, 32>(ta, tb, td, p, pro, sts, sms, st, false, pca, pcb);
+    case 64: return dispatch<E, 64>(ta, tb, td, p, pro, sts, sms, st, false, pca, pcb);
+    case 128: return dispatch<E, 128>(ta, tb, td, p, pro, sts, sms, st, false, pca, pcb);
     default:
-      if constexpr (EB == 2) return dispatch<E, 256>(ta, tb, td, p, pro, sts, sms, st);
+      if constexpr (EB == 2) return dispatch<E, 256>(ta, tb, td, p, pro, sts, sms, st, false, pca, pcb);
       return -9;
   }
 }

@@ -324,7 +324,8 @@ gn_bwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
                     T* __restrict__ dres, int64_t lddr, const float* __restrict__ gamma,
                     const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ table, int64_t table_ns, int HW, int C, int G, int rows_per_block,
-                    const float* __restrict__ coef_a, const float* __restrict__ coef_b, int64_t coef_ld) {
+                    const float* __restrict__ coef_a, const float* __restrict__ coef_b, int64_t coef_ld,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
   dlb_pdl_wait();
   extern __shared__ float smem[];            // k1[C], k2[C], k3[C], s1[G], s2[G]
   float* k1 = smem;
@@ -334,6 +335,15 @@ gn_bwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
   float* s2 = s1 + G;
   const int n = blockIdx.y, cpg = C / G;
   const float* t = table + (int64_t)n * table_ns;
+  if (dgamma != nullptr && blockIdx.x == 0) {
+    // affine-parameter gradients from the sample's complete sums: one block per sample (N atomics per channel)
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+      const float A = t[2 * c], B = t[2 * c + 1];
+      const int g = c / cpg;
+      atomicAdd(&dbeta[c], A);
+      atomicAdd(&dgamma[c], rstd[n * G + g] * (B - mean[n * G + g] * A));
+    }
+  }
   for (int g = threadIdx.x; g < G; g += kThreads) {
     const float mu = mean[n * G + g], r = rstd[n * G + g];
     float a = 0.f, b = 0.f;
@@ -519,19 +529,12 @@ gn_bwd_fused_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
   __syncthreads();
   float* tab = table + (int64_t)n * table_ns;
   for (int i = threadIdx.x; i < 2 * C; i += kThreads) atomicAdd(&tab[i], smem[i]);
-  if (dgamma != nullptr) {
-    for (int cc = threadIdx.x; cc < C; cc += kThreads) {
-      const float A = smem[2 * cc], B = smem[2 * cc + 1];
-      const int g = cc / cpg;
-      atomicAdd(&dbeta[cc], A);
-      atomicAdd(&dgamma[cc], rstd[n * G + g] * (B - mean[n * G + g] * A));
-    }
-  }
   // ---- per-sample barrier ----
+  __shared__ unsigned s_ticket;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    atomicAdd(&done[n], 1u);
+    s_ticket = atomicAdd(&done[n], 1u);
     unsigned spins = 0;
     while (true) {
       unsigned v;
@@ -541,6 +544,17 @@ gn_bwd_fused_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
     }
   }
   __syncthreads();
+  // affine-parameter gradients: dbeta[c] += A, dgamma[c] += rstd*(B - mean*A) with the sample's COMPLETE sums, by the one block
+  // that arrived last -- N atomics per channel instead of N x chunks (every block adding its partials made these 2C addresses
+  // the bottleneck at small batches: 300+ blocks hammering ~1 000 floats; ncu r2_03: 32 us for a 20 MB problem)
+  if (dgamma != nullptr && s_ticket == gridDim.x - 1) {
+    for (int cc = threadIdx.x; cc < C; cc += kThreads) {
+      const float A = __ldcg(tab + 2 * cc), B = __ldcg(tab + 2 * cc + 1);
+      const int g = cc / cpg;
+      atomicAdd(&dbeta[cc], A);
+      atomicAdd(&dgamma[cc], rstd[n * G + g] * (B - mean[n * G + g] * A));
+    }
+  }
   // ---- phase 2 ----
   float* k1 = smem;
   float* k2 = smem + C;
@@ -702,7 +716,7 @@ int bwd_apply_launch(const void* x, int64_t ldx, const void* dy, int64_t lddy, c
                      void* dx, int64_t lddx, void* dres, int64_t lddr, const float* gamma,
                      const float* mean, const float* rstd, const float* table, int64_t table_ns, int N, int HW, int C,
                      int G, int relu, int acc, cudaStream_t st, const float* ca = nullptr, const float* cb = nullptr,
-                     int64_t cld = 0) {
+                     int64_t cld = 0, float* dgamma = nullptr, float* dbeta = nullptr) {
   dim3 grid; int rpb;
   grid_for(N, HW, C, V, grid, rpb);
   const size_t sm = (3 * C + 2 * G) * sizeof(float);
@@ -710,7 +724,7 @@ int bwd_apply_launch(const void* x, int64_t ldx, const void* dy, int64_t lddy, c
   T* DX = (T*)dx; T* DR = (T*)dres;
   const int msrc = !relu ? 0 : (ca ? 2 : 1);
   unr_init();
-#define GOU(RL, RS, AC, U) dlb_launch(gn_bwd_apply_kernel<T, V, RL, RS, AC, U>, grid, dim3(kThreads), sm, st, X, (int64_t)ldx, DY, (int64_t)lddy, Y, (int64_t)ldy, DX, (int64_t)lddx, DR, (int64_t)lddr, gamma, mean, rstd, table, (int64_t)table_ns, HW, C, G, rpb, ca, cb, (int64_t)cld)
+#define GOU(RL, RS, AC, U) dlb_launch(gn_bwd_apply_kernel<T, V, RL, RS, AC, U>, grid, dim3(kThreads), sm, st, X, (int64_t)ldx, DY, (int64_t)lddy, Y, (int64_t)ldy, DX, (int64_t)lddx, DR, (int64_t)lddr, gamma, mean, rstd, table, (int64_t)table_ns, HW, C, G, rpb, ca, cb, (int64_t)cld, dgamma, dbeta)
 #define GO(RL, RS, AC) do { if (g_unr_bwd == 4) GOU(RL, RS, AC, 4); else if (g_unr_bwd == 2) GOU(RL, RS, AC, 2); else GOU(RL, RS, AC, 1); } while (0)
 #define GO2(RL) do { if (dres) { if (acc) GO(RL, true, true); else GO(RL, true, false); } else { if (acc) GO(RL, false, true); else GO(RL, false, false); } } while (0)
   if (msrc == 0) GO2(0); else if (msrc == 1) GO2(1); else GO2(2);
@@ -919,7 +933,14 @@ DLB_API int dlb_gn_backward(int dtype, const void* x, int64_t ldx, const void* d
                             const float* gamma, const float* mean, const float* rstd, float* table,
                             float* dgamma, float* dbeta, int N, int HW, int C, int G, int relu, int acc,
                             void* stream) {
-  int rc = dlb_nc_reduce2_bwd(relu, dtype, x, ldx, dy, lddy, y, ldy, table, 0, mean, rstd, dgamma, dbeta, N, HW, C, G, stream);
+  // the per-(n, c) sums first; the affine-parameter gradients are then added by ONE block per sample of the apply kernel
+  // (they used to be added by every block of the reduce kernel: N x chunks atomics per channel)
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!g_skip_zero && dgamma) { cudaMemsetAsync(dgamma, 0, C * sizeof(float), st); cudaMemsetAsync(dbeta, 0, C * sizeof(float), st); }
+  int rc = dlb_nc_reduce2_bwd(relu, dtype, x, ldx, dy, lddy, y, ldy, table, 0, mean, rstd, nullptr, nullptr, N, HW, C, G, stream);
   if (rc) return rc;
-  return dlb_gn_bwd_apply(dtype, x, ldx, dy, lddy, y, ldy, dx, lddx, dres, lddr, gamma, mean, rstd, table, 0, N, HW, C, G, relu, acc, stream);
+  int64_t table_ns = 2 * (int64_t)C;
+  const bool vec = vec_ok(dtype, C, {ldx, lddy, relu ? ldy : 0, lddx, dres ? lddr : 0}, {x, dy, relu ? y : nullptr, dx, dres});
+  DISPATCH(dtype, vec, (rc = bwd_apply_launch<T, V>(x, ldx, dy, lddy, y, ldy, dx, lddx, dres, lddr, gamma, mean, rstd, table, table_ns, N, HW, C, G, relu, acc, st, nullptr, nullptr, 0, dgamma, dbeta)));
+  return rc;
 }

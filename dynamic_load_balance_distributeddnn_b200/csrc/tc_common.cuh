@@ -224,6 +224,22 @@ inline int make_map(CUtensorMap* map, const void* ptr, long long rows, long long
   return r == CUDA_SUCCESS ? 0 : -11;
 }
 
+// 2-D fp32 tensor map without swizzle (small side tables such as the GroupNorm coefficient rows): OOB rows/cols read as zero
+inline int make_map_f32_plain(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows) {
+  auto enc = get_encode();
+  if (!enc) return -10;
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(0); ctx_bound = true; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -11;
+}
+
 // general rank-n bf16 tensor map (dims/strides innermost first; strides in elements for dims 1..n-1)
 inline int make_map_nd(CUtensorMap* map, const void* ptr, int rank, const long long* dims, const long long* strides, const int* box,
                        int esize = 2, bool atom32 = false) {
