@@ -180,6 +180,6 @@ def test_dense_stage_tf32_matches_fp32_torch(g):
     def rel_l2(a, b):
         return ((a - b).pow(2).sum().sqrt() / b.pow(2).sum().sqrt().clamp_min(1e-12)).item()
     assert (out - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
-    assert rel_l2(gx, x.grad) < 3e-2, rel_l2(gx, x.grad)
+    assert rel_l2(gx, x.grad) < 5e-2, rel_l2(gx, x.grad)
     for a, p in zip(got, stage.parameters()):
-        assert rel_l2(a, p.grad) < 3e-2, (p.shape, rel_l2(a, p.grad))
+        assert rel_l2(a, p.grad) < 5e-2, (p.shape, rel_l2(a, p.grad))

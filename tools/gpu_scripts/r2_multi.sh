@@ -12,10 +12,9 @@ cp gpurun_out/allreduce_sweep_n$N.json $O/ 2>/dev/null
 echo "== bench reference";  timeout 900 $TR --master-port 29802 bench.py --impl reference --gpus $N --steps 20 --warmup 5 2> $O/ref.err | tee $O/ref.json | cut -c1-400
 echo "== bench ours (default)"; timeout 600 $TR --master-port 29803 bench.py --gpus $N --steps 20 --warmup 5 2> $O/ours.err | tee $O/ours.json | cut -c1-500
 if [ -z "$QUICK" ]; then
-echo "== bench ours --dbs-model affine"; timeout 600 $TR --master-port 29804 bench.py --gpus $N --steps 20 --warmup 5 --dbs-model affine --dbs-rounds 3 2> $O/ours_affine.err | tee $O/ours_affine.json | cut -c1-500
-echo "== bench ours --dbs-model proportional"; timeout 600 $TR --master-port 29805 bench.py --gpus $N --steps 20 --warmup 5 --dbs-model proportional 2> $O/ours_prop.err | tee $O/ours_prop.json | cut -c1-500
-echo "== bench ours --no-dbs"; timeout 600 $TR --master-port 29806 bench.py --gpus $N --steps 20 --warmup 5 --no-dbs 2> $O/ours_nodbs.err | tee $O/ours_nodbs.json | cut -c1-500
-echo "== bench ours tf32"; timeout 600 $TR --master-port 29807 bench.py --gpus $N --steps 20 --warmup 5 --dtype tf32 2> $O/ours_tf32.err | tee $O/ours_tf32.json | cut -c1-500
+echo "== bench ours --dbs-model affine (3 rounds)"; timeout 600 $TR --master-port 29804 bench.py --gpus $N --steps 20 --warmup 5 --dbs-model affine --dbs-rounds 3 --alt-dtype "" 2> $O/ours_affine.err | tee $O/ours_affine.json | cut -c1-500
+echo "== bench ours --dbs-model proportional (3 rounds)"; timeout 600 $TR --master-port 29805 bench.py --gpus $N --steps 20 --warmup 5 --dbs-model proportional --dbs-rounds 3 --alt-dtype "" 2> $O/ours_prop3.err | tee $O/ours_prop3.json | cut -c1-500
+echo "== bench ours --no-dbs"; timeout 600 $TR --master-port 29806 bench.py --gpus $N --steps 20 --warmup 5 --no-dbs --alt-dtype "" 2> $O/ours_nodbs.err | tee $O/ours_nodbs.json | cut -c1-500
 fi
 if [ "$N" = "8" ]; then
   echo "== config #3: ResNet-50, B=1024, uniform ranks (DBS must stay at the equal split)"
