@@ -140,6 +140,24 @@ def test_dense_block_backward_with_fused_dgrad(g):
         g.FUSED_DGRAD = False
     (dx0, g0), (dx1, g1) = outs
     assert float((dx0 - dx1).abs().max()) < 4e-2 * max(1.0, float(dx0.abs().max()))
-    for i, (a, b) in enumerate(zip(g0, g1)):
-        err, ref = float((a - b).abs().max()), float(a.abs().max())
-        assert err < 4e-2 * max(1.0, ref), (i, tuple(a.shape), err, ref)
+    # parameter gradients: both paths against a plain fp32 torch evaluation of the same stage on the same (bf16-valued) weights.
+    # The two paths differ by the bf16 rounding of dA (the chain writes it, the fused kernel keeps it in fp32 in TMEM), which a
+    # max-norm comparison of 2 000-term sums with cancellation mistakes for an error: the fused path must simply not be
+    # further from the fp32 truth than the chain is.
+    import torch.nn.functional as F
+    xr = x0.float().clone().requires_grad_(True)
+    ps = [p.detach().float().clone().requires_grad_(True) for p in stage.parameters()]
+    ref = xr
+    for i in range(len(ps) // 6):
+        g1w, g1b, w1, g2w, g2b, w2 = ps[6 * i:6 * i + 6]
+        y = F.conv2d(F.relu(F.group_norm(ref, 32, g1w, g1b)), w1)
+        z = F.conv2d(F.relu(F.group_norm(y, 32, g2w, g2b)), w2, padding=1)
+        ref = torch.cat([z, ref], 1)
+    torch.backends.cudnn.allow_tf32 = False
+    ref.backward(gy.float())
+
+    def rel_l2(a, b):
+        return float((a - b).pow(2).sum().sqrt() / b.pow(2).sum().sqrt().clamp_min(1e-12))
+    for i, (a, b, r) in enumerate(zip(g0, g1, ps)):
+        e_chain, e_fused = rel_l2(a, r.grad), rel_l2(b, r.grad)
+        assert e_fused < max(1.5 * e_chain, 2e-2), (i, tuple(a.shape), e_chain, e_fused)
