@@ -456,7 +456,9 @@ gn_bwd_apply_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
 //            launched back to back and are all resident long before the first one gets here; watchdog instead of a hang)
 //   phase 2: dx (+)= k1*dz + k2*x + k3 over the same rows -- x and dy were read a few microseconds ago by this very block
 // Saves a kernel launch per GroupNorm backward (two per DenseNet layer) and turns the second pass into cache hits.
-template <typename T, int V, bool ACC>
+// STAGE: the block's rows of x and dy stay in shared memory between the two phases (16-byte vectors, [row][C]); phase 2 then
+// reads nothing but dX from global memory -- 4 instead of 6 passes over |x| once the working set no longer fits L2.
+template <typename T, int V, bool ACC, bool STAGE>
 __global__ void __launch_bounds__(kThreads)
 gn_bwd_fused_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy, T* __restrict__ dx, int64_t lddx,
                     const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -473,6 +475,9 @@ gn_bwd_fused_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
   const int c = lane * V;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(HW, r0 + rows_per_block);
+  // staging area behind the coefficient arrays: x rows, then dy rows, C * sizeof(T) bytes each
+  uint8_t* stage_x = reinterpret_cast<uint8_t*>(smem) + (((3 * C + 2 * G) * 4 + 15) & ~15);
+  uint8_t* stage_g = stage_x + (size_t)rows_per_block * C * sizeof(T);
   for (int i = threadIdx.x; i < 2 * C; i += kThreads) smem[i] = 0.f;
   float ka[V], kb[V];
 #pragma unroll
@@ -491,8 +496,18 @@ gn_bwd_fused_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
         const int r = rb + u * row_lanes;
         if (r < r1) {
           const int64_t row = (int64_t)n * HW + r;
-          load_vec<T, V>(x + row * ldx + c, xv[u]);
-          load_vec<T, V>(dy + row * lddy + c, gv[u]);
+          if constexpr (STAGE) {
+            const uint4 xr = *reinterpret_cast<const uint4*>(x + row * ldx + c);
+            const uint4 gr = *reinterpret_cast<const uint4*>(dy + row * lddy + c);
+            const size_t so = ((size_t)(r - r0) * C + c) * sizeof(T);
+            *reinterpret_cast<uint4*>(stage_x + so) = xr;
+            *reinterpret_cast<uint4*>(stage_g + so) = gr;
+            load_vec<T, V>(reinterpret_cast<const T*>(&xr), xv[u]);
+            load_vec<T, V>(reinterpret_cast<const T*>(&gr), gv[u]);
+          } else {
+            load_vec<T, V>(x + row * ldx + c, xv[u]);
+            load_vec<T, V>(dy + row * lddy + c, gv[u]);
+          }
         }
       }
 #pragma unroll
@@ -596,8 +611,14 @@ gn_bwd_fused_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
       const int r = rb + u * row_lanes;
       if (r < r1) {
         const int64_t row = (int64_t)n * HW + r;
-        load_vec<T, V>(x + row * ldx + c, xv[u]);
-        load_vec<T, V>(dy + row * lddy + c, gv[u]);
+        if constexpr (STAGE) {
+          const size_t so = ((size_t)(r - r0) * C + c) * sizeof(T);
+          load_vec<T, V>(reinterpret_cast<const T*>(stage_x + so), xv[u]);
+          load_vec<T, V>(reinterpret_cast<const T*>(stage_g + so), gv[u]);
+        } else {
+          load_vec<T, V>(x + row * ldx + c, xv[u]);
+          load_vec<T, V>(dy + row * lddy + c, gv[u]);
+        }
         if constexpr (ACC) load_vec<T, V>(dx + row * lddx + c, old[u]);
       }
     }
@@ -832,10 +853,34 @@ DLB_API int dlb_gn_bwd_fused(int dtype, const void* x, int64_t ldx, const void* 
   if (!vec_ok(dtype, C, {ldx, lddy, lddx}, {x, dy, dx}) || C / V > kThreads || C > 6000 || (C % G)) return 1;
   dim3 grid; int rpb;
   grid_for(N, HW, C, V, grid, rpb);
+  // staged flavour: once x + dy of the whole problem no longer fit comfortably in L2 (126 MB), keep each block's rows in
+  // shared memory between the phases (<= 96 KB per block -> two blocks per SM)
+  static int stage_on = -1;
+  if (stage_on < 0) { const char* e = getenv("DLB_GN_BWD_STAGE"); stage_on = (e && atoi(e) == 0) ? 0 : 1; }
+  const size_t esz = dtype == DLB_BF16 ? 2 : 4;
+  const size_t row_pair = 2 * (size_t)C * esz;
+  const bool stage = stage_on && (size_t)N * HW * row_pair > (size_t)96 * 1024 * 1024 && row_pair * 8 <= 96 * 1024;
+  if (stage) {
+    int max_rows = (int)((96 * 1024) / row_pair);
+    if (rpb > max_rows) rpb = max_rows;
+    const int chunks = (HW + rpb - 1) / rpb;
+    rpb = (HW + chunks - 1) / chunks;
+    grid = dim3(chunks, N, 1);
+  }
   if (grid.x > 64) return 1;                 // keep a sample's blocks trivially co-resident
-  const size_t sm = (size_t)(3 * C + 2 * G) * sizeof(float);
+  const size_t coef_bytes = (((size_t)(3 * C + 2 * G) * sizeof(float)) + 15) & ~(size_t)15;
+  const size_t sm = coef_bytes + (stage ? (size_t)rpb * row_pair : 0);
   cudaStream_t st = (cudaStream_t)stream;
-#define FGO(TT, VV, AC) dlb_launch(gn_bwd_fused_kernel<TT, VV, AC>, grid, dim3(kThreads), sm, st, (const TT*)x, (int64_t)ldx, (const TT*)dy, (int64_t)lddy, (TT*)dx, (int64_t)lddx, gamma, mean, rstd, table, (int64_t)table_ns, dgamma, dbeta, ca, cb, (int64_t)cld, (unsigned*)done, HW, C, G, rpb)
+#define FGO(TT, VV, AC)                                                                                                          \
+  do {                                                                                                                           \
+    if (stage) {                                                                                                                 \
+      static bool cfgd = false;                                                                                                  \
+      if (!cfgd) { cudaFuncSetAttribute(gn_bwd_fused_kernel<TT, VV, AC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024); cfgd = true; } \
+      dlb_launch(gn_bwd_fused_kernel<TT, VV, AC, true>, grid, dim3(kThreads), sm, st, (const TT*)x, (int64_t)ldx, (const TT*)dy, (int64_t)lddy, (TT*)dx, (int64_t)lddx, gamma, mean, rstd, table, (int64_t)table_ns, dgamma, dbeta, ca, cb, (int64_t)cld, (unsigned*)done, HW, C, G, rpb); \
+    } else {                                                                                                                     \
+      dlb_launch(gn_bwd_fused_kernel<TT, VV, AC, false>, grid, dim3(kThreads), sm, st, (const TT*)x, (int64_t)ldx, (const TT*)dy, (int64_t)lddy, (TT*)dx, (int64_t)lddx, gamma, mean, rstd, table, (int64_t)table_ns, dgamma, dbeta, ca, cb, (int64_t)cld, (unsigned*)done, HW, C, G, rpb); \
+    }                                                                                                                            \
+  } while (0)
   if (dtype == DLB_BF16) { if (acc) FGO(__nv_bfloat16, 8, true); else FGO(__nv_bfloat16, 8, false); }
   else { if (acc) FGO(float, 4, true); else FGO(float, 4, false); }
 #undef FGO
