@@ -119,3 +119,107 @@ DLB_API int dlb_copy2d(const void* src, int64_t lds_bytes, void* dst, int64_t ld
   else dlb_launch(copy2d_kernel<1>, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, (const unsigned char*)src, (int64_t)lds_bytes, (unsigned char*)dst, (int64_t)ldd_bytes, (int64_t)rows, row_bytes);
   return dlb_post_launch();
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// Max pooling, NHWC, k x k window, stride s, padding p (GoogLeNet's 3x3/s1/p1 and 3x3/s2/p1 pools, MnistNet's 2x2;
+// reference Net/GoogleNet.py:42,68,79, Net/MnistNet.py:21-22).  The forward stores the winning tap of every
+// output element (one byte); the backward GATHERS: an input element sums the dy of the <= ceil(k/s)^2 windows that chose it,
+// so no atomics are needed even for overlapping windows.
+namespace {
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, unsigned char* __restrict__ idx,
+                                                          int N, int H, int W, int C, int Ho, int Wo, int k, int s, int p) {
+  dlb_pdl_wait();
+  const int lanes = C / V;
+  const int64_t total = (int64_t)N * Ho * Wo * lanes;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % lanes) * V;
+    int64_t r = i / lanes;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    float best[V]; unsigned char bi[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+    for (int dy = 0; dy < k; ++dy) {
+      const int h = ho * s - p + dy;
+      if (h < 0 || h >= H) continue;
+      for (int dx = 0; dx < k; ++dx) {
+        const int w = wo * s - p + dx;
+        if (w < 0 || w >= W) continue;
+        float v[V];
+        load_vec<T, V>(x + (((int64_t)n * H + h) * W + w) * C + c, v);
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+          if (v[j] > best[j]) { best[j] = v[j]; bi[j] = (unsigned char)(dy * k + dx); }
+      }
+    }
+    const int64_t o = (((int64_t)n * Ho + ho) * Wo + wo) * C + c;
+    store_vec<T, V>(y + o, best);
+#pragma unroll
+    for (int j = 0; j < V; ++j) idx[o + j] = bi[j];
+  }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ dy, const unsigned char* __restrict__ idx, T* __restrict__ dx,
+                                                          int N, int H, int W, int C, int Ho, int Wo, int k, int s, int p) {
+  dlb_pdl_wait();
+  const int lanes = C / V;
+  const int64_t total = (int64_t)N * H * W * lanes;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % lanes) * V;
+    int64_t r = i / lanes;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const int n = (int)(r / H);
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+    // windows (ho, wo) with ho*s - p <= h < ho*s - p + k
+    const int ho0 = max(0, (h + p - k + s) / s), ho1 = min(Ho - 1, (h + p) / s);
+    const int wo0 = max(0, (w + p - k + s) / s), wo1 = min(Wo - 1, (w + p) / s);
+    for (int ho = ho0; ho <= ho1; ++ho)
+      for (int wo = wo0; wo <= wo1; ++wo) {
+        const int tap = (h - (ho * s - p)) * k + (w - (wo * s - p));
+        const int64_t o = (((int64_t)n * Ho + ho) * Wo + wo) * C + c;
+        float g[V];
+        load_vec<T, V>(dy + o, g);
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] += (idx[o + j] == tap) ? g[j] : 0.f;
+      }
+    store_vec<T, V>(dx + (((int64_t)n * H + h) * W + w) * C + c, acc);
+  }
+}
+
+template <typename T, int V>
+int launch_max(bool fwd, const void* a, void* b, unsigned char* idx, int N, int H, int W, int C, int Ho, int Wo, int k, int s, int p,
+               cudaStream_t st) {
+  const int64_t total = fwd ? (int64_t)N * Ho * Wo * (C / V) : (int64_t)N * H * W * (C / V);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (blocks < 1) return 0;
+  if (fwd) dlb_launch(maxpool_fwd_kernel<T, V>, dim3((int)blocks), dim3(256), 0, st, (const T*)a, (T*)b, idx, N, H, W, C, Ho, Wo, k, s, p);
+  else dlb_launch(maxpool_bwd_kernel<T, V>, dim3((int)blocks), dim3(256), 0, st, (const T*)a, (const unsigned char*)idx, (T*)b, N, H, W, C, Ho, Wo, k, s, p);
+  return dlb_post_launch();
+}
+
+}  // namespace
+
+// direction 0: in = x [N,H,W,C], out = y [N,Ho,Wo,C], idx written;  direction 1: in = dy [N,Ho,Wo,C], out = dx [N,H,W,C], idx read.
+DLB_API int dlb_maxpool_nhwc(int direction, int dtype, const void* in, void* out, void* idx, int N, int H, int W, int C, int k, int s, int p,
+                             void* stream) {
+  if (k < 1 || k > 15 || s < 1 || p < 0 || 2 * p > k) return -2;
+  const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool fwd = direction == 0;
+  const bool aligned = (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
+  if (dtype == DLB_BF16) {
+    if (C % 8 == 0 && aligned) return launch_max<__nv_bfloat16, 8>(fwd, in, out, (unsigned char*)idx, N, H, W, C, Ho, Wo, k, s, p, st);
+    return launch_max<__nv_bfloat16, 1>(fwd, in, out, (unsigned char*)idx, N, H, W, C, Ho, Wo, k, s, p, st);
+  }
+  if (C % 4 == 0 && aligned) return launch_max<float, 4>(fwd, in, out, (unsigned char*)idx, N, H, W, C, Ho, Wo, k, s, p, st);
+  return launch_max<float, 1>(fwd, in, out, (unsigned char*)idx, N, H, W, C, Ho, Wo, k, s, p, st);
+}

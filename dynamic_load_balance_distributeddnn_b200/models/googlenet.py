@@ -9,7 +9,8 @@ the intended conv→GN→ReLU.
 import torch
 import torch.nn as nn
 
-from .layers import Conv2d, GroupNormAct, Linear
+from .layers import Conv2d, GroupNormAct, Linear, MaxPool2d
+from .. import ops
 
 
 def _unit(cin, cout, k, groups):
@@ -24,7 +25,7 @@ class Inception(nn.Module):
         self.b2 = nn.Sequential(*_unit(in_planes, n3x3red, 1, 8), *_unit(n3x3red, n3x3, 3, 16))
         self.b3 = nn.Sequential(*_unit(in_planes, n5x5red, 1, 8), *_unit(n5x5red, n5x5, 3, 8),
                                 *_unit(n5x5, n5x5, 3, 8))
-        self.b4 = nn.Sequential(nn.MaxPool2d(3, stride=1, padding=1), *_unit(in_planes, pool_planes, 1, 8))
+        self.b4 = nn.Sequential(MaxPool2d(3, stride=1, padding=1), *_unit(in_planes, pool_planes, 1, 8))
 
     def forward(self, x):
         return torch.cat([self.b1(x), self.b2(x), self.b3(x), self.b4(x)], 1)
@@ -38,7 +39,7 @@ class GoogLeNet(nn.Module):
         self.pre_layers = nn.Sequential(*_unit(3, 192, 3, 8))
         self.a3 = Inception(192, 64, 96, 128, 16, 32, 32)
         self.b3 = Inception(256, 128, 128, 192, 32, 96, 64)
-        self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
+        self.maxpool = MaxPool2d(3, stride=2, padding=1)
         self.a4 = Inception(480, 192, 96, 208, 16, 48, 64)
         self.b4 = Inception(512, 160, 112, 224, 24, 64, 64)
         self.c4 = Inception(512, 128, 128, 256, 24, 64, 64)
@@ -55,4 +56,4 @@ class GoogLeNet(nn.Module):
         out = self.e4(self.d4(self.c4(self.b4(self.a4(out)))))
         out = self.maxpool(out)
         out = self.b5(self.a5(out))
-        return self.linear(self.avgpool(out).flatten(1))
+        return self.linear(ops.avg_pool2d(out, 8).flatten(1))     # AvgPool2d(8) on the 8x8 map (self.avgpool kept for parity)

@@ -45,3 +45,13 @@ class Conv2d(nn.Conv2d):
 class Linear(nn.Linear):
     def forward(self, x):
         return ops.linear(x, self.weight, self.bias)
+
+
+class MaxPool2d(nn.MaxPool2d):
+    """nn.MaxPool2d routed through ``ops.max_pool2d`` (NHWC kernel with a gather backward on CUDA)."""
+
+    def forward(self, x):
+        k = self.kernel_size if isinstance(self.kernel_size, int) else self.kernel_size[0]
+        s = self.stride if isinstance(self.stride, int) else self.stride[0]
+        p = self.padding if isinstance(self.padding, int) else self.padding[0]
+        return ops.max_pool2d(x, k, s, p)

@@ -8,6 +8,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .layers import Conv2d, Linear
+from .. import ops
 
 
 class MnistNet(nn.Module):
@@ -22,8 +23,8 @@ class MnistNet(nn.Module):
         self.fc2 = Linear(50, num_classes)
 
     def forward(self, x):
-        x = F.relu(F.max_pool2d(self.conv1(x), 2))
-        x = F.relu(F.max_pool2d(self.conv2_drop(self.conv2(x)), 2))
+        x = F.relu(ops.max_pool2d(self.conv1(x), 2))
+        x = F.relu(ops.max_pool2d(self.conv2_drop(self.conv2(x)), 2))
         x = x.reshape(x.shape[0], -1) if x.is_contiguous() else x.contiguous().reshape(x.shape[0], -1)
         x = F.relu(self.fc1(x))
         x = F.dropout(x, training=self.training)

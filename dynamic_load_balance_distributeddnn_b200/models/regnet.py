@@ -9,6 +9,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .layers import Conv2d, GroupNormAct, Linear
+from .. import ops
 
 _GROUPS = 32
 
@@ -84,7 +85,7 @@ class RegNet(nn.Module):
     def forward(self, x):
         out = self.gn1(self.conv1(x))
         out = self.layer4(self.layer3(self.layer2(self.layer1(out))))
-        return self.linear(F.adaptive_avg_pool2d(out, (1, 1)).flatten(1))
+        return self.linear(ops.global_avg_pool2d(out).flatten(1))
 
 
 def _cfg(depths, widths, group_width, se_ratio):

@@ -10,6 +10,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .layers import Conv2d, GroupNormAct, Linear
+from .. import ops
 
 _GROUPS = 32
 
@@ -85,7 +86,7 @@ class ResNet(nn.Module):
     def forward(self, x):
         out = self.gn1(self.conv1(x))
         out = self.layer4(self.layer3(self.layer2(self.layer1(out))))
-        out = F.avg_pool2d(out, 4).flatten(1)
+        out = ops.avg_pool2d(out, 4).flatten(1)
         return self.linear(out)
 
 

@@ -413,3 +413,26 @@ def test_stem_conv_kernel(nat, dtype, tol, n, co, hw):
     yr.backward(gy.float())
     assert (y.float() - yr).abs().max().item() < tol * max(1.0, yr.abs().max().item())
     assert (w.grad.float() - wr.grad).abs().max().item() < 2 * tol * max(1.0, wr.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n,c,hw,k,s,p", [(4, 64, 32, 3, 2, 1), (3, 480, 16, 3, 1, 1), (5, 20, 8, 2, 2, 0), (2, 10, 24, 2, 2, 0)])
+def test_max_pool_kernel(nat, dtype, n, c, hw, k, s, p):
+    from dynamic_load_balance_distributeddnn_b200 import ops
+    torch.manual_seed(n + c)
+    x = _cl(torch.randn(n, c, hw, hw, device="cuda")).to(dtype).requires_grad_(True)
+    y = ops.max_pool2d(x, k, s, p)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xr = x.detach().float().requires_grad_(True)
+    yr = F.max_pool2d(xr, k, s, p)
+    yr.backward(gy.float())
+    assert torch.equal(y.float(), yr)
+    tol = 1e-6 if dtype == torch.float32 else 2e-2
+    assert (x.grad.float() - xr.grad).abs().max().item() <= tol * max(1.0, xr.grad.abs().max().item())
+
+
+def test_global_avg_pool_routes_to_kernel(nat):
+    from dynamic_load_balance_distributeddnn_b200 import ops
+    x = _cl(torch.randn(6, 384, 4, 4, device="cuda")).bfloat16()
+    assert (ops.global_avg_pool2d(x).float() - F.adaptive_avg_pool2d(x.float(), 1)).abs().max().item() < 2e-2
