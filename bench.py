@@ -63,7 +63,7 @@ def parse():
                         "'sleep' is absorbed by the asynchronous engine and would not straggle at all.  The reference arm "
                         "always uses its own injector's mechanism (a host sleep between backward and allreduce, dbs.py:236)")
     p.add_argument("--no-dbs", action="store_true")
-    p.add_argument("--dbs-rounds", type=int, default=2, help="untimed measure->rebalance rounds before the timed region (both arms)")
+    p.add_argument("--dbs-rounds", type=int, default=3, help="untimed measure->rebalance rounds before the timed region (both arms)")
     p.add_argument("--dbs-model", default="auto", help="own arm: proportional | affine | auto (the framework default)")
     p.add_argument("--no-graphs", action="store_true")
     p.add_argument("--no-overlap", action="store_true")
@@ -217,7 +217,7 @@ def run_ours(a) -> dict:
                         dynamic_batch_size=not a.no_dbs, cuda_graphs=not a.no_graphs, comm=a.comm, allreduce_algo=a.algo,
                         dtype=dtype, overlap_comm=not a.no_overlap, throttle_rank=world - 1 if throttle > 0 else -1,
                         throttle_ms=throttle, throttle_mode=a.throttle_mode, log_dir="/tmp/dlb_bench/logs",
-                        stats_dir="/tmp/dlb_bench/statis", **extra)
+                        stats_dir="/tmp/dlb_bench/statis", min_local_batch=min(8, max(1, a.batch // (2 * world))), **extra)
         logger = init_logger(cfg, rank, stream=False)
         tr = Trainer(cfg, rank, world, device, logger)
         is_lm = tr.is_lm
@@ -320,7 +320,7 @@ def run_ours(a) -> dict:
                "ms_dev": ms_dev / K, "ms_e2e": ms_e2e / K, "h2d": int(h2d), "launches": int(launches),
                "wait_dev": 1e3 * wait_dev / K, "host_dev": host_dev / K, "host_e2e": host_e2e / K,
                "lb0": lb0, "lb": [int(x) for x in lb], "comm": tr.comm.name, "graphs": bool(tr._graphs),
-               "graph_nodes": getattr(tr, "graph_nodes", None), "dbs_model": cfg.dbs_model,
+               "graph_nodes": getattr(tr, "graph_nodes", None), "dbs_model": cfg.resolved_dbs_model(),
                "loss": float(tr.loss_acc.item())}
         tr.close()
         del tr

@@ -38,9 +38,10 @@ def _largest_remainder(target: np.ndarray, total: int) -> np.ndarray:
     fl = np.floor(target + 1e-12).astype(np.int64)
     left = int(total - fl.sum())
     if left > 0:
-        frac = target - fl
-        # stable: ties go to the lower rank index so every rank computes the same answer
-        order = np.lexsort((np.arange(len(frac)), -frac))
+        frac = np.round(target - fl, 9)           # remainders equal up to float noise are ties
+        # ties go to the larger share, then to the lower rank index: every rank computes the same answer and the multiset
+        # of batches does not depend on the order of the ranks
+        order = np.lexsort((np.arange(len(frac)), -target, -frac))
         fl[order[:left]] += 1
     elif left < 0:                      # only reachable through min/quantum clamping
         frac = target - fl
@@ -200,11 +201,12 @@ class AffineReallocator(Reallocator):
     batches a step is launch-latency bound — its time barely depends on the batch (measured: 9.7 ms at b = 64 and b = 128)
     — and a straggler's extra time is largely a fixed cost: the proportional rule then keeps shrinking the slow rank
     geometrically down to the minimum batch although that buys nothing.  This variant fits (alpha_r, beta_r) from the
-    history of (local batch, compute time) observations (least squares over the last ``window`` distinct batch sizes; proportional
-    rule until a rank has been seen at two different batch sizes) and picks the split that equalises the predicted step
+    history of (local batch, compute time) observations (last ``window`` distinct batch sizes per rank; a slope pooled over
+    all ranks with per-rank intercepts, each rank's own slope shrunk towards it; proportional rule for the very first move,
+    when nothing is identifiable yet) and picks the split that equalises the predicted step
     times:  b_r = (tau - alpha_r) / beta_r  with  tau  such that  sum_r b_r = B  (water-filling at the lower bound).
     A rank whose time does not respond to its batch at all (flat fit) keeps its batch.
-    Opt-in (``--dbs_model affine``); the default remains the reference's rule.
+    ``--dbs_model affine``; ``auto`` (the default) selects it on CUDA devices and the reference's rule on CPU.
     """
 
     def __init__(self, *args, window: int = 6, **kw):
@@ -230,20 +232,48 @@ class AffineReallocator(Reallocator):
         if "obs" in sd:
             self.obs = [[(float(b), float(t)) for b, t in per_rank] for per_rank in sd["obs"]]
 
-    def _fit(self, r: int):
-        pts = self.obs[r]
-        bs = np.array([p[0] for p in pts]); ts = np.array([p[1] for p in pts])
-        if len(pts) < 2 or np.ptp(bs) < 1:
+    def _pooled_slope(self):
+        """Within-rank least-squares slope over ALL ranks' observations (fixed-effects model: one intercept per rank, one common
+        slope).  The ranks of a job are the same kind of GPU running the same kernels, so the marginal cost of a sample is (nearly)
+        common while the fixed cost differs (a straggler's injected / contended milliseconds).  Pooling is what makes the model
+        identifiable early: after the first proportional move the fast ranks have only moved by a sample or two -- their own
+        two-point slopes are noise -- but the straggler's large move pins the common slope."""
+        sxx = sxy = 0.0
+        for pts in self.obs:
+            if len(pts) < 2:
+                continue
+            bs = np.array([q[0] for q in pts]); ts = np.array([q[1] for q in pts])
+            sxx += float(((bs - bs.mean()) ** 2).sum())
+            sxy += float(((bs - bs.mean()) * (ts - ts.mean())).sum())
+        if sxx < 1.0:
             return None
-        beta, alpha = np.polyfit(bs, ts, 1)
+        return sxy / sxx
+
+    def _fit(self, r: int, pooled):
+        """(alpha_r, beta_r): the rank's own slope shrunk towards the pooled one (prior weight = one pair of observations a
+        quarter of the mean batch apart), intercept from the rank's mean point."""
+        pts = self.obs[r]
+        if not pts or pooled is None:
+            return None
+        bs = np.array([q[0] for q in pts]); ts = np.array([q[1] for q in pts])
+        sxx = float(((bs - bs.mean()) ** 2).sum())
+        sxy = float(((bs - bs.mean()) * (ts - ts.mean())).sum())
+        kappa = (0.25 * self.batch_size / self.world_size) ** 2
+        beta = (sxy + kappa * pooled) / (sxx + kappa)
         if not np.isfinite(beta) or beta * bs.mean() < 0.02 * ts.mean():
             return float(ts.mean()), 0.0                          # flat: the batch does not move this rank's time
-        return max(float(alpha), 0.0), float(beta)
+        alpha = float(ts.mean() - beta * bs.mean())
+        if alpha < 0.0:
+            # a negative fixed cost is not physical: the borrowed slope is too steep for this rank (e.g. the pooled slope is
+            # dominated by a genuinely slower device) -> the reference's proportional model for this rank
+            return 0.0, float(ts.mean() / bs.mean())
+        return alpha, float(beta)
 
     def step(self) -> Tuple[np.ndarray, np.ndarray]:
         if not self.enabled:
             return super().step()
-        fits = [self._fit(r) for r in range(self.world_size)]
+        pooled = self._pooled_slope()
+        fits = [self._fit(r, pooled) for r in range(self.world_size)]
         if any(f is None for f in fits):
             return super().step()                                 # not identifiable yet: proportional (reference) rule
         alpha = np.array([f[0] for f in fits]); beta = np.array([f[1] for f in fits])

@@ -100,7 +100,7 @@ def get_parser() -> argparse.ArgumentParser:
     x.add_argument("--rebalance_every", type=int, default=0,
                    help="rebalance every N steps instead of once per epoch (0 = per epoch)")
     x.add_argument("--time_ema", type=float, default=0.0)
-    x.add_argument("--dbs_model", choices=("proportional", "affine"), default="proportional",
+    x.add_argument("--dbs_model", choices=("auto", "proportional", "affine"), default="auto",
                    help="proportional = the reference's rule; affine = fit t_r(b) = alpha + beta*b per rank and equalise "
                         "predicted step times (for latency-bound steps where time is not proportional to the batch)")
     x.add_argument("--lr_policy", choices=("one_cycle", "legacy"), default="one_cycle")

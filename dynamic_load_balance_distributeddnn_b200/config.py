@@ -53,7 +53,8 @@ class DBSConfig:
     batch_quantum: int = 1
     rebalance_every: int = 0             # 0 = once per epoch (reference); N>0 = every N steps
     time_ema: float = 0.0                # EMA on per-rank compute time (0 = off = reference)
-    dbs_model: str = "proportional"      # proportional (reference get_size) | affine (t = alpha + beta*b, latency-aware)
+    dbs_model: str = "auto"              # proportional (reference get_size) | affine (t = alpha + beta*b, latency-aware) | auto
+                                         # (affine on CUDA devices, where a step has a large fixed cost; the reference rule on CPU)
     lr_policy: str = "one_cycle"         # one_cycle | legacy (the reference's live decay-only curve)
     clip_grad_norm: float = -1.0         # <0: model default (0.25 for transformer, none for CNNs)
     clip_mode: str = "local"             # local (reference, pre-allreduce) | global (post-reduce)
@@ -118,6 +119,11 @@ class DBSConfig:
         if self.comm != "auto":
             return self.comm
         return "symm" if device.startswith("cuda") else "gloo"
+
+    def resolved_dbs_model(self) -> str:
+        if self.dbs_model != "auto":
+            return self.dbs_model
+        return "proportional" if self.debug else "affine"
 
     def resolved_clip(self) -> float:
         if self.clip_grad_norm >= 0:

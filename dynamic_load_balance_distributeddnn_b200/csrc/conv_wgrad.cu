@@ -213,7 +213,8 @@ int wgrad3x3_impl(const void* x, long long ldx, const void* dy, long long lddy, 
   int hb, nb;
   if (!w3_tile_geometry(H, W, hb, nb)) return -7;
   const long long M = (long long)N * H * W;
-  if (M % 128) return -8;                                     // whole 128-pixel tiles (N * H * W multiple of 128)
+  // a last partial tile (images past N inside a multi-image box / rows past M of dY) is zero-filled by the TMA unit on BOTH
+  // operands, so it contributes nothing: any N is accepted (DBS hands out odd local batches all the time)
   if ((Ci % V) || (ldx % V) || (lddy % V) || ((uintptr_t)x & 15) || ((uintptr_t)dy & 15) || ((uintptr_t)dw & 3)) return -3;
   static int sm_count = 0;
   if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
@@ -231,7 +232,7 @@ int wgrad3x3_impl(const void* x, long long ldx, const void* dy, long long lddy, 
   // the box (DenseNet growth 32 in bf16) the TMA unit zero-fills the rest instead of reading neighbouring channels
   W3Params p;
   p.H = H; p.W = W; p.Ci = Ci; p.Co = Co; p.hb = hb; p.nb = nb; p.dw = dw;
-  p.num_tiles = (int)(M / 128);
+  p.num_tiles = (int)((M + 127) / 128);
   p.ci_tiles = (Ci + 127) / 128;
   p.co_tiles = (Co + C::kN - 1) / C::kN;
   p.taps_per_group = C::kMaxTaps;
@@ -264,7 +265,7 @@ int wgrad3x3_impl(const void* x, long long ldx, const void* dy, long long lddy, 
 
 // dW[Co][3][3][Ci] (fp32, zero-initialised by the caller or accumulated into) += wgrad of the 3x3/s1/p1 convolution.
 // x: [N,H,W,Ci] with pixel stride ldx; dy: [N,H,W,Co] with pixel stride lddy (both may be channel slices of wider NHWC buffers).
-// Requirements: 128 % W == 0 with whole-row tiles (same geometry as dlb_conv3x3_tc), N*H*W % 128 == 0, Ci and the strides
+// Requirements: 128 % W == 0 with whole-row tiles (same geometry as dlb_conv3x3_tc), any N, Ci and the strides
 // multiples of the 16-byte vector; Co arbitrary (channels beyond Co inside the 128-byte box are masked in the epilogue).
 DLB_API int dlb_wgrad3x3_tc_dt(int dtype, const void* x, long long ldx, const void* dy, long long lddy, float* dw, int N, int H, int W,
                                int Ci, int Co, int sm_limit, void* stream) {

@@ -1,8 +1,10 @@
 // Fused data-gradient GEMM + GroupNorm(+ReLU) backward for a pre-activation 1x1 convolution
 // (GN -> ReLU -> conv1x1, the first half of the DenseNet bottleneck; reference Net/Densenet.py:13-19).
 //
-// EXPERIMENTAL (round-2 groundwork): compiled into the library but only used when DLB_FUSED_DGRAD=1; the default
-// backward keeps the validated three-kernel chain  dgrad GEMM -> nc_reduce2<MODE 3> -> gn_bwd_apply<RELU 2>.
+// Default backward of the dense-block bottleneck (DLB_FUSED_DGRAD=0 restores the chain dgrad GEMM -> fused GN backward).
+// Element type E: bf16 (kind::f16) or fp32 storage with TF32 math (kind::tf32).  A tile is always TWO 128-byte column
+// groups wide (128 bf16 / 64 fp32 channels), so every shared-memory box, swizzle pattern and barrier byte count below is
+// the same for both types.
 //
 // Why: with  A = relu(GN(x)),  y = A * W^T  the input gradient is
 //     dA = dY * W                                        (GEMM, K = Cmid = 128)
@@ -20,20 +22,50 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, UMMA_K = 16;
+constexpr int BM = 128;
 constexpr int kEpiWarps = 8;
 constexpr int kThreadsDG = 384;                 // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
-constexpr int kABytes = BM * BK * 2;            // 16 KB
-constexpr int kBBytes = BN * BK * 2;            // 16 KB (two [64 k][64 n] boxes)
-constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kHalfBytes = BM * 64 * 2;         // one [128 rows][64 cols] box = 16 KB
+constexpr int kABytes = BM * 128;               // 16 KB: [128 rows][128 bytes of k]
+constexpr int kHalfBytes = BM * 128;            // one [128 rows][128 bytes of channels] box = 16 KB
 constexpr int kTensorBytes = 2 * kHalfBytes;    // x (or dX) tile: 32 KB
 
-template <int MODE> struct DCfg {
+template <typename E, int MODE> struct DCfg {
+  using EL = Elt<E>;
+  static constexpr int AT = EL::kAtom;            // channels per 128-byte column group (64 bf16 / 32 fp32)
+  static constexpr int BN = 2 * AT, BK = AT, UMMA_K = EL::kUmmaK;
+  static constexpr int kMnBox = BK * 128;         // one MN-major B box: [BK k-rows][128 bytes of n]
+  static constexpr int kBBytes = 2 * kMnBox;      // 16 KB bf16 / 8 KB fp32
+  static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = MODE == 2 ? 3 : 4;
   static constexpr int kAuxSlotBytes = (MODE == 2 ? 2 : 1) * kTensorBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kAuxSlotBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
+
+// four consecutive channels (index group j4 of the 32-column chunk) out of / into the row's 16-byte chunks
+template <typename E>
+__device__ __forceinline__ void unpack4(const uint4* ch, int j4, float (&o)[4]) {
+  if constexpr (sizeof(E) == 2) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&ch[j4 >> 1]) + (j4 & 1) * 2;
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[0]));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[1]));
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+  } else {
+    o[0] = __uint_as_float(ch[j4].x); o[1] = __uint_as_float(ch[j4].y);
+    o[2] = __uint_as_float(ch[j4].z); o[3] = __uint_as_float(ch[j4].w);
+  }
+}
+template <typename E>
+__device__ __forceinline__ void pack4(uint4* ch, int j4, const float (&o)[4]) {
+  if constexpr (sizeof(E) == 2) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(&ch[j4 >> 1]) + (j4 & 1) * 2;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]);
+    __nv_bfloat162 h1 = __floats2bfloat162_rn(o[2], o[3]);
+    w[0] = *reinterpret_cast<uint32_t*>(&h0);
+    w[1] = *reinterpret_cast<uint32_t*>(&h1);
+  } else {
+    ch[j4] = make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]));
+  }
+}
 
 struct DgParams {
   int M, N, K;                 // pixels, input channels of the conv (width of x / dX), mid channels (width of dY)
@@ -47,12 +79,16 @@ struct DgParams {
   long long table_ns;
 };
 
-template <int MODE>
+template <typename E, int MODE>
 __global__ void __launch_bounds__(kThreadsDG, 1)
 dgrad_gn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_gl,
                 const __grid_constant__ CUtensorMap tmap_gs, const DgParams p) {
-  using C = DCfg<MODE>;
+  using C = DCfg<E, MODE>;
+  using EL = Elt<E>;
+  constexpr int BN = C::BN, BK = C::BK, AT = C::AT, UMMA_K = C::UMMA_K;
+  constexpr int kStageBytes = C::kStageBytes, kBBytes = C::kBBytes, kMnBox = C::kMnBox;
+  constexpr int kCh = 32 / EL::kPer16;                 // 16-byte chunks per 32 channels (4 bf16 / 8 fp32)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* aux_base = smem + C::kStages * kStageBytes;                     // 1024-byte aligned
@@ -110,17 +146,17 @@ dgrad_gn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       int slot = 0; uint32_t aux_phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m0 = (t / num_n) * BM, n0 = (t % num_n) * BN;
-        const bool h1 = n0 + 64 < p.N;                           // second 64-column half intersects the tensor
+        const bool h1 = n0 + AT < p.N;                           // second column group intersects the tensor
         // epilogue operands of this tile first: they are the bulk of the bytes and the epilogue is the long pole
         mbar_wait(smem_u32(&aux_empty[slot]), aux_phase ^ 1);
         const uint32_t ab = smem_u32(aux_base + slot * C::kAuxSlotBytes);
         const uint32_t af = smem_u32(&aux_full[slot]);
         mbar_expect_tx(af, (uint32_t)((MODE == 2 ? 2 : 1) * (h1 ? kTensorBytes : kHalfBytes)));
         tma_load_2d(ab, &tmap_x, af, n0, m0);
-        if (h1) tma_load_2d(ab + kHalfBytes, &tmap_x, af, n0 + 64, m0);
+        if (h1) tma_load_2d(ab + kHalfBytes, &tmap_x, af, n0 + AT, m0);
         if constexpr (MODE == 2) {
           tma_load_2d(ab + kTensorBytes, &tmap_gl, af, n0, m0);
-          if (h1) tma_load_2d(ab + kTensorBytes + kHalfBytes, &tmap_gl, af, n0 + 64, m0);
+          if (h1) tma_load_2d(ab + kTensorBytes + kHalfBytes, &tmap_gl, af, n0 + AT, m0);
         }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
@@ -130,7 +166,7 @@ dgrad_gn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           mbar_expect_tx(fb, (uint32_t)(kABytes + (h1 ? kBBytes : kBBytes / 2)));
           tma_load_2d(sa, &tmap_a, fb, kb * BK, m0);
           tma_load_2d(sb, &tmap_b, fb, n0, kb * BK);
-          if (h1) tma_load_2d(sb + 8192, &tmap_b, fb, n0 + 64, kb * BK);
+          if (h1) tma_load_2d(sb + kMnBox, &tmap_b, fb, n0 + AT, kb * BK);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
         slot ^= 1;
@@ -140,14 +176,14 @@ dgrad_gn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
-      // D = f32, A = B = bf16, A K-major, B MN-major (bit 16), M = 128, N = 128 or 64 (tail tile)
-      const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(BM >> 4) << 24);
+      // D = f32, A / B format of E, A K-major, B MN-major (bit 16), M = 128, N = both column groups or one (tail tile)
+      const uint32_t idesc_base = (1u << 4) | (EL::kFmt << 7) | (EL::kFmt << 10) | (1u << 16) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int n0 = (t % num_n) * BN;
-        const bool h1 = n0 + 64 < p.N;
-        const uint32_t idesc = idesc_base | ((uint32_t)((h1 ? 128 : 64) >> 3) << 17);
+        const bool h1 = n0 + AT < p.N;
+        const uint32_t idesc = idesc_base | ((uint32_t)((h1 ? BN : AT) >> 3) << 17);
         mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -155,10 +191,10 @@ dgrad_gn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-          const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc_mn(sa + kABytes);
+          const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc_mn(sa + kABytes, kMnBox, EL::kMn32);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(128 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            EL::mma(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(8 * UMMA_K * k), idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(smem_u32(&empty_bar[stage]));
           if (kb == num_kb - 1) umma_commit(smem_u32(&tmem_full[acc]));
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -170,7 +206,7 @@ dgrad_gn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // ===================================== epilogue =========================================
     const int ew = warp - 4;
     const int q = ew & 3;                        // TMEM lane quadrant (== warp % 4)
-    const int hsel = ew >> 2;                    // which 64-column half of the tile
+    const int hsel = ew >> 2;                    // which 128-byte column group of the tile
     const int sw = lane & 7;                     // 128B-swizzle phase of this thread's row ((q*32 + lane) & 7)
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -179,20 +215,20 @@ dgrad_gn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       mbar_wait(smem_u32(&aux_full[acc]), acc_phase);
       tc_fence_after();
       const int rbase = m0 + q * 32;
-      const bool live = (n0 + hsel * 64 < p.N) && (rbase < p.M);      // warp-uniform (M % 32 == 0)
+      const bool live = (n0 + hsel * AT < p.N) && (rbase < p.M);      // warp-uniform (M % 32 == 0)
       if (live) {
         const int sample = rbase / p.rows_per_sample;
         const uint32_t xrow = smem_u32(aux_base + acc * C::kAuxSlotBytes + hsel * kHalfBytes + (q * 32 + lane) * 128);
         const uint32_t grow = xrow + kTensorBytes;                    // MODE 2: same position in the dX tile
 #pragma unroll 1
-        for (int c0 = 0; c0 < 64; c0 += 32) {
+        for (int c0 = 0; c0 < AT; c0 += 32) {
           uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + hsel * 64 + c0), v);
-          const int jb = c0 >> 3;                                     // first 16-byte chunk of this 32-column group
-          uint4 xr[4];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + hsel * AT + c0), v);
+          const int jb = c0 / EL::kPer16;                             // first 16-byte chunk of this 32-column group
+          uint4 xr[kCh];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) xr[j] = lds128(xrow + (uint32_t)(((jb + j) ^ sw) << 4));
-          const int col = n0 + hsel * 64 + c0;                        // global channel of v[0]
+          for (int j = 0; j < kCh; ++j) xr[j] = lds128(xrow + (uint32_t)(((jb + j) ^ sw) << 4));
+          const int col = n0 + hsel * AT + c0;                        // global channel of v[0]
           const float4* pa = reinterpret_cast<const float4*>(p.ca + (long long)sample * p.cld + col);
           const float4* pb = reinterpret_cast<const float4*>(p.cb + (long long)sample * p.cld + col);
           if constexpr (MODE == 1) {
@@ -200,10 +236,8 @@ dgrad_gn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               const float4 a = __ldg(pa + j4), b = __ldg(pb + j4);
-              const uint32_t* xw = reinterpret_cast<const uint32_t*>(&xr[j4 >> 1]) + (j4 & 1) * 2;
-              const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw[0]));
-              const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw[1]));
-              const float xs[4] = {x01.x, x01.y, x23.x, x23.y};
+              float xs[4];
+              unpack4<E>(xr, j4, xs);
               const float as[4] = {a.x, a.y, a.z, a.w};
               const float bs[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
@@ -237,20 +271,15 @@ dgrad_gn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           } else {
             const float4* p2 = reinterpret_cast<const float4*>(p.k2 + (long long)sample * p.cld + col);
             const float4* p3 = reinterpret_cast<const float4*>(p.k3 + (long long)sample * p.cld + col);
-            uint4 gr[4];
+            uint4 gr[kCh];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) gr[j] = lds128(grow + (uint32_t)(((jb + j) ^ sw) << 4));
+            for (int j = 0; j < kCh; ++j) gr[j] = lds128(grow + (uint32_t)(((jb + j) ^ sw) << 4));
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               const float4 a = __ldg(pa + j4), b = __ldg(pb + j4), c2 = __ldg(p2 + j4), c3 = __ldg(p3 + j4);
-              const uint32_t* xw = reinterpret_cast<const uint32_t*>(&xr[j4 >> 1]) + (j4 & 1) * 2;
-              uint32_t* gw = reinterpret_cast<uint32_t*>(&gr[j4 >> 1]) + (j4 & 1) * 2;
-              const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw[0]));
-              const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw[1]));
-              const float2 g01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[0]));
-              const float2 g23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[1]));
-              const float xs[4] = {x01.x, x01.y, x23.x, x23.y};
-              const float gs[4] = {g01.x, g01.y, g23.x, g23.y};
+              float xs[4], gs[4];
+              unpack4<E>(xr, j4, xs);
+              unpack4<E>(gr, j4, gs);
               const float as[4] = {a.x, a.y, a.z, a.w};
               const float bs[4] = {b.x, b.y, b.z, b.w};
               const float k2s[4] = {c2.x, c2.y, c2.z, c2.w};
@@ -262,23 +291,20 @@ dgrad_gn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 const float dz = fmaf(as[e], xs[e], bs[e]) > 0.f ? da : 0.f;
                 o[e] = gs[e] + fmaf(as[e], dz, fmaf(k2s[e], xs[e], k3s[e]));
               }
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]);
-              __nv_bfloat162 h1v = __floats2bfloat162_rn(o[2], o[3]);
-              gw[0] = *reinterpret_cast<uint32_t*>(&h0);
-              gw[1] = *reinterpret_cast<uint32_t*>(&h1v);
+              pack4<E>(gr, j4, o);
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) sts128(grow + (uint32_t)(((jb + j) ^ sw) << 4), gr[j]);
+            for (int j = 0; j < kCh; ++j) sts128(grow + (uint32_t)(((jb + j) ^ sw) << 4), gr[j]);
           }
         }
         if constexpr (MODE == 2) {
-          // the warp's [32 rows][64 cols] box of the dX tile now holds the updated gradient: TMA-store it in place
+          // the warp's [32 rows][128 bytes] box of the dX tile now holds the updated gradient: TMA-store it in place
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
             const uint32_t box = smem_u32(aux_base + acc * C::kAuxSlotBytes + kTensorBytes + hsel * kHalfBytes + q * 4096);
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                         ::"l"(&tmap_gs), "r"(box), "r"(n0 + hsel * 64), "r"(rbase)
+                         ::"l"(&tmap_gs), "r"(box), "r"(n0 + hsel * AT), "r"(rbase)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be refilled once it has been read
@@ -347,11 +373,12 @@ gn_bwd_coeff_kernel(const float* __restrict__ table, long long table_ns, const f
   }
 }
 
-template <int MODE>
+template <typename E, int MODE>
 int launch_dg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tx, const CUtensorMap& tgl, const CUtensorMap& tgs,
               const DgParams& p, int sms, cudaStream_t st) {
-  using C = DCfg<MODE>;
-  auto kern = dgrad_gn_kernel<MODE>;
+  using C = DCfg<E, MODE>;
+  constexpr int BN = C::BN;
+  auto kern = dgrad_gn_kernel<E, MODE>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
@@ -364,23 +391,18 @@ int launch_dg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
   return dlb_post_launch();
 }
 
-}  // namespace
-
-// mode 1: table[samples][table_ns] += per-(sample, channel) (sum dz, sum dz*x),  dz = (dY*W) * [ca*x + cb > 0]
-// mode 2: dX += ca*dz + k2*x + k3                                              (in place, bf16)
-//   dy [M][K] (row stride lddy), w [K][N] (row stride ldw; the 1x1 conv weight [Cmid][Cin] as stored), x / dx [M][N]
-//   (row strides ldx / lddx: channel slices of the block buffers are addressed in place).
-DLB_API int dlb_dgrad_gn(int mode, const void* dy, long long lddy, const void* w, long long ldw, const void* x, long long ldx,
-                         void* dx, long long lddx, int M, int N, int K, int rows_per_sample, const float* ca, const float* cb,
-                         const float* k2, const float* k3, long long cld, float* table, long long table_ns, int sm_limit,
-                         void* stream) {
+template <typename E>
+int dgrad_gn_impl(int mode, const void* dy, long long lddy, const void* w, long long ldw, const void* x, long long ldx,
+                  void* dx, long long lddx, int M, int N, int K, int rows_per_sample, const float* ca, const float* cb,
+                  const float* k2, const float* k3, long long cld, float* table, long long table_ns, int sm_limit, cudaStream_t st) {
+  constexpr int EB = Elt<E>::kBytes, AT = Elt<E>::kAtom, V = 16 / EB;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (mode != 1 && mode != 2) return -2;
-  if ((K % 8) || (N % 8) || (lddy % 8) || (ldw % 8) || (ldx % 8) || ((uintptr_t)dy & 15) || ((uintptr_t)w & 15) || ((uintptr_t)x & 15)) return -3;
+  if ((K % V) || (N % V) || (lddy % V) || (ldw % V) || (ldx % V) || ((uintptr_t)dy & 15) || ((uintptr_t)w & 15) || ((uintptr_t)x & 15)) return -3;
   if (rows_per_sample <= 0 || (rows_per_sample % 32) || (M % rows_per_sample) || M < BM) return -4;
   if (!ca || !cb || (cld % 64) || cld < (N + 63) / 64 * 64 || ((uintptr_t)ca & 15) || ((uintptr_t)cb & 15)) return -5;
   if (mode == 1 && !table) return -6;
-  if (mode == 2 && (!dx || !k2 || !k3 || (lddx % 8) || ((uintptr_t)dx & 15) || ((uintptr_t)k2 & 15) || ((uintptr_t)k3 & 15))) return -6;
+  if (mode == 2 && (!dx || !k2 || !k3 || (lddx % V) || ((uintptr_t)dx & 15) || ((uintptr_t)k2 & 15) || ((uintptr_t)k3 & 15))) return -6;
   static int sm_count = 0;
   if (!sm_count) {
     int dev = 0;
@@ -390,16 +412,16 @@ DLB_API int dlb_dgrad_gn(int mode, const void* dy, long long lddy, const void* w
   int sms = sm_count;
   if (sm_limit > 0 && sm_limit < sms) sms = sm_limit;
   CUtensorMap ta, tb, tx, tgl, tgs;
-  int rc = make_map(&ta, dy, M, K, lddy, BM);
+  int rc = make_map(&ta, dy, M, K, lddy, BM, EB);
   if (rc) return rc - 10;
-  rc = make_map(&tb, w, K, N, ldw, 64);
+  rc = make_map(&tb, w, K, N, ldw, AT, EB, Elt<E>::kMn32);      // [BK k-rows][128 bytes of n] boxes, MN-major operand
   if (rc) return rc - 20;
-  rc = make_map(&tx, x, M, N, ldx, BM);
+  rc = make_map(&tx, x, M, N, ldx, BM, EB);
   if (rc) return rc - 30;
   if (mode == 2) {
-    rc = make_map(&tgl, dx, M, N, lddx, BM);
+    rc = make_map(&tgl, dx, M, N, lddx, BM, EB);
     if (rc) return rc - 40;
-    rc = make_map(&tgs, dx, M, N, lddx, 32);
+    rc = make_map(&tgs, dx, M, N, lddx, 32, EB);
     if (rc) return rc - 50;
   } else {
     tgl = tx; tgs = tx;                         // unused in mode 1
@@ -407,8 +429,32 @@ DLB_API int dlb_dgrad_gn(int mode, const void* dy, long long lddy, const void* w
   DgParams p;
   p.M = M; p.N = N; p.K = K; p.rows_per_sample = rows_per_sample;
   p.ca = ca; p.cb = cb; p.k2 = k2; p.k3 = k3; p.cld = cld; p.table = table; p.table_ns = table_ns;
-  cudaStream_t st = (cudaStream_t)stream;
-  return mode == 1 ? launch_dg<1>(ta, tb, tx, tgl, tgs, p, sms, st) : launch_dg<2>(ta, tb, tx, tgl, tgs, p, sms, st);
+  return mode == 1 ? launch_dg<E, 1>(ta, tb, tx, tgl, tgs, p, sms, st) : launch_dg<E, 2>(ta, tb, tx, tgl, tgs, p, sms, st);
+}
+
+}  // namespace
+
+// mode 1: table[samples][table_ns] += per-(sample, channel) (sum dz, sum dz*x),  dz = (dY*W) * [ca*x + cb > 0]
+// mode 2: dX += ca*dz + k2*x + k3                                              (in place, element type of the operands)
+//   dy [M][K] (row stride lddy), w [K][N] (row stride ldw; the 1x1 conv weight [Cmid][Cin] as stored), x / dx [M][N]
+//   (row strides ldx / lddx: channel slices of the block buffers are addressed in place).  dtype: DLB_BF16 or DLB_F32 (TF32 math).
+DLB_API int dlb_dgrad_gn_dt(int dtype, int mode, const void* dy, long long lddy, const void* w, long long ldw, const void* x, long long ldx,
+                            void* dx, long long lddx, int M, int N, int K, int rows_per_sample, const float* ca, const float* cb,
+                            const float* k2, const float* k3, long long cld, float* table, long long table_ns, int sm_limit,
+                            void* stream) {
+  if (dtype == DLB_F32)
+    return dgrad_gn_impl<float>(mode, dy, lddy, w, ldw, x, ldx, dx, lddx, M, N, K, rows_per_sample, ca, cb, k2, k3, cld, table, table_ns,
+                                sm_limit, (cudaStream_t)stream);
+  return dgrad_gn_impl<__nv_bfloat16>(mode, dy, lddy, w, ldw, x, ldx, dx, lddx, M, N, K, rows_per_sample, ca, cb, k2, k3, cld, table,
+                                      table_ns, sm_limit, (cudaStream_t)stream);
+}
+
+DLB_API int dlb_dgrad_gn(int mode, const void* dy, long long lddy, const void* w, long long ldw, const void* x, long long ldx,
+                         void* dx, long long lddx, int M, int N, int K, int rows_per_sample, const float* ca, const float* cb,
+                         const float* k2, const float* k3, long long cld, float* table, long long table_ns, int sm_limit,
+                         void* stream) {
+  return dlb_dgrad_gn_dt(DLB_BF16, mode, dy, lddy, w, ldw, x, ldx, dx, lddx, M, N, K, rows_per_sample, ca, cb, k2, k3, cld, table,
+                         table_ns, sm_limit, stream);
 }
 
 DLB_API int dlb_gn_bwd_coeff(const float* table, long long table_ns, const float* gamma, const float* mean, const float* rstd,

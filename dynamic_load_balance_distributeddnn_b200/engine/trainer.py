@@ -101,7 +101,7 @@ class Trainer:
         if self.cuda:
             torch.cuda.manual_seed(cfg.seed + 1 + self.rank)
         # ---- balancer, injector, recorder ----
-        realloc_cls = AffineReallocator if cfg.dbs_model == "affine" else Reallocator
+        realloc_cls = AffineReallocator if cfg.resolved_dbs_model() == "affine" else Reallocator
         self.realloc = realloc_cls(self.world, cfg.batch_size, cfg.dynamic_batch_size, cfg.rounding,
                                    cfg.min_local_batch, cfg.batch_quantum, cfg.time_ema)
         self.injector = StragglerInjector(self.rank, cfg.fault_tolerance, cfg.fault_tolerance_chance,

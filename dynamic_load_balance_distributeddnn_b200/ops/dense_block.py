@@ -322,8 +322,7 @@ class _DenseBlockFn(torch.autograd.Function):
                 # (the wgrad re-applies GN+ReLU to the raw buffer slice in its operand prologue) and the GN1
                 # backward recomputes the ReLU mask from the saved affine coefficients.
                 w1_2d = gemm_tc._w2d(w1)                                            # [cm, cl], consumed MN-major: no transpose
-                fuse_dg = (gemm_tc.FUSED_DGRAD and hw % 32 == 0 and n * hw >= 128 and gemm_tc.dgrad_gn_available()
-                           and buf.dtype == torch.bfloat16)
+                fuse_dg = hw % 32 == 0 and n * hw >= 128 and gemm_tc.fused_dgrad_enabled(buf.dtype)
                 if not fuse_dg:
                     dxhat = torch.empty((n, cl, h, w), dtype=buf.dtype, device=buf.device, memory_format=torch.channels_last)
                     gemm_tc.gemm_bmn_raw(dy.data_ptr(), cm, w1_2d.data_ptr(), w1_2d.stride(0), dxhat.data_ptr(), cl, n * hw, cl, cm,
@@ -344,12 +343,12 @@ class _DenseBlockFn(torch.autograd.Function):
                     # experimental: the dgrad GEMM runs twice (K = cm is small) and dA never touches HBM --
                     # pass 1 accumulates the GroupNorm-backward sums in its epilogue, pass 2 applies them onto dX in place
                     gemm_tc.dgrad_gn_raw(1, dy.data_ptr(), cm, w1_2d.data_ptr(), w1_2d.stride(0), xs, ct, 0, 0, n * hw, cl, cm, hw,
-                                         ca, cb, None, None, t1.data_ptr(), 2 * cl, buf.device)
+                                         ca, cb, None, None, t1.data_ptr(), 2 * cl, buf.device, dtype=dt)
                     k23 = torch.empty((2, n, kpad), dtype=torch.float32, device=buf.device)
                     gemm_tc.gn_bwd_coeff_raw(t1.data_ptr(), 2 * cl, g1w, mean1, rstd1, k23[0], k23[1], dg1.data_ptr(), db1.data_ptr(),
                                              n, cl, groups, hw, buf.device)
                     gemm_tc.dgrad_gn_raw(2, dy.data_ptr(), cm, w1_2d.data_ptr(), w1_2d.stride(0), xs, ct, dxs, ct, n * hw, cl, cm, hw,
-                                         ca, cb, k23[0], k23[1], 0, 0, buf.device)
+                                         ca, cb, k23[0], k23[1], 0, 0, buf.device, dtype=dt)
                 else:
                     rc = 1
                     if _FUSED_GN_BWD:

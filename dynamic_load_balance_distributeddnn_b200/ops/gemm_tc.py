@@ -25,8 +25,8 @@ def _lib():
         nat.declare("dlb_conv3x3_tc_dt", i32, [i32, i32, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, vp, i64, i32, vp])
         nat.declare("dlb_wgrad3x3_tc_dt", i32, [i32, vp, i64, vp, i64, vp, i32, i32, i32, i32, i32, i32, vp])
         nat.declare("dlb_wgrad_tc_dt", i32, [i32, vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, vp, i64, i32, i32, vp])
-        nat.declare("dlb_dgrad_gn", i32, [i32, vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, i64, vp, i64,
-                                          i32, vp])
+        nat.declare("dlb_dgrad_gn_dt", i32, [i32, i32, vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, i64, vp, i64,
+                                             i32, vp])
         nat.declare("dlb_gn_bwd_coeff", i32, [vp, i64, vp, vp, vp, vp, vp, i64, vp, vp, i32, i32, i32, i32, vp])
         _DECLARED = True
     return lib
@@ -109,23 +109,31 @@ def wgrad(dy: torch.Tensor, x: torch.Tensor, pro_a=None, pro_b=None, rows_per_sa
     return dw
 
 
-# ---- dgrad GEMM fused with the GroupNorm(+ReLU) backward of its input, csrc/dgrad_gn.cu (bf16; DLB_FUSED_DGRAD=0 disables) ----
+# ---- dgrad GEMM fused with the GroupNorm(+ReLU) backward of its input, csrc/dgrad_gn.cu (DLB_FUSED_DGRAD=0 disables) ----
 # validated on B200 in round 2: kernel tests vs fp64, stage-level gradients no further from the fp32 truth than the
-# three-kernel chain (tests/test_gpu_experimental.py), -5 % step time at batch 512 and -6 % at batch 64
+# three-kernel chain (tests/test_gpu_dgrad_gn.py), -5 % step time at batch 512 and -6 % at batch 64 (bf16)
 FUSED_DGRAD = os.environ.get("DLB_FUSED_DGRAD", "1") == "1"
+# the fp32-storage / TF32-math flavour of the same kernels (DLB_FUSED_DGRAD_TF32=0 keeps tf32 on the chain)
+FUSED_DGRAD_TF32 = os.environ.get("DLB_FUSED_DGRAD_TF32", "1") == "1"
 
 
 def dgrad_gn_available() -> bool:
-    return available() and hasattr(nat.get(), "dlb_dgrad_gn")
+    return available() and hasattr(nat.get(), "dlb_dgrad_gn_dt")
+
+
+def fused_dgrad_enabled(dtype: torch.dtype) -> bool:
+    if not (FUSED_DGRAD and dgrad_gn_available()):
+        return False
+    return dtype == torch.bfloat16 or (dtype == torch.float32 and FUSED_DGRAD_TF32)
 
 
 def dgrad_gn_raw(mode: int, dy_ptr: int, lddy: int, w_ptr: int, ldw: int, x_ptr: int, ldx: int, dx_ptr: int, lddx: int,
                  m: int, n: int, k: int, rows_per_sample: int, ca: torch.Tensor, cb: torch.Tensor,
                  k2: Optional[torch.Tensor], k3: Optional[torch.Tensor], table_ptr: int, table_ns: int, device,
-                 sm_limit: int = 0) -> None:
+                 sm_limit: int = 0, dtype: int = nat.BF16) -> None:
     """mode 1: table += per-(sample, channel) (sum dz, sum dz*x) with dz = (dy @ w) * [ca*x + cb > 0];
     mode 2: dx += ca*dz + k2*x + k3 in place.  dy [m,k], w [k,n] row-major, x/dx [m,n] with free row strides."""
-    rc = _lib().dlb_dgrad_gn(mode, dy_ptr, lddy, w_ptr, ldw, x_ptr, ldx, dx_ptr, lddx, m, n, k, rows_per_sample, ca.data_ptr(),
+    rc = _lib().dlb_dgrad_gn_dt(dtype, mode, dy_ptr, lddy, w_ptr, ldw, x_ptr, ldx, dx_ptr, lddx, m, n, k, rows_per_sample, ca.data_ptr(),
                              cb.data_ptr(), nat.ptr(k2), nat.ptr(k3), ca.shape[1], table_ptr, table_ns, sm_limit,
                              nat.stream_ptr(device))
     nat.check(rc, f"dgrad_gn(mode {mode})")
@@ -182,7 +190,7 @@ WGRAD3 = os.environ.get("DLB_TC_WGRAD3", "1") == "1"
 
 def wgrad3x3_supported(n: int, h: int, w: int, ci: int, dtype: torch.dtype) -> bool:
     return (WGRAD3 and available() and hasattr(nat.get(), "dlb_wgrad3x3_tc_dt") and dtype in TC_DTYPES and conv3x3_geometry_ok(h, w)
-            and (n * h * w) % 128 == 0 and ci % (8 if dtype == torch.bfloat16 else 4) == 0)
+            and ci % (8 if dtype == torch.bfloat16 else 4) == 0)
 
 
 def wgrad3x3_raw(x_ptr: int, ldx: int, dy_ptr: int, lddy: int, dw: torch.Tensor, n: int, h: int, w: int, ci: int, co: int, device,
@@ -321,13 +329,55 @@ class _LinearFn(torch.autograd.Function):
         return dx, dw
 
 
+class _LinearPadFn(torch.autograd.Function):
+    """Small classifier heads (N = 10 / 100 outputs: not a multiple of the 16-byte vector) on the same tcgen05 GEMMs: the flat
+    parameter store keeps zero rows behind such a matrix up to a multiple of 8 (``_dlb_padded_rows``), so the weight is
+    consumed as an aligned [Np, K] operand, the output / its gradient live in [T, Np] buffers and the caller sees the
+    first N columns (reference classifier heads: Net/Densenet.py:83, Net/Resnet.py:87, Net/RegNet.py:104)."""
+
+    @staticmethod
+    def forward(ctx, x2, weight, n_pad):
+        t, k = x2.shape
+        n = weight.shape[0]
+        wp = torch.as_strided(weight, (n_pad, k), (weight.stride(0), 1))
+        y = torch.empty((t, n_pad), dtype=x2.dtype, device=x2.device)
+        gemm_raw(x2.data_ptr(), x2.stride(0), wp.data_ptr(), wp.stride(0), y.data_ptr(), n_pad, t, n_pad, k, x2.device,
+                 dtype=nat.dtype_code(x2.dtype))
+        ctx.save_for_backward(x2, wp)
+        ctx.n = n
+        return y[:, :n]
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, wp = ctx.saved_tensors
+        t, k = x2.shape
+        n, n_pad = ctx.n, wp.shape[0]
+        dyp = torch.zeros((t, n_pad), dtype=x2.dtype, device=x2.device)
+        dyp[:, :n].copy_(dy)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((t, k), dtype=x2.dtype, device=x2.device)
+            gemm_bmn_raw(dyp.data_ptr(), n_pad, wp.data_ptr(), wp.stride(0), dx.data_ptr(), k, t, k, n_pad, x2.device,
+                         dtype=nat.dtype_code(x2.dtype))
+        if ctx.needs_input_grad[1]:
+            dwf = torch.zeros((n_pad, k), dtype=torch.float32, device=x2.device)
+            wgrad_raw(dyp.data_ptr(), n_pad, x2.data_ptr(), x2.stride(0), dwf, t, n_pad, k, x2.device, dtype=nat.dtype_code(x2.dtype))
+            dw = dwf[:n].to(wp.dtype)
+        return dx, dw, None
+
+
 def linear_supported(x, weight) -> bool:
     if not available() or x.dtype not in TC_DTYPES or weight.dtype != x.dtype or weight.dim() != 2:
         return False
     n, k = weight.shape
     v = 8 if x.dtype == torch.bfloat16 else 4
     tokens = x.numel() // max(1, x.shape[-1])
-    return k % v == 0 and n % v == 0 and tokens >= 128 and weight.stride(1) == 1 and weight.stride(0) % v == 0
+    if n % v != 0:
+        # small heads: only through the zero-padded rows of the flat parameter store (see _LinearPadFn)
+        n_pad = int(getattr(weight, "_dlb_padded_rows", 0))
+        return (n_pad >= n and n_pad % v == 0 and k % v == 0 and tokens >= 32 and weight.stride(1) == 1 and weight.stride(0) == k
+                and weight.is_contiguous())
+    return k % v == 0 and tokens >= 128 and weight.stride(1) == 1 and weight.stride(0) % v == 0
 
 
 def linear(x, weight, bias=None):
@@ -335,7 +385,13 @@ def linear(x, weight, bias=None):
     x2 = x.reshape(-1, k)
     if x2.stride(1) != 1 or x2.stride(0) % (8 if x2.dtype == torch.bfloat16 else 4) != 0 or (x2.data_ptr() & 15):
         x2 = x2.contiguous()
-    y = _LinearFn.apply(x2, weight).view(*x.shape[:-1], weight.shape[0])
+    n = weight.shape[0]
+    if n % (8 if x2.dtype == torch.bfloat16 else 4) != 0:
+        y = _LinearPadFn.apply(x2, weight, int(weight._dlb_padded_rows))            # [T, N] view of a [T, Np] buffer
+        if bias is not None:
+            y = y + bias.to(y.dtype)
+        return y.reshape(*x.shape[:-1], n)
+    y = _LinearFn.apply(x2, weight).view(*x.shape[:-1], n)
     if bias is not None:
         y = y + bias.to(y.dtype)
     return y

@@ -53,4 +53,9 @@ def test_dbs_model_and_profile_extension_flags():
     from dynamic_load_balance_distributeddnn_b200.cli import config_from_args
     cfg = config_from_args(["-ws", "2", "--dbs_model", "affine", "--profile", "true"])
     assert cfg.dbs_model == "affine" and cfg.profile is True
-    assert config_from_args([]).dbs_model == "proportional"
+    base = config_from_args([])
+    assert base.dbs_model == "auto"
+    # auto: the reference's rule in CPU debug mode, the latency-aware model on CUDA devices
+    assert config_from_args(["-d", "true"]).resolved_dbs_model() == "proportional"
+    assert config_from_args(["-d", "false"]).resolved_dbs_model() == "affine"
+    assert config_from_args(["-d", "false", "--dbs_model", "proportional"]).resolved_dbs_model() == "proportional"

@@ -18,12 +18,20 @@ def g():
     return gemm_tc
 
 
-def _problem(ns, hw, cl, cm, ct, seed):
+DTYPES = [torch.bfloat16, torch.float32]      # fp32 storage = TF32 math (kind::tf32)
+
+
+def _code(dtype):
+    from dynamic_load_balance_distributeddnn_b200.ops import _native as nat
+    return nat.dtype_code(dtype)
+
+
+def _problem(ns, hw, cl, cm, ct, seed, dtype=torch.bfloat16):
     torch.manual_seed(seed)
     m = ns * hw
-    dy = torch.randn(m, cm, device="cuda").bfloat16()
-    w = (torch.randn(cm, cl, device="cuda") / cm ** 0.5).bfloat16()
-    big = torch.randn(m, ct, device="cuda").bfloat16()
+    dy = torch.randn(m, cm, device="cuda").to(dtype)
+    w = (torch.randn(cm, cl, device="cuda") / cm ** 0.5).to(dtype)
+    big = torch.randn(m, ct, device="cuda").to(dtype)
     off = ct - cl
     kp = (cl + 63) // 64 * 64
     ca = torch.zeros(ns, kp, device="cuda"); cb = torch.zeros(ns, kp, device="cuda")
@@ -36,7 +44,7 @@ def _problem(ns, hw, cl, cm, ct, seed):
         near = (z.abs() < 1e-3).view(m, cl)
         if not near.any():
             break
-        x[near] = (x[near].float() + 1.0).bfloat16()
+        x[near] = (x[near].float() + 1.0).to(dtype)
     return dy, w, big, off, ca, cb, kp
 
 
@@ -50,31 +58,35 @@ def _reference(dy, w, x, ca, cb, ns, hw, cl):
 
 @pytest.mark.parametrize("ns,hw,cl,cm,ct", [(4, 64, 96, 128, 160), (2, 1024, 256, 128, 256), (4, 32, 64, 128, 64), (9, 32, 72, 128, 72),
                                             (5, 256, 200, 128, 328), (2, 64, 1000, 128, 1024), (16, 256, 416, 64, 512)])
-def test_dgrad_gn_stats_pass(g, ns, hw, cl, cm, ct):
-    dy, w, big, off, ca, cb, kp = _problem(ns, hw, cl, cm, ct, ns + hw + cl)
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dgrad_gn_stats_pass(g, dtype, ns, hw, cl, cm, ct):
+    dy, w, big, off, ca, cb, kp = _problem(ns, hw, cl, cm, ct, ns + hw + cl, dtype)
     x = big[:, off:]
     table = torch.zeros(ns, cl, 2, device="cuda")
     g.dgrad_gn_raw(1, dy.data_ptr(), cm, w.data_ptr(), cl, x.data_ptr(), ct, 0, 0, ns * hw, cl, cm, hw, ca, cb, None, None,
-                   table.data_ptr(), 2 * cl, dy.device)
+                   table.data_ptr(), 2 * cl, dy.device, dtype=_code(dtype))
     torch.cuda.synchronize()
     _, ref = _reference(dy, w, x, ca, cb, ns, hw, cl)
     scale = ref.abs().max().item()
-    assert (table.double() - ref).abs().max().item() < 2e-3 * scale, ((table.double() - ref).abs().max().item(), scale)
+    # bf16 operands are exact in the tensor core (fp32 accumulate); TF32 rounds the fp32 operands to 10 mantissa bits
+    tol = 2e-3 if dtype == torch.bfloat16 else 6e-3
+    assert (table.double() - ref).abs().max().item() < tol * scale, ((table.double() - ref).abs().max().item(), scale)
 
 
 @pytest.mark.parametrize("ns,hw,cl,cm,ct", [(4, 64, 96, 128, 160), (2, 1024, 256, 128, 256), (4, 32, 64, 128, 64), (9, 32, 72, 128, 72),
                                             (5, 256, 200, 128, 328), (2, 64, 1000, 128, 1024)])
-def test_dgrad_gn_apply_pass(g, ns, hw, cl, cm, ct):
-    dy, w, big, off, ca, cb, kp = _problem(ns, hw, cl, cm, ct, 7 + ns + hw + cl)
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dgrad_gn_apply_pass(g, dtype, ns, hw, cl, cm, ct):
+    dy, w, big, off, ca, cb, kp = _problem(ns, hw, cl, cm, ct, 7 + ns + hw + cl, dtype)
     x = big[:, off:]
     k2 = torch.zeros(ns, kp, device="cuda"); k3 = torch.zeros(ns, kp, device="cuda")
     k2[:, :cl] = torch.randn(ns, cl, device="cuda") * 0.1
     k3[:, :cl] = torch.randn(ns, cl, device="cuda") * 0.1
-    dbig = torch.randn(ns * hw, ct, device="cuda").bfloat16()
+    dbig = torch.randn(ns * hw, ct, device="cuda").to(dtype)
     before = dbig.clone()
     dx = dbig[:, off:]
     g.dgrad_gn_raw(2, dy.data_ptr(), cm, w.data_ptr(), cl, x.data_ptr(), ct, dx.data_ptr(), ct, ns * hw, cl, cm, hw, ca, cb, k2, k3,
-                   0, 0, dy.device)
+                   0, 0, dy.device, dtype=_code(dtype))
     torch.cuda.synchronize()
     dz, _ = _reference(dy, w, x, ca, cb, ns, hw, cl)
     xv = x.double().view(ns, hw, cl)
@@ -113,16 +125,19 @@ def test_gn_bwd_coeff_matches_apply_kernel_math(g):
     assert torch.allclose(dg.double(), xh.sum(0), atol=1e-3, rtol=1e-4)
 
 
-def test_dense_block_backward_with_fused_dgrad(g):
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dense_block_backward_with_fused_dgrad(g, dtype):
     """Whole dense stage: gradients with the fused dgrad+GN-backward path == the validated three-kernel chain."""
     from dynamic_load_balance_distributeddnn_b200.models import densenet
     torch.manual_seed(0)
     stage = densenet.DenseNet([4], growth_rate=32, num_classes=10).dense1.cuda()
     for m in stage.modules():
         if isinstance(m, torch.nn.Conv2d):
-            m.weight.data = m.weight.data.bfloat16()
-    x0 = torch.randn(8, 64, 16, 16, device="cuda").contiguous(memory_format=torch.channels_last).bfloat16()
+            m.weight.data = m.weight.data.to(dtype)
+    x0 = torch.randn(8, 64, 16, 16, device="cuda").contiguous(memory_format=torch.channels_last).to(dtype)
     outs = []
+    saved = (g.FUSED_DGRAD, g.FUSED_DGRAD_TF32)
+    g.FUSED_DGRAD_TF32 = True
     try:
         for fused in (False, True):
             g.FUSED_DGRAD = fused
@@ -130,12 +145,12 @@ def test_dense_block_backward_with_fused_dgrad(g):
                 p.grad = None
             x = x0.clone().requires_grad_(True)
             y = stage(x)
-            gy = torch.randn(y.shape, device="cuda", generator=torch.Generator("cuda").manual_seed(5)).bfloat16()
+            gy = torch.randn(y.shape, device="cuda", generator=torch.Generator("cuda").manual_seed(5)).to(dtype)
             y.backward(gy)
             torch.cuda.synchronize()
             outs.append((x.grad.float(), [p.grad.float().clone() for p in stage.parameters()]))
     finally:
-        g.FUSED_DGRAD = False
+        g.FUSED_DGRAD, g.FUSED_DGRAD_TF32 = saved
     (dx0, g0), (dx1, g1) = outs
     assert float((dx0 - dx1).abs().max()) < 4e-2 * max(1.0, float(dx0.abs().max()))
     # parameter gradients: both paths against a plain fp32 torch evaluation of the same stage on the same (bf16-valued) weights.

@@ -198,7 +198,7 @@ def test_conv3x3_strided_io_and_stats(g):
 
 @pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 1e-2), (torch.float32, 4e-3)])
 @pytest.mark.parametrize("n,ci,co,hw", [(8, 128, 32, 32), (6, 128, 32, 16), (16, 128, 32, 8), (32, 128, 32, 4), (4, 64, 64, 32),
-                                         (8, 96, 160, 16), (4, 256, 256, 8)])
+                                         (8, 96, 160, 16), (4, 256, 256, 8), (67, 128, 32, 4), (21, 128, 32, 8), (5, 96, 32, 4)])
 def test_wgrad3x3_tcgen05(g, dtype, tol, n, ci, co, hw):
     """9-tap MN-major split-K weight gradient (csrc/conv_wgrad.cu): x and dy are channel slices of wider NHWC buffers"""
     torch.backends.cudnn.allow_tf32 = False
@@ -218,3 +218,28 @@ def test_wgrad3x3_tcgen05(g, dtype, tol, n, ci, co, hw):
     ref = wr.grad.permute(0, 2, 3, 1)                  # [co][3][3][ci]
     err = (dw - ref).abs().max().item()
     assert err < tol * max(1.0, ref.abs().max().item()), (err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 3e-2), (torch.float32, 5e-3)])
+@pytest.mark.parametrize("t,n,k", [(512, 10, 1024), (64, 10, 1024), (200, 100, 384), (48, 10, 512)])
+def test_small_classifier_head_on_tcgen05(g, dtype, tol, t, n, k):
+    """N = 10 / 100 heads through the zero rows the flat parameter store keeps behind the matrix (_LinearPadFn)"""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(t + n)
+    n_pad = (n + 7) // 8 * 8
+    store = torch.zeros(n_pad * k + 64, device="cuda", dtype=dtype)
+    w = torch.nn.Parameter(store[:n * k].view(n, k))
+    w.data.copy_((torch.randn(n, k, device="cuda") / k ** 0.5).to(dtype))
+    w._dlb_padded_rows = n_pad
+    x = torch.randn(t, k, device="cuda").to(dtype).requires_grad_(True)
+    b = torch.randn(n, device="cuda").to(dtype).requires_grad_(True)
+    assert g.linear_supported(x, w)
+    y = g.linear(x, w, b)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xr, wr, br = (v.detach().float().requires_grad_(True) for v in (x, w, b))
+    yr = torch.nn.functional.linear(xr, wr, br)
+    yr.backward(gy.float())
+    assert (y.float() - yr).abs().max().item() < tol * max(1.0, yr.abs().max().item())
+    assert (x.grad.float() - xr.grad).abs().max().item() < tol * max(1.0, xr.grad.abs().max().item())
+    assert (w.grad.float() - wr.grad).abs().max().item() < tol * max(1.0, wr.grad.abs().max().item())
