@@ -20,6 +20,7 @@ static int g_skip_zero = 0;      // callers that pre-zero one big arena set this
 // rows in flight per thread (independent 16-byte loads issued before the first use) of the streaming kernels; tunable at run
 // time for sweeps (dlb_norm_tune / DLB_GN_UNR_{RED,FWD,BWD}); defaults are the measured optimum on B200
 static int g_unr_red = 0, g_unr_fwd = 0, g_unr_bwd = 0, g_min_kb = 0;
+static int g_bulk_on = -1, g_bulk_kb = 64;   // fused backward: bulk-copy flavour (DLB_GN_BWD_BULK / DLB_GN_BULK_KB, dlb_norm_bulk)
 static int unr_env(const char* name, int dflt) {
   const char* e = getenv(name);
   const int v = e ? atoi(e) : dflt;
@@ -639,6 +640,194 @@ gn_bwd_fused_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Bulk-copy (TMA unit, cp.async.bulk) flavour of the fused backward: the block's rows of x, dy (and dX when accumulating) are
+// fetched by asynchronous bulk copies into shared memory -- one copy per row per tensor, issued up front by one warp and
+// tracked by a single mbarrier -- so the bytes in flight are bounded by the tile (tens of KB per block) instead of by
+// registers x resident warps (2 x 16 B per thread in the register flavour: ~64 KB per SM at full occupancy, less than the
+// ~52 KB x latency product HBM3e needs once anything else limits occupancy).  Both phases then compute out of shared memory,
+// the dX tile is updated in place and written back with bulk stores: x and dy cross the memory system once, not twice.
+__device__ __forceinline__ uint32_t gn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gn_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void gn_bulk_store(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+template <typename T, int V, bool ACC>
+__global__ void __launch_bounds__(kThreads)
+gn_bwd_bulk_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy, T* __restrict__ dx, int64_t lddx,
+                   const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                   float* __restrict__ table, int64_t table_ns, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                   const float* __restrict__ coef_a, const float* __restrict__ coef_b, int64_t coef_ld,
+                   unsigned* __restrict__ done, int HW, int C, int G, int rows_per_block) {
+  extern __shared__ __align__(16) float smem[];   // [acc 2C | k1 k2 k3 s1 s2][mbarrier][x tile][dy tile][dX tile]
+  const int n = blockIdx.y, cpg = C / G;
+  const int lanes = C / V;                        // <= kThreads (checked by the host)
+  const int row_lanes = kThreads / lanes;
+  const int lane = threadIdx.x % lanes, rl = threadIdx.x / lanes;
+  const bool active = rl < row_lanes;
+  const int c = lane * V;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(HW, r0 + rows_per_block);
+  const int nrows = r1 - r0;
+  const uint32_t row_bytes = (uint32_t)C * sizeof(T);
+  uint8_t* base = reinterpret_cast<uint8_t*>(smem) + ((((size_t)(3 * C + 2 * G) * 4) + 15) & ~(size_t)15);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(base);
+  uint8_t* tile_x = base + 16;
+  uint8_t* tile_g = tile_x + (size_t)rows_per_block * row_bytes;
+  uint8_t* tile_d = tile_g + (size_t)rows_per_block * row_bytes;
+  const uint32_t bar_a = gn_smem_u32(bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1u) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 2 * C; i += kThreads) smem[i] = 0.f;
+  __syncthreads();
+  dlb_pdl_wait();                                 // nothing above reads what the previous kernel wrote
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)nrows * row_bytes * (ACC ? 3u : 2u)) : "memory");
+    __syncwarp();
+    for (int r = threadIdx.x; r < nrows; r += 32) {
+      const int64_t row = (int64_t)n * HW + r0 + r;
+      gn_bulk_load(gn_smem_u32(tile_x + (size_t)r * row_bytes), x + row * ldx, row_bytes, bar_a);
+      gn_bulk_load(gn_smem_u32(tile_g + (size_t)r * row_bytes), dy + row * lddy, row_bytes, bar_a);
+      if constexpr (ACC) gn_bulk_load(gn_smem_u32(tile_d + (size_t)r * row_bytes), dx + row * lddx, row_bytes, bar_a);
+    }
+  }
+  float ka[V], kb[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { ka[i] = coef_a[(int64_t)n * coef_ld + c + i]; kb[i] = coef_b[(int64_t)n * coef_ld + c + i]; }
+  {                                               // wait for the tiles (watchdog instead of a hang)
+    uint32_t ok = 0, spins = 0;
+    while (true) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(bar_a), "r"(0u) : "memory");
+      if (ok) break;
+      if (++spins > (1u << 22)) __trap();
+    }
+  }
+  // ---- phase 1: per-(n, c) sums of dz and dz*x over this block's rows ----
+  if (active) {
+    float a0[V], a1[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { a0[i] = 0.f; a1[i] = 0.f; }
+    for (int r = rl; r < nrows; r += row_lanes) {
+      float xv[V], gv[V];
+      load_vec<T, V>(reinterpret_cast<const T*>(tile_x + (size_t)r * row_bytes) + c, xv);
+      load_vec<T, V>(reinterpret_cast<const T*>(tile_g + (size_t)r * row_bytes) + c, gv);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float gz = fmaf(ka[i], xv[i], kb[i]) > 0.f ? gv[i] : 0.f;
+        a0[i] += gz; a1[i] += gz * xv[i];
+      }
+    }
+    bool owner = true;
+    if (lanes < 32 && (lanes & (lanes - 1)) == 0) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        for (int o = lanes; o < 32; o <<= 1) {
+          a0[i] += __shfl_xor_sync(0xffffffffu, a0[i], o);
+          a1[i] += __shfl_xor_sync(0xffffffffu, a1[i], o);
+        }
+      }
+      owner = (threadIdx.x & 31) < lanes;
+    }
+    if (owner) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        atomicAdd(&smem[2 * (c + i)], a0[i]);
+        atomicAdd(&smem[2 * (c + i) + 1], a1[i]);
+      }
+    }
+  }
+  __syncthreads();
+  float* tab = table + (int64_t)n * table_ns;
+  for (int i = threadIdx.x; i < 2 * C; i += kThreads) atomicAdd(&tab[i], smem[i]);
+  // ---- per-sample barrier (same protocol as gn_bwd_fused_kernel) ----
+  __shared__ unsigned s_ticket;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s_ticket = atomicAdd(&done[n], 1u);
+    unsigned spins = 0;
+    while (true) {
+      unsigned v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(done + n) : "memory");
+      if (v >= gridDim.x) break;
+      if (++spins > (1u << 24)) __trap();
+    }
+  }
+  __syncthreads();
+  if (dgamma != nullptr && s_ticket == gridDim.x - 1) {
+    for (int cc = threadIdx.x; cc < C; cc += kThreads) {
+      const float A = __ldcg(tab + 2 * cc), B = __ldcg(tab + 2 * cc + 1);
+      const int g = cc / cpg;
+      atomicAdd(&dbeta[cc], A);
+      atomicAdd(&dgamma[cc], rstd[n * G + g] * (B - mean[n * G + g] * A));
+    }
+  }
+  // ---- phase 2: dX tile (+)= k1*dz + k2*x + k3, in shared memory, then bulk stores ----
+  float* k1 = smem;
+  float* k2 = smem + C;
+  float* k3 = smem + 2 * C;
+  float* s1 = smem + 3 * C;
+  float* s2 = s1 + G;
+  for (int g = threadIdx.x; g < G; g += kThreads) {
+    const float mu = mean[n * G + g], r = rstd[n * G + g];
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < cpg; ++i) {
+      const int cc = g * cpg + i;
+      const float A = __ldcg(tab + 2 * cc), B = __ldcg(tab + 2 * cc + 1);
+      a += gamma[cc] * A;
+      b += gamma[cc] * r * (B - mu * A);
+    }
+    s1[g] = a;
+    s2[g] = b;
+  }
+  __syncthreads();
+  const float inv_m = 1.f / ((float)cpg * (float)HW);
+  for (int cc = threadIdx.x; cc < C; cc += kThreads) {
+    const int g = cc / cpg;
+    const float mu = mean[n * G + g], r = rstd[n * G + g];
+    k1[cc] = gamma[cc] * r;
+    const float q = r * r * s2[g] * inv_m;
+    k2[cc] = -q;
+    k3[cc] = -r * s1[g] * inv_m + q * mu;
+  }
+  __syncthreads();
+  if (active) {
+    float q1[V], q2[V], q3[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) { q1[k] = k1[c + k]; q2[k] = k2[c + k]; q3[k] = k3[c + k]; }
+    for (int r = rl; r < nrows; r += row_lanes) {
+      float xv[V], gv[V], out[V];
+      load_vec<T, V>(reinterpret_cast<const T*>(tile_x + (size_t)r * row_bytes) + c, xv);
+      load_vec<T, V>(reinterpret_cast<const T*>(tile_g + (size_t)r * row_bytes) + c, gv);
+      T* drow = reinterpret_cast<T*>(tile_d + (size_t)r * row_bytes) + c;
+      if constexpr (ACC) load_vec<T, V>(drow, out);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float gz = fmaf(ka[k], xv[k], kb[k]) > 0.f ? gv[k] : 0.f;
+        const float v = fmaf(q1[k], gz, fmaf(q2[k], xv[k], q3[k]));
+        out[k] = ACC ? out[k] + v : v;
+      }
+      store_vec<T, V>(drow, out);
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the bulk-copy engine
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    for (int r = threadIdx.x; r < nrows; r += 32)
+      gn_bulk_store(dx + ((int64_t)n * HW + r0 + r) * lddx, gn_smem_u32(tile_d + (size_t)r * row_bytes), row_bytes);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // shared memory must outlive the reads of the copy engine
+  }
+}
+
 // dgamma[c] = sum_n rstd*(B - mu*A), dbeta[c] = sum_n A.   Block = 32 channels x 8 sample-lanes.
 __global__ void __launch_bounds__(256) gn_param_grad_kernel(const float* __restrict__ table, int64_t table_ns, const float* __restrict__ mean,
                                      const float* __restrict__ rstd, float* __restrict__ dgamma,
@@ -782,6 +971,11 @@ DLB_API void dlb_norm_tune(int unr_red, int unr_fwd, int unr_bwd) {
   if (unr_bwd == 1 || unr_bwd == 2 || unr_bwd == 4) g_unr_bwd = unr_bwd;
 }
 DLB_API void dlb_norm_tune_kb(int min_kb) { if (min_kb > 0) g_min_kb = min_kb; }
+// fused GroupNorm backward: bulk-copy (TMA unit) flavour on/off (-1 keeps) and its tile budget in KB per block (0 keeps)
+DLB_API void dlb_norm_bulk(int on, int tile_kb) {
+  if (on == 0 || on == 1) g_bulk_on = on;
+  if (tile_kb >= 8 && tile_kb <= 190) g_bulk_kb = tile_kb;
+}
 
 // table: fp32 [N][table_ns] with (q0,q1) pairs for C channels starting at `table`; zeroed here.
 DLB_API int dlb_nc_reduce2(int mode, int dtype, const void* x, int64_t ldx, const void* dy, int64_t lddy,
@@ -869,10 +1063,45 @@ DLB_API int dlb_gn_bwd_fused(int dtype, const void* x, int64_t ldx, const void* 
     rpb = (HW + chunks - 1) / chunks;
     grid = dim3(chunks, N, 1);
   }
+  cudaStream_t st = (cudaStream_t)stream;
+  // bulk-copy flavour (DLB_GN_BWD_BULK=0 disables): tiles of <= DLB_GN_BULK_KB (default 64) KB per block
+  if (g_bulk_on < 0) {
+    const char* e = getenv("DLB_GN_BWD_BULK"); g_bulk_on = (e && atoi(e) == 0) ? 0 : 1;
+    const char* k = getenv("DLB_GN_BULK_KB"); if (k && atoi(k) >= 8 && atoi(k) <= 190) g_bulk_kb = atoi(k);
+  }
+  const int bulk_on = g_bulk_on, bulk_kb = g_bulk_kb;
+  if (bulk_on && !stage) {
+    const size_t row_all = (size_t)C * esz * (acc ? 3 : 3);          // the dX tile exists in both flavours (written in place)
+    int R = (int)(((size_t)bulk_kb * 1024) / row_all);
+    if (R > HW) R = HW;
+    if (R >= 1) {
+      int chunks = (HW + R - 1) / R;
+      // small problems: at least ~2 blocks per SM as long as a block keeps >= 4 rows
+      const int want = (2 * 148 + N - 1) / N;
+      if (chunks < want) chunks = want;
+      if (chunks > HW / 4) chunks = HW / 4 > 0 ? HW / 4 : 1;
+      R = (HW + chunks - 1) / chunks;
+      chunks = (HW + R - 1) / R;
+      const size_t coef_b = (((size_t)(3 * C + 2 * G) * sizeof(float)) + 15) & ~(size_t)15;
+      const size_t smb = coef_b + 16 + 3 * (size_t)R * C * esz;
+      if (chunks <= 64 && smb <= 196 * 1024) {
+        dim3 g2(chunks, N, 1);
+#define BGO(TT, VV, AC)                                                                                                          \
+  do {                                                                                                                           \
+    static bool cfgd = false;                                                                                                    \
+    if (!cfgd) { cudaFuncSetAttribute(gn_bwd_bulk_kernel<TT, VV, AC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); cfgd = true; } \
+    dlb_launch(gn_bwd_bulk_kernel<TT, VV, AC>, g2, dim3(kThreads), smb, st, (const TT*)x, (int64_t)ldx, (const TT*)dy, (int64_t)lddy, (TT*)dx, (int64_t)lddx, gamma, mean, rstd, table, (int64_t)table_ns, dgamma, dbeta, ca, cb, (int64_t)cld, (unsigned*)done, HW, C, G, R); \
+  } while (0)
+        if (dtype == DLB_BF16) { if (acc) BGO(__nv_bfloat16, 8, true); else BGO(__nv_bfloat16, 8, false); }
+        else { if (acc) BGO(float, 4, true); else BGO(float, 4, false); }
+#undef BGO
+        return dlb_post_launch();
+      }
+    }
+  }
   if (grid.x > 64) return 1;                 // keep a sample's blocks trivially co-resident
   const size_t coef_bytes = (((size_t)(3 * C + 2 * G) * sizeof(float)) + 15) & ~(size_t)15;
   const size_t sm = coef_bytes + (stage ? (size_t)rpb * row_pair : 0);
-  cudaStream_t st = (cudaStream_t)stream;
 #define FGO(TT, VV, AC)                                                                                                          \
   do {                                                                                                                           \
     if (stage) {                                                                                                                 \

@@ -59,6 +59,7 @@ def _declare(lib: ctypes.CDLL) -> None:
         "dlb_gn_bwd_fused": (i32, [i32, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, vp]),
         "dlb_copy_stats": (i32, [i32, vp, i64, vp, i64, vp, i64, i32, i32, i32, vp]),
         "dlb_norm_skip_zero": (None, [i32]),
+        "dlb_norm_bulk": (None, [i32, i32]),
         "dlb_gn_coeff": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, c_float, vp]),
         "dlb_gn_fwd_apply": (i32, [i32, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
         "dlb_gn_bwd_apply": (i32, [i32, vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, i64,

@@ -32,7 +32,54 @@ def timeit(fn, iters=5):
     return min(ts)
 
 
+def gnbwd():
+    """fused GroupNorm backward (one launch: reduce + per-sample barrier + apply): register flavour vs bulk-copy flavour at
+    several tile budgets, DenseNet-121 shapes (x / dX = channel slices of the block buffer, accumulate) and the bottleneck
+    shape (C = 128, fresh output).  Traffic model: x + dy read once, dX read + written (4 passes; 3 without accumulation)."""
+    lib = nat.require()
+    st = nat.stream_ptr()
+    out = []
+    shapes = [(512, 1024, 128, 128, 0), (512, 1024, 224, 256, 1), (512, 256, 128, 128, 0), (512, 256, 480, 512, 1), (512, 64, 128, 128, 0),
+              (512, 64, 992, 1024, 1), (64, 1024, 224, 256, 1), (64, 256, 480, 512, 1), (64, 64, 992, 1024, 1), (64, 64, 128, 128, 0)]
+    for dname, dtype in (("tf32", torch.float32), ("bf16", torch.bfloat16)):
+        for (n, hw, c, ct, acc) in shapes:
+            xb = torch.randn(n, hw, ct, device="cuda").to(dtype); db_ = torch.randn(n, hw, ct, device="cuda").to(dtype)
+            x, dx = xb[..., ct - c:], db_[..., ct - c:]
+            dy = torch.randn(n, hw, c, device="cuda").to(dtype)
+            gamma = torch.ones(c, device="cuda"); mean = torch.zeros(n * 32, device="cuda"); rstd = torch.ones(n * 32, device="cuda")
+            kp = (c + 63) // 64 * 64
+            ca = torch.ones(n, kp, device="cuda"); cb = torch.zeros(n, kp, device="cuda")
+            table = torch.zeros(n, 2 * c, device="cuda"); dg = torch.zeros(c, device="cuda"); dbt = torch.zeros(c, device="cuda")
+            done = torch.zeros(n, dtype=torch.int32, device="cuda")
+            nbytes = n * hw * c * x.element_size()
+            traffic = (4 if acc else 3) * nbytes
+
+            def run():
+                done.zero_()
+                rc = lib.dlb_gn_bwd_fused(nat.dtype_code(dtype), x.data_ptr(), ct, dy.data_ptr(), c, dx.data_ptr(), ct, gamma.data_ptr(),
+                                          mean.data_ptr(), rstd.data_ptr(), table.data_ptr(), 0, dg.data_ptr(), dbt.data_ptr(),
+                                          ca.data_ptr(), cb.data_ptr(), kp, done.data_ptr(), n, hw, c, 32, acc, st)
+                assert rc in (0, 1), rc
+                return rc
+            line = f"{dname} N={n:4d} HW={hw:5d} C={c:4d}/{ct:4d} acc={acc} ({traffic / 1e6:7.1f} MB):"
+            for tag, on, kb in (("reg", 0, 0), ("bulk32", 1, 32), ("bulk48", 1, 48), ("bulk64", 1, 64), ("bulk96", 1, 96)):
+                lib.dlb_norm_bulk(on, kb)
+                if run() == 1:
+                    line += f"  {tag} n/a"
+                    continue
+                ms = timeit(run)
+                gbs = traffic / ms / 1e6
+                out.append((dname, n, hw, c, ct, acc, tag, ms * 1e3, gbs / PEAK))
+                line += f"  {tag} {ms * 1e3:6.1f}us {100 * gbs / PEAK:4.0f}%"
+            lib.dlb_norm_bulk(1, 64)
+            print(line, flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "gn_bwd_flavours.json"), "w"))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "gnbwd":
+        return gnbwd()
     lib = nat.require()
     st = nat.stream_ptr()
     rows = []
