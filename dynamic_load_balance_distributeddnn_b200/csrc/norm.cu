@@ -1064,9 +1064,13 @@ DLB_API int dlb_gn_bwd_fused(int dtype, const void* x, int64_t ldx, const void* 
     grid = dim3(chunks, N, 1);
   }
   cudaStream_t st = (cudaStream_t)stream;
-  // bulk-copy flavour (DLB_GN_BWD_BULK=0 disables): tiles of <= DLB_GN_BULK_KB (default 64) KB per block
+  // bulk-copy flavour (opt-in, DLB_GN_BWD_BULK=1): tiles of <= DLB_GN_BULK_KB (default 64) KB per block
   if (g_bulk_on < 0) {
-    const char* e = getenv("DLB_GN_BWD_BULK"); g_bulk_on = (e && atoi(e) == 0) ? 0 : 1;
+    // measured on B200 (profiles/r2_09_gn_bwd_flavours.txt): the bulk flavour LOSES to the register flavour at every DenseNet
+    // shape (tf32 batch 512: 27-45 % vs 52-57 % of the copy peak; step 28.9 vs 26.9 ms) -- one bulk copy per 0.5-4 KB row is
+    // too fine-grained for the copy engine and the small tiles multiply the per-block preamble and per-sample barrier
+    // (ncu: 6 400 blocks, 14 waves, DRAM 22 %).  Opt-in: DLB_GN_BWD_BULK=1.
+    const char* e = getenv("DLB_GN_BWD_BULK"); g_bulk_on = (e && atoi(e) == 1) ? 1 : 0;
     const char* k = getenv("DLB_GN_BULK_KB"); if (k && atoi(k) >= 8 && atoi(k) <= 190) g_bulk_kb = atoi(k);
   }
   const int bulk_on = g_bulk_on, bulk_kb = g_bulk_kb;

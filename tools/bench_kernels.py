@@ -71,7 +71,7 @@ def gnbwd():
                 gbs = traffic / ms / 1e6
                 out.append((dname, n, hw, c, ct, acc, tag, ms * 1e3, gbs / PEAK))
                 line += f"  {tag} {ms * 1e3:6.1f}us {100 * gbs / PEAK:4.0f}%"
-            lib.dlb_norm_bulk(1, 64)
+            lib.dlb_norm_bulk(0, 64)
             print(line, flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "gn_bwd_flavours.json"), "w"))
