@@ -11,7 +11,8 @@ when N > 1 so the DBS rebalancer has something to do.
 BOTH arms run the same schedule (W = max(5, --warmup) steps per phase):
 
     N = 1 (or --no-dbs):  W warm-up steps                                   -> K timed steps
-    N > 1 with DBS:       R x [W steps -> exchange compute times -> re-split]  (R = --dbs-rounds, default 2)
+    N > 1 with DBS:       R x [S steps -> exchange compute times -> re-split]  (R = --dbs-rounds, default 3; S = --dbs-steps,
+                          default 10: the first steps at a new local batch are capture / warm-up and not part of the signal)
                           -> W warm-up steps at the final split              -> K timed steps at that split
 
 Own arm: two timed regions of exactly K steps each, both bracketed by barrier + cuda synchronize and timed with CUDA
@@ -64,6 +65,7 @@ def parse():
                         "always uses its own injector's mechanism (a host sleep between backward and allreduce, dbs.py:236)")
     p.add_argument("--no-dbs", action="store_true")
     p.add_argument("--dbs-rounds", type=int, default=3, help="untimed measure->rebalance rounds before the timed region (both arms)")
+    p.add_argument("--dbs-steps", type=int, default=10, help="steps per measure->rebalance round (both arms)")
     p.add_argument("--dbs-model", default="auto", help="own arm: proportional | affine | auto (the framework default)")
     p.add_argument("--no-graphs", action="store_true")
     p.add_argument("--no-overlap", action="store_true")
@@ -172,8 +174,8 @@ def common_config(a, world, is_lm, throttle, rounds, W):
     """The part of `config` that must be IDENTICAL in both arms (what the benchmark is)."""
     cfg = {"model": MODEL_NAMES.get(a.model, a.model), "global_batch": a.batch, "parallelism": f"dp{world}",
            "dataset": f"{a.dataset}-shape synthetic", "optimizer": "SGD momentum 0.9 (inside the timed region)",
-           "dbs": not a.no_dbs, "dbs_rounds_before_timing": rounds, "warmup_steps_per_phase": W,
-           "untimed_steps_total": (rounds + 1) * W,
+           "dbs": not a.no_dbs, "dbs_rounds_before_timing": rounds, "dbs_steps_per_round": max(3, a.dbs_steps) if rounds else 0,
+           "warmup_steps_per_phase": W, "untimed_steps_total": rounds * max(3, a.dbs_steps) + W,
            "throttle": {"rank": world - 1, "ms_per_step": throttle} if throttle > 0 else None,
            "l2": "per-step working set (activations + gradients, > 1 GB) exceeds the 126 MB L2; no explicit flush"}
     if is_lm:
@@ -209,7 +211,8 @@ def run_ours(a) -> dict:
     clocks = ClockSampler(local)
 
     def measure(dtype: str) -> dict:
-        total_steps = (rounds + 1) * W + 2 * K + 8
+        S = max(3, a.dbs_steps)
+        total_steps = rounds * S + W + 2 * K + 8
         extra = {} if a.dbs_model == "auto" else {"dbs_model": a.dbs_model}
         cfg = DBSConfig(debug=False, world_size=world, batch_size=a.batch, model=a.model, dataset=a.dataset, synthetic=True,
                         train_samples=(a.batch * 36 * (total_steps + 4)) if lm else a.batch * total_steps, test_samples=256,
@@ -271,12 +274,12 @@ def run_ours(a) -> dict:
         # all-gather kernel, re-split (exactly what Trainer.run does once per epoch) -------------------------------------
         fractions, lb = tr.realloc.step()
         tr.flat.set_weights(tr.realloc.weights())
-        tr.injector.begin_epoch(0, W)
+        tr.injector.begin_epoch(0, max(W, S))
         lb0 = [int(x) for x in lb]
         for rnd in range(rounds):
             tr.comm.barrier()
             tr.reset_timers()
-            run_steps(make_shard(lb, W, 1 + rnd), W)
+            run_steps(make_shard(lb, S, 1 + rnd), S)
             compute_s, sync_s, _ = tr.epoch_times()      # the device-side accounting the trainer feeds to the DBS reallocator
             times = tr.comm.gather_times(compute_s)
             tr.realloc.observe(times)
@@ -534,7 +537,7 @@ def run_reference(a) -> dict:
 
     # same schedule as the own arm: R x (W steps -> exchange times -> get_size), W warm-up steps at the final split, K timed
     for rnd in range(rounds):
-        epoch(rnd, W, False, True)                          # get_size at the start of the epoch, as its run() does
+        epoch(rnd, max(3, a.dbs_steps), False, True)        # get_size at the start of the epoch, as its run() does
     if rounds:
         partition = dbs.get_size(nodes_time, partition)     # the split the next epoch of its run() would use
     epoch(rounds, W, False, False)

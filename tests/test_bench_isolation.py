@@ -45,9 +45,10 @@ def test_no_top_level_net_package():
 def test_both_arms_share_schedule_and_config():
     sys.path.insert(0, ROOT)
     import bench
-    a = bench.parse.__globals__["argparse"].Namespace(warmup=5, steps=20, dbs_rounds=2, no_dbs=False, model="densenet",
+    a = bench.parse.__globals__["argparse"].Namespace(warmup=5, steps=20, dbs_rounds=2, dbs_steps=10, no_dbs=False, model="densenet",
                                                         dataset="cifar10", batch=512)
     assert bench.schedule(a, 1) == (5, 20, 0)
     assert bench.schedule(a, 8) == (5, 20, 2)
     c = bench.common_config(a, 8, False, 3.0, 2, 5)
-    assert c["model"] == "densenet121" and c["global_batch"] == 512 and c["parallelism"] == "dp8" and c["untimed_steps_total"] == 15
+    assert c["model"] == "densenet121" and c["global_batch"] == 512 and c["parallelism"] == "dp8" and c["untimed_steps_total"] == 25
+    assert c["dbs_steps_per_round"] == 10 and bench.common_config(a, 1, False, 0.0, 0, 5)["untimed_steps_total"] == 5
