@@ -280,8 +280,12 @@ def run_ours(a) -> dict:
             tr.comm.barrier()
             tr.reset_timers()
             run_steps(make_shard(lb, S, 1 + rnd), S)
+            n_steady = tr.tracker.steps
             compute_s, sync_s, _ = tr.epoch_times()      # the device-side accounting the trainer feeds to the DBS reallocator
             times = tr.comm.gather_times(compute_s)
+            if rank == 0:
+                print(f"[bench] dbs round {rnd}: split {[int(x) for x in lb]} compute ms/step "
+                      f"{[round(float(t) * 1e3 / S, 3) for t in times]} (steady {n_steady}/{S})", file=sys.stderr, flush=True)
             tr.realloc.observe(times)
             fractions, lb = tr.realloc.step()
             tr.flat.set_weights(tr.realloc.weights())

@@ -360,7 +360,7 @@ DLB_API void* dlb_comm_create(int rank, int world, const unsigned long long* in_
 
 DLB_API void dlb_comm_destroy(void* ctx) { delete (CommCtx*)ctx; }
 DLB_API void dlb_comm_set_timeout(void* ctx, double seconds) { ((CommCtx*)ctx)->args.timeout_ns = (unsigned long long)(seconds * 1e9); }
-DLB_API int dlb_comm_flag_words() { return 3 * kMaxBlocks * kMaxWorld; }
+DLB_API int dlb_comm_flag_words() { return 4 * kMaxBlocks * kMaxWorld; }      // channels: 0 entry, 1 exit, 2 barrier / time table, 3 gate
 DLB_API int dlb_comm_max_blocks() { return kMaxBlocks; }
 
 // algo: 0 one-shot, 1 two-shot, 2 nvls.  wire: DLB_F32 / DLB_BF16.  offset/count in elements; count must be
@@ -411,6 +411,18 @@ DLB_API int dlb_weighted_allreduce_sgd(void* ctx, int algo, int wire, long long 
 DLB_API int dlb_time_allgather(void* ctx, const float* my_value, int table_offset_floats, void* stream) {
   CommCtx* c = (CommCtx*)ctx;
   time_allgather_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(c->args, my_value, nullptr, table_offset_floats);
+  return dlb_post_launch();
+}
+
+// Bucket gate: a ONE-WARP kernel that waits (flag channel 3) until every peer has reached the same bucket, launched on the
+// communication stream right before that bucket's allreduce.  The allreduce kernel itself is 32-64 CTAs x 512 threads; while
+// it spins at its entry barrier for a late peer it pins those SMs, and the 1-CTA-per-SM tensor-core kernels of the backward
+// pass (50-64 K registers each) cannot co-reside with it: the fast rank's backward stalls bucket by bucket on the straggler
+// (measured at 2 GPUs: "compute" 17.7 ms on the fast rank vs 18.4 on the straggler where 15.6 was expected), which also
+// hides the imbalance from the DBS time signal.  With the gate the wait costs one warp; the straggler wait is accounted here.
+DLB_API int dlb_comm_gate(void* ctx, void* stream) {
+  CommCtx* c = (CommCtx*)ctx;
+  barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(c->args, 3);
   return dlb_post_launch();
 }
 

@@ -91,6 +91,7 @@ def _declare(lib: ctypes.CDLL) -> None:
         "dlb_weighted_allreduce": (i32, [vp, i32, i32, i64, i64, i32, vp, vp, vp]),
         "dlb_time_allgather": (i32, [vp, vp, i32, vp]),
         "dlb_device_barrier": (i32, [vp, i32, vp]),
+        "dlb_comm_gate": (i32, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         if hasattr(lib, name):

@@ -17,6 +17,7 @@ parameter averaging (C2), barrier (C3), weighted gradient allreduce (C4), per-ra
 from __future__ import annotations
 
 import ctypes
+import os
 import time
 from typing import List, Optional, Sequence
 
@@ -117,6 +118,8 @@ class SymmComm(Comm):
         self.algo = algo
         self.blocks = blocks
         self.timeout_s = timeout_s
+        # one-warp gate kernel in front of every bucket's allreduce (csrc/comm.cu: dlb_comm_gate); DLB_COMM_GATE=0 disables
+        self.gate = os.environ.get("DLB_COMM_GATE", "1") == "1" and hasattr(self.lib, "dlb_comm_gate")
         self._ctx = None
         self._time_ctx = None
         self._counters = torch.zeros(4, dtype=torch.int64, device=self.device)   # [0]=wait_ns, [1]=err flag (int32 view)
@@ -197,6 +200,8 @@ class SymmComm(Comm):
         esize = 2 if self._wire == torch.bfloat16 else 4
         for (off, n) in buckets:
             algo = self.pick_algo(n * esize)
+            if self.gate and self.world > 1:
+                nat.check(self.lib.dlb_comm_gate(self._ctx, st), "comm_gate")
             rc = self.lib.dlb_weighted_allreduce(self._ctx, ALGO_CODES[algo], wire, off, n, self.pick_blocks(n * esize, algo),
                                                  nat.ptr(weights_dev), None, st)
             nat.check(rc, "weighted_allreduce")
@@ -210,6 +215,8 @@ class SymmComm(Comm):
         esize = 2 if self._wire == torch.bfloat16 else 4
         for (off, n) in buckets:
             algo = self.pick_algo(n * esize)
+            if self.gate and self.world > 1:
+                nat.check(self.lib.dlb_comm_gate(self._ctx, st), "comm_gate")
             rc = self.lib.dlb_weighted_allreduce_sgd(self._ctx, ALGO_CODES[algo], wire, off, n, self.pick_blocks(n * esize, algo),
                                                      None, sgd["master"], sgd["mom"], sgd["shadow"], sgd["lr"], sgd["zero_in"],
                                                      sgd["momentum"], sgd["weight_decay"], None, st)
