@@ -15,6 +15,7 @@ class-conditional colour blobs + noise, so a model can actually learn it.
 """
 from __future__ import annotations
 
+import time
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -128,6 +129,7 @@ class BatchStager:
         self.device = torch.device(device)
         self.cuda = self.device.type == "cuda"
         self.bytes_per_step = 0
+        self.blocked_s = 0.0          # host time spent waiting for a slot (back-pressure: the device is the bottleneck)
         if self.cuda:
             h, w, c = ds.shape
             self._host_img = [torch.empty(max_batch, h, w, c, dtype=torch.uint8).pin_memory() for _ in range(slots)]
@@ -146,7 +148,9 @@ class BatchStager:
             return self.ds.images.index_select(0, idx), self.ds.labels.index_select(0, idx)
         s = self._slot
         self._slot = (s + 1) % self.slots
+        t0 = time.perf_counter()
         self._consumed[s].synchronize()           # previous user of this slot has finished
+        self.blocked_s += time.perf_counter() - t0
         torch.index_select(self.ds.images, 0, idx, out=self._host_img[s][:b])
         torch.index_select(self.ds.labels, 0, idx, out=self._host_lab[s][:b])
         with torch.cuda.stream(self._stream):
