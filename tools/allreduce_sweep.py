@@ -26,6 +26,7 @@ dist.init_process_group("nccl", device_id=torch.device(dev), timeout=datetime.ti
 max_bytes = int(os.environ.get("SWEEP_MAX_BYTES", str(1 << 30)))
 n_max = max_bytes // 4
 comm = SymmComm(dev, timeout_s=20.0)
+comm.gate = False            # time the collective kernels alone (the one-warp bucket gate is a training-loop device)
 gin, gout = comm.alloc_grad_buffers(n_max, torch.float32, dev)
 gin.normal_()
 w = torch.full((world,), 1.0 / world, device=dev)
