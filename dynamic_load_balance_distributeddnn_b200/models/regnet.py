@@ -6,7 +6,6 @@ average pool, linear.  SE squeeze width derives from the block *input* width (``
 RegNetY-400MF: 5 714 362 params / 303 tensors.
 """
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .layers import Conv2d, GroupNormAct, Linear
 from .. import ops

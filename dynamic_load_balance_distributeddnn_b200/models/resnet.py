@@ -7,7 +7,6 @@ reference so checkpoints interchange (ResNet-50: 23 520 842 params / 161 tensors
 42 512 970 / 314).
 """
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .layers import Conv2d, GroupNormAct, Linear
 from .. import ops

@@ -1,6 +1,5 @@
 """Numerics of the hand-written sm_100a kernels against plain PyTorch fp32 references (run on the B200
 box: ``gpurun -- python -m pytest tests -m gpu``)."""
-import ctypes
 import math
 
 import os
