@@ -123,3 +123,28 @@ label="graph_1" graph[style="dashed"];
     roots, leaves, (path_nodes, path_kernels), acyclic = gn.critical_path(nodes, edges)
     assert (roots, leaves, path_nodes, path_kernels, acyclic) == (1, 2, 4, 3, True)
     assert gn.main([str(dot)]) == 0
+
+
+def test_trace_overlap_tool(tmp_path):
+    """tools/trace_overlap.py on a synthetic Kineto trace: per-stream totals, nccl detection, overlap of the collective with
+    compute on other streams."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ev = []
+    # compute stream 7: two kernels [0, 100) and [150, 250);  comm stream 9: allreduce [50, 200) -> 50 + 50 of 150 us overlapped
+    ev.append({"cat": "kernel", "name": "void gemm_tc_kernel<float>(int)", "ts": 0, "dur": 100, "args": {"stream": 7}})
+    ev.append({"cat": "kernel", "name": "void gn_fwd_apply_kernel<float>(int)", "ts": 150, "dur": 100, "args": {"stream": 7}})
+    ev.append({"cat": "kernel", "name": "void weighted_allreduce_kernel<float, 2, 8>(CommArgs)", "ts": 50, "dur": 150, "args": {"stream": 9}})
+    ev.append({"cat": "cpu_op", "name": "aten::add", "ts": 0, "dur": 5})
+    p = tmp_path / "t.trace.json"
+    p.write_text(json.dumps({"traceEvents": ev}))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "trace_overlap.py"), str(p)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "3 kernel events on 2 streams" in out.stdout
+    assert "nccl kernels in trace: 0" in out.stdout
+    assert "1 launches" in out.stdout and "66.7% of it concurrent" in out.stdout
+    ev.append({"cat": "kernel", "name": "ncclDevKernel_AllReduce_Sum_f32_RING_LL(x)", "ts": 300, "dur": 10, "args": {"stream": 11}})
+    p.write_text(json.dumps(ev))                                     # bare-list flavour of the format
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "trace_overlap.py"), str(p)], capture_output=True, text=True)
+    assert "nccl kernels in trace: 1" in out.stdout
