@@ -11,7 +11,7 @@ when N > 1 so the DBS rebalancer has something to do.
 BOTH arms run the same schedule (W = max(5, --warmup) steps per phase):
 
     N = 1 (or --no-dbs):  W warm-up steps                                   -> K timed steps
-    N > 1 with DBS:       R x [S steps -> exchange compute times -> re-split]  (R = --dbs-rounds, default 3; S = --dbs-steps,
+    N > 1 with DBS:       R x [S steps -> exchange compute times -> re-split]  (R = --dbs-rounds, default 4; S = --dbs-steps,
                           default 10: the first steps at a new local batch are capture / warm-up and not part of the signal)
                           -> W warm-up steps at the final split              -> K timed steps at that split
 
@@ -64,7 +64,7 @@ def parse():
                         "'sleep' is absorbed by the asynchronous engine and would not straggle at all.  The reference arm "
                         "always uses its own injector's mechanism (a host sleep between backward and allreduce, dbs.py:236)")
     p.add_argument("--no-dbs", action="store_true")
-    p.add_argument("--dbs-rounds", type=int, default=3, help="untimed measure->rebalance rounds before the timed region (both arms)")
+    p.add_argument("--dbs-rounds", type=int, default=4, help="untimed measure->rebalance rounds before the timed region (both arms)")
     p.add_argument("--dbs-steps", type=int, default=10, help="steps per measure->rebalance round (both arms)")
     p.add_argument("--dbs-model", default="auto", help="own arm: proportional | affine | auto (the framework default)")
     p.add_argument("--no-graphs", action="store_true")
