@@ -5,7 +5,7 @@ mkdir -p gpurun_out; O=gpurun_out/r2_01; mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/gpu.txt
 echo "== tf32 gemm tests"; timeout 600 python -m pytest tests/test_gpu_gemm_tf32.py -q 2>&1 | tail -15 | tee $O/pytest_tf32.txt
 echo "== gpu tests";       timeout 900 python -m pytest tests -m gpu -q --deselect tests/test_gpu_gemm_tf32.py 2>&1 | tail -8 | tee $O/pytest_gpu.txt
-echo "== experimental";    DLB_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_experimental.py -x -q 2>&1 | tail -8 | tee $O/pytest_exp.txt
+echo "== experimental";    timeout 300 python -m pytest tests/test_gpu_dgrad_gn.py -x -q 2>&1 | tail -8 | tee $O/pytest_exp.txt
 echo "== microbench";      timeout 300 python tools/bench_dgrad_gn.py 2>&1 | tail -10 | tee $O/bench_dgrad_gn.txt
 echo "== bench reference"; timeout 600 python bench.py --impl reference --steps 20 --warmup 5 2> $O/ref.err | tee $O/ref.json | cut -c1-300
 echo "== bench ours";      timeout 300 python bench.py --steps 20 --warmup 5 2> $O/ours.err | tee $O/ours.json | cut -c1-300

@@ -2,7 +2,7 @@
 # Round 2, GPU call 5 (1 GPU, short): validate stem rewrite + staged GN backward before the 8-GPU call.
 mkdir -p gpurun_out; O=gpurun_out/r2_05; mkdir -p $O
 echo "== tests"; timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_gradpath.py tests/test_gpu_gemm_tf32.py -q -x 2>&1 | tee $O/pytest.txt | tail -5
-echo "== experimental"; DLB_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_experimental.py -q 2>&1 | tail -4 | tee $O/pytest_exp.txt
+echo "== experimental"; timeout 300 python -m pytest tests/test_gpu_dgrad_gn.py -q 2>&1 | tail -4 | tee $O/pytest_exp.txt
 b() { tag=$1; shift; timeout 400 python bench.py --steps 20 --warmup 5 "$@" 2> $O/$tag.err | tee $O/$tag.json | python -c "
 import json,sys
 d=json.loads(sys.stdin.readline()); a=d.get('alt') or {}
