@@ -93,3 +93,29 @@ def test_partitioner_segments_cover_one_permutation():
             seen += list(p.use(r).indices)
         used += p.steps * 32
     assert len(seen) == len(set(seen)) == 3 * 5 * 32
+
+
+def test_real_dataset_files_are_used_when_present(tmp_path):
+    """A pre-populated torchvision layout (here: FashionMNIST raw idx files, which the reference's `-ds mnist` reads) is
+    loaded instead of the synthetic stand-in; `--synthetic false` without files fails loudly."""
+    import struct
+    pytest.importorskip("torchvision")
+    from dynamic_load_balance_distributeddnn_b200.data import vision
+    raw = tmp_path / "FashionMNIST" / "raw"
+    raw.mkdir(parents=True)
+    rng = np.random.RandomState(0)
+
+    def write(prefix, n):
+        img = rng.randint(0, 256, size=(n, 28, 28), dtype=np.uint8)
+        lab = rng.randint(0, 10, size=(n,), dtype=np.uint8)
+        (raw / f"{prefix}-images-idx3-ubyte").write_bytes(struct.pack(">IIII", 0x00000803, n, 28, 28) + img.tobytes())
+        (raw / f"{prefix}-labels-idx1-ubyte").write_bytes(struct.pack(">II", 0x00000801, n) + lab.tobytes())
+        return img, lab
+    img, lab = write("train", 48)
+    write("t10k", 16)
+    ds = vision.load_image_dataset("mnist", True, root=str(tmp_path), synthetic=False)
+    assert not ds.synthetic and tuple(ds.images.shape) == (48, 28, 28, 1) and ds.images.dtype == torch.uint8
+    assert np.array_equal(ds.images[..., 0].numpy(), img) and np.array_equal(ds.labels.numpy(), lab.astype(np.int64))
+    assert len(vision.load_image_dataset("mnist", False, root=str(tmp_path), synthetic=None).labels) == 16
+    with pytest.raises(FileNotFoundError):
+        vision.load_image_dataset("cifar10", True, root=str(tmp_path / "nothing"), synthetic=False)
